@@ -1,0 +1,215 @@
+"""ctypes bindings for the two CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+`Oracle`  -> oracle/liborc.so          (restatement, oracle/dwt_oracle.c)
+`Ref`     -> oracle/_ref/libdwt_ref.so (the unmodified reference compiled by oracle/Makefile)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Nothing under libdwt_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORC_SO = os.path.join(HERE, "liborc.so")
+REF_SO = os.path.join(HERE, "_ref", "libdwt_ref.so")
+
+_DT = {"s": np.float32, "d": np.float64, "i": np.int32}
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE], stdout=subprocess.DEVNULL)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """The restatement.  Images are numpy arrays indexed [y, x]; strides come from the array."""
+
+    def __init__(self):
+        if not os.path.exists(ORC_SO):
+            build()
+        self.lib = L = C.CDLL(ORC_SO)
+        i64, ci, vp = C.c_int64, C.c_int, C.c_void_p
+        for name in ("cdf97_s", "cdf97_d", "cdf53_i"):
+            getattr(L, f"orc_{name}_2f").argtypes = [vp, i64, i64, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
+            getattr(L, f"orc_{name}_2i").argtypes = [vp, i64, i64, ci, ci, ci, ci, ci, ci, ci]
+        L.orc_fill_s.argtypes = [vp, i64, i64, ci, ci, ci, ci, ci]
+        L.orc_fill_d.argtypes = [vp, i64, i64, ci, ci, ci, ci]
+        L.orc_fill_i.argtypes = [vp, i64, i64, ci, ci, ci, ci, ci]
+        L.orc_volume_fill_s.argtypes = [vp, i64, i64, i64, ci, ci, ci]
+        L.orc_cdf97_3f_s.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, ci, ci]
+        L.orc_cdf97_3i_s.argtypes = [vp, i64, i64, i64, ci, ci, ci]
+        L.orc_ceil_log2.argtypes = [ci]
+        L.orc_ceil_log2.restype = ci
+        L.orc_get_max_threads.restype = ci
+
+    name = "port"
+
+    @staticmethod
+    def _fn(wavelet, t):
+        return {"97s": "cdf97_s", "97d": "cdf97_d", "53i": "cdf53_i"}[f"{wavelet}{t}"]
+
+    def fwd2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        """In place on `img` ([oy, ox] outer array); returns achieved J."""
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        j = C.c_int(j_max)
+        getattr(self.lib, f"orc_{self._fn(wavelet, t)}_2f")(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one, zero_padding)
+        return j.value
+
+    def inv2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        getattr(self.lib, f"orc_{self._fn(wavelet, t)}_2i")(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
+
+    def fill(self, img, t, rand=0, type_=0, wrap32=1):
+        ny, nx = img.shape
+        if t == "s":
+            self.lib.orc_fill_s(_ptr(img), img.strides[0], img.strides[1], nx, ny, rand, type_, wrap32)
+        elif t == "d":
+            self.lib.orc_fill_d(_ptr(img), img.strides[0], img.strides[1], nx, ny, rand, wrap32)
+        else:
+            self.lib.orc_fill_i(_ptr(img), img.strides[0], img.strides[1], nx, ny, rand, type_, wrap32)
+        return img
+
+    def volume_fill(self, vol):
+        nz, ny, nx = vol.shape
+        self.lib.orc_volume_fill_s(_ptr(vol), vol.strides[2], vol.strides[1], vol.strides[0], nx, ny, nz)
+        return vol
+
+    def fwd3(self, src, dst):
+        nz, ny, nx = src.shape
+        self.lib.orc_cdf97_3f_s(_ptr(src), src.strides[2], src.strides[1], src.strides[0],
+                                _ptr(dst), dst.strides[2], dst.strides[1], dst.strides[0], nx, ny, nz)
+
+    def inv3(self, vol):
+        nz, ny, nx = vol.shape
+        self.lib.orc_cdf97_3i_s(_ptr(vol), vol.strides[2], vol.strides[1], vol.strides[0], nx, ny, nz)
+
+    def ceil_log2(self, x):
+        return self.lib.orc_ceil_log2(x)
+
+    def threads(self):
+        return self.lib.orc_get_max_threads()
+
+    def set_threads(self, n):
+        self.lib.orc_set_threads(n)
+
+
+class _Volume(C.Structure):  # src/volume.h:14-24
+    _fields_ = [("size_x", C.c_int), ("size_y", C.c_int), ("size_z", C.c_int),
+                ("stride_x", C.c_size_t), ("stride_y", C.c_size_t), ("stride_z", C.c_size_t),
+                ("data", C.c_void_p)]
+
+
+class Ref:
+    """The compiled reference, through its own prototypes (src/libdwt.h:526-992): int byte strides."""
+
+    name = "reference"
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        self.lib = L = C.CDLL(REF_SO)
+        ci, vp = C.c_int, C.c_void_p
+        for n in ("dwt_cdf97_2f_s", "dwt_cdf97_2f_d", "dwt_cdf53_2f_i"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
+        for n in ("dwt_cdf97_2i_s", "dwt_cdf97_2i_d", "dwt_cdf53_2i_i"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
+        for n in ("dwt_util_test_image_fill_s", "dwt_util_test_image_fill_d", "dwt_util_test_image_fill_i"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci]
+        for n in ("dwt_util_test_image_fill2_s", "dwt_util_test_image_fill2_i"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci]
+        L.dwt_util_set_num_threads.argtypes = [ci]
+        L.dwt_util_get_num_threads.restype = ci
+        L.dwt_util_set_accel.argtypes = [ci]
+        L.dwt_util_set_num_workers.argtypes = [ci]
+        L.dwt_util_get_opt_stride.argtypes = [ci]
+        L.dwt_util_get_opt_stride.restype = ci
+        VP = C.POINTER(_Volume)
+        L.volume_fill_s.argtypes = [VP]
+        L.cdf97_3f_op_sep_horizontal_s.argtypes = [VP, VP]
+        L.cdf97_3f_ip_sep_horizontal_s.argtypes = [VP]
+        L.cdf97_3i_ip_sep_horizontal_s.argtypes = [VP]
+        L.dwt_util_init()
+
+    @staticmethod
+    def _fn(wavelet, t, d):
+        return {"97s": "dwt_cdf97_2%s_s", "97d": "dwt_cdf97_2%s_d", "53i": "dwt_cdf53_2%s_i"}[f"{wavelet}{t}"] % d
+
+    @staticmethod
+    def _check(img):
+        oy, _ = img.shape
+        assert abs(img.strides[0]) * oy < 2 ** 31, "reference addresses images with int (src/inline.h:188)"
+
+    def fwd2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        self._check(img)
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        j = C.c_int(j_max)
+        getattr(self.lib, self._fn(wavelet, t, "f"))(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one, zero_padding)
+        return j.value
+
+    def inv2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        self._check(img)
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        getattr(self.lib, self._fn(wavelet, t, "i"))(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
+
+    def fill(self, img, t, rand=0, type_=0, wrap32=1):
+        self._check(img)
+        ny, nx = img.shape
+        if t == "d":
+            assert type_ == 0
+            self.lib.dwt_util_test_image_fill_d(_ptr(img), img.strides[0], img.strides[1], nx, ny, rand)
+        else:
+            getattr(self.lib, f"dwt_util_test_image_fill2_{t}")(
+                _ptr(img), img.strides[0], img.strides[1], nx, ny, rand, type_)
+        return img
+
+    @staticmethod
+    def _vol(a):
+        nz, ny, nx = a.shape
+        return _Volume(nx, ny, nz, a.strides[2], a.strides[1], a.strides[0], a.ctypes.data)
+
+    def volume_fill(self, vol):
+        v = self._vol(vol)
+        self.lib.volume_fill_s(C.byref(v))
+        return vol
+
+    def fwd3(self, src, dst):
+        s, d = self._vol(src), self._vol(dst)
+        self.lib.cdf97_3f_op_sep_horizontal_s(C.byref(s), C.byref(d))
+
+    def inv3(self, vol):
+        v = self._vol(vol)
+        self.lib.cdf97_3i_ip_sep_horizontal_s(C.byref(v))
+
+    def threads(self):
+        return self.lib.dwt_util_get_num_threads()
+
+    def set_threads(self, n):
+        self.lib.dwt_util_set_num_threads(n)
+
+    def opt_stride(self, nbytes):
+        return self.lib.dwt_util_get_opt_stride(nbytes)
+
+
+def strided_image(shape, t, row_bytes=None):
+    """A [oy, ox] view with an arbitrary (possibly unaligned, e.g. prime) row stride in bytes."""
+    dt = np.dtype(_DT[t])
+    oy, ox = shape
+    row_bytes = row_bytes or ox * dt.itemsize
+    raw = np.zeros(row_bytes * oy + 64, dtype=np.uint8)
+    return np.ndarray(shape=(oy, ox), dtype=dt, buffer=raw, strides=(row_bytes, dt.itemsize))
