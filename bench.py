@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+Metric: "CDF 9/7 + 5/3 fwd+inv Gpixel/s & % HBM roofline, 8192^2 j=max".
+One STEP = the hot path over one batch of synthetic input: M (default 4) independent 8192x8192 images per
+sample type, each transformed forward (all M) and then inverse (all M), full depth J=13, for CDF 9/7
+float32 and for CDF 5/3 int32 -- the reference's own perf protocol (M images, all forward then all
+inverse, src/libdwt.c:21391) with 4*M transforms of 64 Mpixel per step.  `value` is the number of pixels
+transformed (W*H per transform) per second, data resident in HBM; every image is 256 MiB (> 126 MB L2)
+and M of them are cycled, so no transform finds its input in L2.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): every rank runs the same batch on its own GPU (independent frames
+shard with no collective -> "weak" scaling); value = pixels of all ranks / max-over-ranks device time.
+`--impl reference` times the reference's own CPU code (oracle/_ref/libdwt_ref.so, OpenMP on all host
+cores; the oracle port if the compiled reference is absent) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 8192
+J = 13
+PIX = W * H
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(w, h, j, es):
+    """every level reads its LL input once and writes its four subbands once."""
+    return 2 * es * sum(-(-w // (1 << l)) * -(-h // (1 << l)) for l in range(j))
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ======================================================================================================
+# CPU arm: the reference's own implementation on the host cores
+# ======================================================================================================
+def cpu_impl():
+    from oracle.orc import Oracle, Ref
+    if Ref.available():
+        r = Ref()
+        return r, "reference"
+    return Oracle(), "port"
+
+
+def cpu_time_step(impl, threads, reps=1):
+    """One bounded sample: ONE 8192^2 image per type, forward + inverse (4 transforms = 1/M of a step)."""
+    impl.set_threads(threads)
+    secs = {}
+    for (w, t, dt) in (("97", "s", np.float32), ("53", "i", np.int32)):
+        img = np.zeros((H, W), dtype=dt)
+        impl.fill(img, t)
+        best_f = best_i = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            j = impl.fwd2(img, w, t)
+            t1 = time.perf_counter()
+            impl.inv2(img, w, t, j_max=j)
+            t2 = time.perf_counter()
+            best_f, best_i = min(best_f, t1 - t0), min(best_i, t2 - t1)
+        secs[w + t + "_fwd"] = best_f
+        secs[w + t + "_inv"] = best_i
+    return secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    impl, kind = cpu_impl()
+    threads = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_time_step(impl, threads)
+    tot = 0.0
+    last = None
+    for _ in range(args.steps):
+        last = cpu_time_step(impl, threads)
+        tot += sum(last.values())
+    ms = tot / args.steps * 1e3
+    value = 4 * PIX / (ms * 1e-3) / 1e9
+    sample = "1 image of 8192x8192 per type (float32 9/7 + int32 5/3), forward+inverse, J=13 = 4 transforms per step"
+    line = {
+        "impl": "reference", "metric": "cdf97_f32+cdf53_i32 fwd+inv throughput, 8192x8192 j=max", "value": value,
+        "unit": "Gpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": "8192x8192 full-depth (J=13) 2-D DWT, CDF 9/7 float32 + CDF 5/3 int32, forward+inverse",
+                   "sample": sample, "pattern": "dwt_util_test_image_fill_{s,i}"},
+        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": threads, "kind": kind, "sample": sample,
+                         "seconds": last},
+        "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ======================================================================================================
+# GPU arm
+# ======================================================================================================
+def run_ours(args):
+    import torch
+    import libdwt_b200 as d
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libdwt_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = d.lib()
+    L.init(local)
+    M = args.images
+
+    kinds = [(d.CDF97_F32, "97s", 4), (d.CDF53_I32, "53i", 4)]
+    imgs = {}
+    for k, name, es in kinds:
+        imgs[name] = [d.DeviceImage(k, W, H) for _ in range(M)]
+        for m, im in enumerate(imgs[name]):
+            im.fill(m % 6, 0, 0)
+    L.check(L.c.dwtb200_sync())
+
+    launches = [0]
+
+    def step(count=False):
+        for _, name, _ in kinds:
+            for im in imgs[name]:
+                j = im.fwd2()
+                assert j == J
+                if count:
+                    launches[0] += im.last_launches
+            for im in imgs[name]:
+                im.inv2(J)
+                if count:
+                    launches[0] += im.last_launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.check(L.c.dwtb200_timer_start())
+    for s in range(args.steps):
+        step(count=(s == 0))
+    ms_total = L.c.dwtb200_timer_stop_ms()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = ms_total / args.steps
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    pix_step = 4 * M * PIX
+    value = world * pix_step / (ms * 1e-3) / 1e9
+
+    # ---- per-transform breakdown (device events, same cycling of M images) ----
+    breakdown = {}
+    for _, name, es in kinds:
+        for direction in ("fwd", "inv"):
+            # put the images into the right state first
+            if direction == "inv":
+                pass   # images hold coefficients after the forward loop below
+            L.check(L.c.dwtb200_sync())
+            reps = 3
+            tot = 0.0
+            for _ in range(reps):
+                if direction == "fwd":
+                    L.check(L.c.dwtb200_timer_start())
+                    for im in imgs[name]:
+                        im.fwd2()
+                    tot += L.c.dwtb200_timer_stop_ms()
+                    for im in imgs[name]:
+                        im.inv2(J)
+                else:
+                    for im in imgs[name]:
+                        im.fwd2()
+                    L.check(L.c.dwtb200_sync())
+                    L.check(L.c.dwtb200_timer_start())
+                    for im in imgs[name]:
+                        im.inv2(J)
+                    tot += L.c.dwtb200_timer_stop_ms()
+            t = tot / (reps * M) * 1e-3
+            b = algorithmic_bytes(W, H, J, es)
+            breakdown[f"{name}_{direction}"] = {"us": t * 1e6, "gpixel_s": PIX / t / 1e9, "gb_s": b / t / 1e9}
+
+    # ---- roofline of the dominant kernel: level 0 of the forward 9/7 float transform ----
+    # (one launch = one j_max=1 transform: reads the 8192^2 plane once, writes the four subbands once)
+    peak, peak_src = peaks()
+    ims = imgs["97s"]
+    for im in ims:
+        im.fwd2(1); im.inv2(1)
+    L.check(L.c.dwtb200_sync())
+    reps = 5
+    L.check(L.c.dwtb200_timer_start())
+    for _ in range(reps):
+        for im in ims:
+            im.fwd2(1)
+    t_fwd0 = L.c.dwtb200_timer_stop_ms() / (reps * M) * 1e-3
+    assert ims[0].last_launches == 1
+    bytes0 = 2 * 4 * PIX
+    for im in ims:            # leave the images in a defined state (coefficients of an odd number of j=1 passes are fine)
+        im.fill(0, 0, 0)
+    roof = {"bound": "hbm", "kernel": "k_fwd_level<W97F,8> (level 0 of dwt_cdf97_2f_s, 8192x8192)", "achieved": bytes0 / t_fwd0 / 1e9,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes0 / t_fwd0 / 1e9 / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": bytes0, "us_per_launch": t_fwd0 * 1e6,
+            "whole_pyramid_frac": {k: v["gb_s"] / peak for k, v in breakdown.items()}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get("k_fwd_level_w97f_level0_bytes")
+        except Exception:
+            pass
+
+    # ---- end to end through the reference-facing host call: pinned host image, H2D + transform + D2H ----
+    e2e = None
+    if rank == 0 or world > 1:
+        nbytes = W * H * 4
+        hp = {}
+        for k, name, es in kinds:
+            p = L.c.dwtb200_host_alloc(nbytes)
+            if not p:
+                raise SystemExit(L.c.dwtb200_last_error().decode())
+            arr = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * nbytes).from_address(p)).view(np.float32 if name == "97s" else np.int32).reshape(H, W)
+            hp[name] = (p, arr)
+        # fill host inputs by downloading the device pattern once
+        for k, name, es in kinds:
+            imgs[name][0].fill(0, 0, 0)
+            imgs[name][0].download(hp[name][1])
+        fwd = {"97s": d.dwt_cdf97_2f_s, "53i": d.dwt_cdf53_2f_i}
+        inv = {"97s": d.dwt_cdf97_2i_s, "53i": d.dwt_cdf53_2i_i}
+
+        def e2e_step():
+            for _, name, _ in kinds:
+                p, arr = hp[name]
+                jj = [-1]
+                fwd[name](p, W * 4, 4, W, H, W, H, jj, 0, 0)
+                inv[name](p, W * 4, 4, W, H, W, H, jj[0], 0, 0)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+        e2e = {"value": world * 4 * PIX / te / 1e9, "unit": "Gpixel/s", "h2d_bytes_per_step": 4 * nbytes, "d2h_bytes_per_step": 4 * nbytes,
+               "ms_per_step": te * 1e3, "what": "dwt_cdf97_2f_s+2i_s and dwt_cdf53_2f_i+2i_i on a pinned host 8192x8192 image (4 transforms)"}
+        for name in hp:
+            L.c.dwtb200_host_free(hp[name][0])
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        impl, kind = cpu_impl()
+        threads = os.cpu_count() or 1
+        secs = cpu_time_step(impl, threads)
+        cpu = {"value": 4 * PIX / sum(secs.values()) / 1e9, "unit": "Gpixel/s", "cores": threads, "kind": kind,
+               "sample": "1 image of 8192x8192 per type, forward+inverse, J=13 (4 transforms = 1/M of a GPU step)", "seconds": secs}
+
+    if rank == 0:
+        line = {
+            "metric": "cdf97_f32+cdf53_i32 fwd+inv throughput, 8192x8192 j=max", "value": value, "unit": "Gpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+            "config": {"workload": "8192x8192 full-depth (J=13) 2-D DWT, CDF 9/7 float32 + CDF 5/3 int32, forward+inverse",
+                       "images_per_type_per_step": M, "transforms_per_step": 4 * M, "pixels_per_step": pix_step,
+                       "pattern": "dwt_util_test_image_fill_{s,i}, rand = image index % 6",
+                       "l2": "each image is 256 MiB (> 126 MB L2) and M images are cycled: inputs larger than L2",
+                       "sharding": "independent frames per GPU, no collective"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
+            "breakdown": breakdown,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=4, help="independent 8192^2 images per sample type per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 3 if args.impl == "reference" else 20
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+/*
+ * dwtb200.h -- C ABI of libdwtb200.so, the B200 (sm_100a) implementation of libdwt's separable
+ * lifting DWT hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the libdwt
+ * source tree, /root/reference/).  The reference-named symbols (dwt_cdf97_2f_s, ...) are exported
+ * by the thin C99 layer libdwt_b200/csrc/libdwt_compat.c, which calls the functions below; see
+ * INTEGRATION.md for how the unmodified examples link against it.
+ *
+ * Conventions
+ *   - "kind" selects wavelet and sample type (DWTB200_CDF97_F32, ...).
+ *   - host strides are in BYTES exactly as in libdwt: stride_x between rows, stride_y between
+ *     columns (src/libdwt.h:528-529); they may be unaligned (dwt_util_get_opt_stride returns primes).
+ *   - functions return 0 on success, a negative DWTB200_E* code otherwise; dwtb200_last_error()
+ *     describes the failure.  There is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with DWTB200_ENODEV.
+ *   - not re-entrant, like the reference (process-global state, src/libdwt.c:478-756).
+ */
+#ifndef DWTB200_H
+#define DWTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    DWTB200_CDF97_F32 = 0, /* dwt_cdf97_2f_s / dwt_cdf97_2i_s   src/libdwt.c:12776, 17040 */
+    DWTB200_CDF97_F64 = 1, /* dwt_cdf97_2f_d / dwt_cdf97_2i_d   src/libdwt.c:12451, 16884 */
+    DWTB200_CDF53_I32 = 2  /* dwt_cdf53_2f_i / dwt_cdf53_2i_i   src/libdwt.c:16304, 18142 */
+};
+
+enum {
+    DWTB200_OK = 0,
+    DWTB200_ENODEV = -1,  /* no CUDA device / driver */
+    DWTB200_ECUDA = -2,   /* a CUDA call failed */
+    DWTB200_EINVAL = -3,  /* bad argument */
+    DWTB200_ENOMEM = -4
+};
+
+/* ---- lifecycle: dwt_util_init / dwt_util_finish / dwt_util_abort (src/libdwt.c:19158, 19186, 19200) ---- */
+int dwtb200_init(int device);      /* device < 0: LOCAL_RANK env or 0.  Idempotent. */
+void dwtb200_finish(void);
+const char *dwtb200_last_error(void);
+int dwtb200_device_count(void);
+int dwtb200_device(void);          /* device in use, -1 before init */
+
+/* ---- pinned host images: dwt_util_alloc_image / dwt_util_free_image (src/libdwt.c:1437, 1482) ---- */
+void *dwtb200_host_alloc(size_t bytes);   /* page-locked, 16-byte aligned like memalign(16, ...) */
+void dwtb200_host_free(void *ptr);
+
+/* ---- level arithmetic shared with the reference drivers (src/libdwt.c:12807-12810, inline.h:443-460) ---- */
+int dwtb200_ceil_log2(int x);
+int dwtb200_clamp_j(int j_max, int size_o_big_x, int size_o_big_y, int decompose_one);
+
+/* ---- reference-semantics transforms on HOST memory, in place, synchronous ----------------------
+ * dwt_cdf97_2f_s/_d, dwt_cdf53_2f_i (src/libdwt.h:526-537, 562-573, 686-697) and the inverses
+ * (src/libdwt.h:831-842, 867-878, 981-992): same argument meaning, Mallat layout, *j_max_ptr
+ * clamped to ceil_log2(decompose_one ? max : min) and left holding the achieved depth.
+ * H2D copy, transform, D2H copy; results are visible in ptr on return. */
+int dwtb200_fwd2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
+                      int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+int dwtb200_inv2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
+                      int size_i_big_x, int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+
+/* ---- device-resident images (what the roofline numbers are measured on) ---------------------------
+ * A dwtb200_image is `frames` independent planes of size_o_big_x x size_o_big_y samples living in
+ * HBM (two ping-pong planes plus LL scratch).  fwd2/inv2 have the semantics above, leave the result
+ * on the device and return without synchronising (work is ordered on the library stream). */
+typedef struct dwtb200_image dwtb200_image;
+dwtb200_image *dwtb200_image_create(int kind, int size_o_big_x, int size_o_big_y, int frames);
+void dwtb200_image_destroy(dwtb200_image *img);
+/* host <-> device, one frame; arbitrary byte strides (dwt_util_memcpy_stride_*, src/system.c:90-180) */
+int dwtb200_image_upload(dwtb200_image *img, int frame, const void *host, int64_t stride_x, int64_t stride_y);
+int dwtb200_image_download(dwtb200_image *img, int frame, void *host, int64_t stride_x, int64_t stride_y);
+/* dwt_util_test_image_fill{,2}_{s,d,i} on the device (src/libdwt.c:1247-1385); frame k uses
+ * rand = (rand_mod > 0 ? k % rand_mod : rand), cf. volume_fill_s (src/volume.c:41) */
+int dwtb200_image_fill(dwtb200_image *img, int rand, int type, int rand_mod);
+int dwtb200_image_fwd2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one,
+                       int zero_padding);
+int dwtb200_image_inv2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, int j_max, int decompose_one,
+                       int zero_padding);
+/* current plane of frame 0 (device pointer) and its pitch in bytes; frames are frame_bytes apart */
+void *dwtb200_image_devptr(dwtb200_image *img, size_t *pitch_bytes, size_t *frame_bytes);
+/* bit-exact comparison of the current planes of two images on the device: number of differing samples */
+int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b);
+/* max |a-b| over the current planes (float/double kinds), cf. dwt_util_compare_s (src/libdwt.c:1593) */
+double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b);
+int dwtb200_image_copy(dwtb200_image *dst, dwtb200_image *src);
+/* kernels launched by the last fwd2/inv2 on this image (graph nodes) */
+int dwtb200_image_last_launches(dwtb200_image *img);
+/* 0: streaming + tail kernels (dense planes), 1: generic pass kernels; which one the last call used */
+int dwtb200_image_last_path(dwtb200_image *img);
+/* testing hook: force the generic pass kernels (1) or let the library choose (0) */
+void dwtb200_force_generic(int on);
+/* tuning hook: output rows per strip of the streaming kernels (0 = heuristic) */
+void dwtb200_set_strip_rows(int rows);
+
+/* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t
+ * src/volume.h:14-24: stride_x = pixel, stride_y = row, stride_z = slice, all in bytes) -------- */
+int dwtb200_fwd3_host(const void *src, size_t s_stride_x, size_t s_stride_y, size_t s_stride_z, void *dst,
+                      size_t d_stride_x, size_t d_stride_y, size_t d_stride_z, int size_x, int size_y, int size_z);
+int dwtb200_inv3_host(void *vol, size_t stride_x, size_t stride_y, size_t stride_z, int size_x, int size_y,
+                      int size_z);
+typedef struct dwtb200_volume dwtb200_volume;
+dwtb200_volume *dwtb200_volume_create(int size_x, int size_y, int size_z);
+void dwtb200_volume_destroy(dwtb200_volume *v);
+int dwtb200_volume_upload(dwtb200_volume *v, const void *host, size_t stride_x, size_t stride_y, size_t stride_z);
+int dwtb200_volume_download(dwtb200_volume *v, void *host, size_t stride_x, size_t stride_y, size_t stride_z);
+int dwtb200_volume_fill(dwtb200_volume *v);   /* volume_fill_s, src/volume.c:41 */
+int dwtb200_volume_fwd3(dwtb200_volume *v);   /* cdf97_3f_ip_sep_horizontal_s */
+int dwtb200_volume_inv3(dwtb200_volume *v);   /* cdf97_3i_ip_sep_horizontal_s */
+
+/* ---- device-event timing: replaces dwt_util_get_clock around transforms (src/libdwt.c:18701) ---- */
+int dwtb200_sync(void);                 /* wait for the library stream */
+int dwtb200_timer_start(void);          /* record an event on the library stream */
+double dwtb200_timer_stop_ms(void);     /* record, synchronise, elapsed milliseconds (< 0 on error) */
+void *dwtb200_stream(void);             /* cudaStream_t of the library stream */
+/* write `bytes` of device scratch so the 126 MB L2 holds none of the previous step's data */
+int dwtb200_flush_l2(size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWTB200_H */

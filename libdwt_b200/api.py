@@ -1,0 +1,263 @@
+"""ctypes bindings of libdwtb200.so (include/dwtb200.h) and the reference-named host API.
+
+The module-level functions dwt_cdf97_2f_s ... dwt_cdf53_2i_i take exactly the arguments of the
+reference prototypes (/root/reference/src/libdwt.h:526-992): a host pointer (here: anything exposing
+the buffer protocol / a numpy array / an int address), byte strides, outer and inner sizes, j_max
+(by reference for the forward transforms: a ctypes.c_int or a one-element list), decompose_one and
+zero_padding.  They are synchronous and in place on host memory like the reference.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libdwtb200.so")
+
+CDF97_F32, CDF97_F64, CDF53_I32 = 0, 1, 2
+_DT = {CDF97_F32: np.float32, CDF97_F64: np.float64, CDF53_I32: np.int32}
+_KIND = {("97", "s"): CDF97_F32, ("97", "d"): CDF97_F64, ("53", "i"): CDF53_I32}
+
+# every symbol include/dwtb200.h declares: (name, restype, argtypes)
+_i, _i64, _vp, _sz, _dbl = C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_double
+_ip = C.POINTER(C.c_int)
+SYMBOLS = [
+    ("dwtb200_init", _i, [_i]), ("dwtb200_finish", None, []), ("dwtb200_last_error", C.c_char_p, []),
+    ("dwtb200_device_count", _i, []), ("dwtb200_device", _i, []),
+    ("dwtb200_host_alloc", _vp, [_sz]), ("dwtb200_host_free", None, [_vp]),
+    ("dwtb200_ceil_log2", _i, [_i]), ("dwtb200_clamp_j", _i, [_i, _i, _i, _i]),
+    ("dwtb200_fwd2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
+    ("dwtb200_inv2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
+    ("dwtb200_image_upload", _i, [_vp, _i, _vp, _i64, _i64]), ("dwtb200_image_download", _i, [_vp, _i, _vp, _i64, _i64]),
+    ("dwtb200_image_fill", _i, [_vp, _i, _i, _i]),
+    ("dwtb200_image_fwd2", _i, [_vp, _i, _i, _ip, _i, _i]), ("dwtb200_image_inv2", _i, [_vp, _i, _i, _i, _i, _i]),
+    ("dwtb200_image_devptr", _vp, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
+    ("dwtb200_image_copy", _i, [_vp, _vp]),
+    ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
+    ("dwtb200_force_generic", None, [_i]), ("dwtb200_set_strip_rows", None, [_i]),
+    ("dwtb200_fwd3_host", _i, [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _sz, _i, _i, _i]),
+    ("dwtb200_inv3_host", _i, [_vp, _sz, _sz, _sz, _i, _i, _i]),
+    ("dwtb200_volume_create", _vp, [_i, _i, _i]), ("dwtb200_volume_destroy", None, [_vp]),
+    ("dwtb200_volume_upload", _i, [_vp, _vp, _sz, _sz, _sz]), ("dwtb200_volume_download", _i, [_vp, _vp, _sz, _sz, _sz]),
+    ("dwtb200_volume_fill", _i, [_vp]), ("dwtb200_volume_fwd3", _i, [_vp]), ("dwtb200_volume_inv3", _i, [_vp]),
+    ("dwtb200_sync", _i, []), ("dwtb200_timer_start", _i, []), ("dwtb200_timer_stop_ms", _dbl, []),
+    ("dwtb200_stream", _vp, []), ("dwtb200_flush_l2", _i, [_sz]),
+]
+
+
+class DwtError(RuntimeError):
+    pass
+
+
+class Library:
+    """The loaded C ABI.  Loading needs libcudart but no GPU; compute calls need a B200."""
+
+    def __init__(self, path=SO):
+        if not os.path.exists(path):
+            raise DwtError(f"{path} is missing: run `make` (or __graft_entry__.build()); there is no fallback path")
+        self.c = C.CDLL(path)
+        for name, res, args in SYMBOLS:
+            f = getattr(self.c, name)
+            f.restype, f.argtypes = res, args
+
+    def check(self, rc):
+        if rc != 0:
+            raise DwtError(f"libdwtb200 error {rc}: {self.c.dwtb200_last_error().decode()}")
+
+    def init(self, device=-1):
+        self.check(self.c.dwtb200_init(device))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = Library()
+    return _lib
+
+
+def kind_of(wavelet, t):
+    return _KIND[(str(wavelet), t)]
+
+
+def _addr(ptr):
+    if isinstance(ptr, np.ndarray):
+        return ptr.ctypes.data
+    if isinstance(ptr, int):
+        return ptr
+    if isinstance(ptr, C.c_void_p):
+        return ptr.value
+    return C.addressof(C.c_char.from_buffer(ptr))
+
+
+# ---- the reference's prototypes (src/libdwt.h:526-537, 562-573, 686-697, 831-842, 867-878, 981-992) ----
+def _fwd(kind, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max_ptr,
+         decompose_one, zero_padding):
+    j = C.c_int(j_max_ptr[0] if isinstance(j_max_ptr, list) else j_max_ptr.value)
+    L = lib()
+    L.check(L.c.dwtb200_fwd2_host(kind, _addr(ptr), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                  size_i_big_y, C.byref(j), decompose_one, zero_padding))
+    if isinstance(j_max_ptr, list):
+        j_max_ptr[0] = j.value
+    else:
+        j_max_ptr.value = j.value
+
+
+def _inv(kind, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max,
+         decompose_one, zero_padding):
+    L = lib()
+    L.check(L.c.dwtb200_inv2_host(kind, _addr(ptr), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                  size_i_big_y, j_max, decompose_one, zero_padding))
+
+
+def dwt_cdf97_2f_s(*a): _fwd(CDF97_F32, *a)
+def dwt_cdf97_2i_s(*a): _inv(CDF97_F32, *a)
+def dwt_cdf97_2f_d(*a): _fwd(CDF97_F64, *a)
+def dwt_cdf97_2i_d(*a): _inv(CDF97_F64, *a)
+def dwt_cdf53_2f_i(*a): _fwd(CDF53_I32, *a)
+def dwt_cdf53_2i_i(*a): _inv(CDF53_I32, *a)
+
+
+# ---- numpy conveniences with the calling shape of oracle/orc.py (images are [y, x] arrays) ----
+def fwd2(img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+    oy, ox = img.shape
+    iy, ix = inner if inner is not None else (oy, ox)
+    j = [j_max]
+    _fwd(kind_of(wavelet, t), img, img.strides[0], img.strides[1], ox, oy, ix, iy, j, decompose_one, zero_padding)
+    return j[0]
+
+
+def inv2(img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+    oy, ox = img.shape
+    iy, ix = inner if inner is not None else (oy, ox)
+    _inv(kind_of(wavelet, t), img, img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
+
+
+def fwd3(src, dst):
+    """cdf97_3f_op_sep_horizontal_s (src/volume-dwt.c:727): arrays are [z, y, x] float32."""
+    nz, ny, nx = src.shape
+    L = lib()
+    L.check(L.c.dwtb200_fwd3_host(src.ctypes.data, src.strides[2], src.strides[1], src.strides[0],
+                                  dst.ctypes.data, dst.strides[2], dst.strides[1], dst.strides[0], nx, ny, nz))
+
+
+def inv3(vol):
+    """cdf97_3i_ip_sep_horizontal_s (src/volume-dwt.c:1115)."""
+    nz, ny, nx = vol.shape
+    L = lib()
+    L.check(L.c.dwtb200_inv3_host(vol.ctypes.data, vol.strides[2], vol.strides[1], vol.strides[0], nx, ny, nz))
+
+
+class DeviceImage:
+    """`frames` device-resident planes (dwtb200_image): what the roofline numbers are measured on."""
+
+    def __init__(self, kind, size_x, size_y, frames=1):
+        self.L = lib()
+        self.L.init()
+        self.kind, self.size_x, self.size_y, self.frames = kind, size_x, size_y, frames
+        self.h = self.L.c.dwtb200_image_create(kind, size_x, size_y, frames)
+        if not self.h:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.c.dwtb200_image_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def dtype(self):
+        return _DT[self.kind]
+
+    def upload(self, arr, frame=0):
+        self.L.check(self.L.c.dwtb200_image_upload(self.h, frame, arr.ctypes.data, arr.strides[0], arr.strides[1]))
+
+    def download(self, arr=None, frame=0):
+        if arr is None:
+            arr = np.empty((self.size_y, self.size_x), dtype=self.dtype)
+        self.L.check(self.L.c.dwtb200_image_download(self.h, frame, arr.ctypes.data, arr.strides[0], arr.strides[1]))
+        return arr
+
+    def fill(self, rand=0, type_=0, rand_mod=0):
+        self.L.check(self.L.c.dwtb200_image_fill(self.h, rand, type_, rand_mod))
+
+    def fwd2(self, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        j = C.c_int(j_max)
+        self.L.check(self.L.c.dwtb200_image_fwd2(self.h, ix, iy, C.byref(j), decompose_one, zero_padding))
+        return j.value
+
+    def inv2(self, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        self.L.check(self.L.c.dwtb200_image_inv2(self.h, ix, iy, j_max, decompose_one, zero_padding))
+
+    def diff(self, other):
+        r = self.L.c.dwtb200_image_diff(self.h, other.h)
+        if r < 0:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+        return r
+
+    def maxabs(self, other):
+        r = self.L.c.dwtb200_image_maxabs(self.h, other.h)
+        if r < 0:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+        return r
+
+    def copy_from(self, other):
+        self.L.check(self.L.c.dwtb200_image_copy(self.h, other.h))
+
+    @property
+    def last_launches(self):
+        return self.L.c.dwtb200_image_last_launches(self.h)
+
+    @property
+    def last_path(self):
+        return self.L.c.dwtb200_image_last_path(self.h)
+
+
+class DeviceVolume:
+    def __init__(self, nx, ny, nz):
+        self.L = lib()
+        self.L.init()
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.h = self.L.c.dwtb200_volume_create(nx, ny, nz)
+        if not self.h:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.c.dwtb200_volume_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, a):
+        self.L.check(self.L.c.dwtb200_volume_upload(self.h, a.ctypes.data, a.strides[2], a.strides[1], a.strides[0]))
+
+    def download(self, a=None):
+        if a is None:
+            a = np.empty((self.nz, self.ny, self.nx), dtype=np.float32)
+        self.L.check(self.L.c.dwtb200_volume_download(self.h, a.ctypes.data, a.strides[2], a.strides[1], a.strides[0]))
+        return a
+
+    def fill(self):
+        self.L.check(self.L.c.dwtb200_volume_fill(self.h))
+
+    def fwd3(self):
+        self.L.check(self.L.c.dwtb200_volume_fwd3(self.h))
+
+    def inv3(self):
+        self.L.check(self.L.c.dwtb200_volume_inv3(self.h))

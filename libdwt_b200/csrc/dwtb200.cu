@@ -1,0 +1,909 @@
+// dwtb200.cu -- host side of libdwtb200.so: the C ABI of include/dwtb200.h.
+//
+// This file is the B200 replacement of the reference's level drivers
+//   dwt_cdf97_2f_s / 2i_s   /root/reference/src/libdwt.c:12776, 17040
+//   dwt_cdf97_2f_d / 2i_d   src/libdwt.c:12451, 16884
+//   dwt_cdf53_2f_i / 2i_i   src/libdwt.c:16304, 18142
+//   cdf97_3f_{op,ip}_sep_horizontal_s / cdf97_3i_ip_sep_horizontal_s   src/volume-dwt.c:727, 677, 1115
+// and of the image allocation / transfer around them (dwt_util_alloc_image src/libdwt.c:1437,
+// dwt_util_memcpy_stride_* src/system.c:90-180).
+//
+// Data layout in HBM (one dwtb200_image = `frames` independent planes):
+//   plane[0], plane[1]   two full planes, pitch = width rounded up to 32 elements (128 B / 256 B rows);
+//                        a transform reads plane[cur] and writes plane[cur^1] (Mallat layout forbids
+//                        in-place tiling: level-j H subbands land where other tiles still read), then cur flips
+//   ll[0], ll[1]         LL ping-pong scratch: level j writes its LL band to ll[j&1] (S/4 and S/16 samples)
+// Each level of the dense path is ONE kernel launch (kernels_stream.cu) reading its LL input once and
+// writing its four subbands once; the coarse levels whose LL band fits one CTA's shared memory are ONE
+// launch in total (kernels_tail.cu).  The launch sequence of a call is captured into a CUDA graph and
+// cached per image and argument set.  Sparse layouts (outer != inner) and degenerate shapes take the
+// generic pass kernels (kernels_generic.cu), two launches per level.
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
+// returns DWTB200_ENODEV.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/dwtb200.h"
+#include "kernels.h"
+
+using namespace dwtb200;
+
+// ---- global context (the reference keeps process-global state too, src/libdwt.c:478-756) ----
+namespace {
+struct Ctx {
+    int dev = -1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    char err[512] = "";
+    int force_generic = 0;
+    int strip_rows = 0;
+    int use_graph = 1;
+    int launches = 0;   // counts kernel launches issued by the drivers
+    void *flush = nullptr;
+    size_t flush_bytes = 0;
+    void *stage = nullptr;   // device staging for strided repack
+    size_t stage_bytes = 0;
+    int sm_count = 148;
+} g;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g.err, sizeof g.err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(DWTB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cdiv_pow2(int v, int j) { return (int)(((int64_t)v + ((int64_t)1 << j) - 1) >> j); }
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+inline size_t esize(int kind) { return kind == DWTB200_CDF97_F64 ? 8 : 4; }
+inline bool guard(int kind) { return kind == DWTB200_CDF97_F32; }            // src/libdwt.c:12837
+inline bool inv_cols_first(int kind) { return kind == DWTB200_CDF53_I32; }   // src/libdwt.c:18178
+
+int ensure_stage(size_t bytes)
+{
+    if (bytes <= g.stage_bytes) return 0;
+    if (g.stage) cudaFree(g.stage);
+    g.stage = nullptr;
+    g.stage_bytes = 0;
+    CK(cudaMalloc(&g.stage, bytes));
+    g.stage_bytes = bytes;
+    return 0;
+}
+}  // namespace
+
+struct dwtb200_image {
+    int kind = 0, ox = 0, oy = 0, frames = 0;
+    size_t es = 4;
+    int64_t pitch = 0, frame = 0;   // elements
+    void *plane[2] = {nullptr, nullptr};
+    int cur = 0;
+    void *ll[2] = {nullptr, nullptr};
+    int last_launches = 0, last_path = 0;
+    typedef std::tuple<int, int, int, int, int, int, int, int, int> Key;
+    struct Entry {
+        cudaGraphExec_t exec;
+        int launches, path, flips;
+    };
+    std::map<Key, Entry> graphs;
+};
+
+struct dwtb200_volume {
+    int nx = 0, ny = 0, nz = 0;
+    int64_t pitch = 0, slice = 0;   // elements
+    float *buf[2] = {nullptr, nullptr};
+    int cur = 0;
+};
+
+extern "C" {
+
+// =====================================================================================================
+// lifecycle
+// =====================================================================================================
+int dwtb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dwtb200_init(int device)
+{
+    if (g.dev >= 0) return DWTB200_OK;
+    const int n = dwtb200_device_count();
+    if (n <= 0) return fail(DWTB200_ENODEV, "no CUDA device (libdwtb200 has no CPU fallback)");
+    if (device < 0) {
+        const char *e = getenv("DWT_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        device = e ? atoi(e) % n : 0;
+    }
+    if (device >= n) return fail(DWTB200_EINVAL, "device %d out of range (%d devices)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(DWTB200_ENODEV, "device %d is sm_%d%d; libdwtb200 is built for sm_100a only", device, prop.major, prop.minor);
+    g.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g.e0));
+    CK(cudaEventCreate(&g.e1));
+    const char *ng = getenv("DWTB200_NO_GRAPH");
+    g.use_graph = !(ng && atoi(ng));
+    g.dev = device;
+    return DWTB200_OK;
+}
+
+void dwtb200_finish(void)
+{
+    if (g.dev < 0) return;
+    cudaStreamSynchronize(g.st);
+    if (g.flush) cudaFree(g.flush);
+    if (g.stage) cudaFree(g.stage);
+    g.flush = g.stage = nullptr;
+    g.flush_bytes = g.stage_bytes = 0;
+    cudaEventDestroy(g.e0);
+    cudaEventDestroy(g.e1);
+    cudaStreamDestroy(g.st);
+    g.st = nullptr;
+    g.dev = -1;
+}
+
+const char *dwtb200_last_error(void) { return g.err; }
+int dwtb200_device(void) { return g.dev; }
+
+#define NEED_DEV()                                       \
+    do {                                                 \
+        if (g.dev < 0) {                                 \
+            const int r_ = dwtb200_init(-1);             \
+            if (r_) return r_;                           \
+        }                                                \
+    } while (0)
+
+void *dwtb200_host_alloc(size_t bytes)
+{
+    if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fail(DWTB200_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void dwtb200_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int dwtb200_ceil_log2(int x)
+{
+    int j = 0;
+    while (((int64_t)1 << j) < x) j++;
+    return j;
+}
+int dwtb200_clamp_j(int j_max, int ox, int oy, int decompose_one)
+{
+    const int omin = ox < oy ? ox : oy, omax = ox < oy ? oy : ox;
+    const int lim = dwtb200_ceil_log2(decompose_one ? omax : omin);
+    return (j_max < 0 || j_max > lim) ? lim : j_max;
+}
+
+void dwtb200_force_generic(int on) { g.force_generic = on; }
+void dwtb200_set_strip_rows(int rows) { g.strip_rows = rows; }
+
+// =====================================================================================================
+// images
+// =====================================================================================================
+dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
+{
+    if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
+    if (kind < 0 || kind > 2 || ox < 1 || oy < 1 || frames < 1) {
+        fail(DWTB200_EINVAL, "image_create: bad arguments");
+        return nullptr;
+    }
+    dwtb200_image *im = new dwtb200_image;
+    im->kind = kind;
+    im->ox = ox;
+    im->oy = oy;
+    im->frames = frames;
+    im->es = esize(kind);
+    im->pitch = align_up(ox, 32);
+    im->frame = im->pitch * oy;
+    const size_t plane_bytes = (size_t)im->frame * frames * im->es;
+    const size_t ll0 = (size_t)align_up(cdiv_pow2(ox, 1), 32) * cdiv_pow2(oy, 1) * frames * im->es;
+    const size_t ll1 = (size_t)align_up(cdiv_pow2(ox, 2), 32) * cdiv_pow2(oy, 2) * frames * im->es;
+    bool ok = cudaMalloc(&im->plane[0], plane_bytes) == cudaSuccess && cudaMalloc(&im->plane[1], plane_bytes) == cudaSuccess &&
+              cudaMalloc(&im->ll[0], ll0) == cudaSuccess && cudaMalloc(&im->ll[1], ll1) == cudaSuccess;
+    if (ok) ok = cudaMemsetAsync(im->plane[0], 0, plane_bytes, g.st) == cudaSuccess &&
+                 cudaMemsetAsync(im->plane[1], 0, plane_bytes, g.st) == cudaSuccess;
+    if (!ok) {
+        fail(DWTB200_ENOMEM, "image_create(%d x %d x %d): %s", ox, oy, frames, cudaGetErrorString(cudaGetLastError()));
+        dwtb200_image_destroy(im);
+        return nullptr;
+    }
+    return im;
+}
+
+void dwtb200_image_destroy(dwtb200_image *im)
+{
+    if (!im) return;
+    if (g.st) cudaStreamSynchronize(g.st);
+    for (auto &kv : im->graphs) cudaGraphExecDestroy(kv.second.exec);
+    for (int i = 0; i < 2; i++) {
+        if (im->plane[i]) cudaFree(im->plane[i]);
+        if (im->ll[i]) cudaFree(im->ll[i]);
+    }
+    delete im;
+}
+
+static inline char *frame_ptr(dwtb200_image *im, int which, int frame)
+{
+    return (char *)im->plane[which] + (size_t)frame * im->frame * im->es;
+}
+
+// host span touched by an (ox x oy) image with byte strides sx (rows) / sy (columns)
+static inline size_t host_span(int ox, int oy, int64_t sx, int64_t sy, size_t es)
+{
+    return (size_t)((int64_t)(oy - 1) * sx + (int64_t)(ox - 1) * sy) + es;
+}
+
+int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t sx, int64_t sy)
+{
+    NEED_DEV();
+    if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_upload: bad arguments");
+    char *d = frame_ptr(im, im->cur, frame);
+    if (sy == (int64_t)im->es && sx >= (int64_t)(im->ox * im->es)) {
+        CK(cudaMemcpy2DAsync(d, im->pitch * im->es, host, (size_t)sx, im->ox * im->es, im->oy, cudaMemcpyHostToDevice, g.st));
+    } else {
+        const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
+        int r = ensure_stage(span);
+        if (r) return r;
+        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyHostToDevice, g.st));
+        launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 1, g.st);
+        CK(cudaGetLastError());
+    }
+    return DWTB200_OK;
+}
+
+int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx, int64_t sy)
+{
+    NEED_DEV();
+    if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_download: bad arguments");
+    char *d = frame_ptr(im, im->cur, frame);
+    if (sy == (int64_t)im->es && sx >= (int64_t)(im->ox * im->es)) {
+        CK(cudaMemcpy2DAsync(host, (size_t)sx, d, im->pitch * im->es, im->ox * im->es, im->oy, cudaMemcpyDeviceToHost, g.st));
+    } else {
+        // bytes of the caller's buffer that do not belong to this image (other channels, padding) must
+        // survive: stage the whole span, scatter the samples into it, copy the span back
+        const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
+        int r = ensure_stage(span);
+        if (r) return r;
+        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyHostToDevice, g.st));
+        launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 0, g.st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host, g.stage, span, cudaMemcpyDeviceToHost, g.st));
+    }
+    CK(cudaStreamSynchronize(g.st));
+    return DWTB200_OK;
+}
+
+int dwtb200_image_fill(dwtb200_image *im, int rnd, int type, int rand_mod)
+{
+    NEED_DEV();
+    if (!im) return fail(DWTB200_EINVAL, "image_fill: null image");
+    launch_fill(im->kind, im->plane[im->cur], im->pitch, im->frame, im->ox, im->oy, rnd, type, rand_mod, im->frames, g.st);
+    CK(cudaGetLastError());
+    return DWTB200_OK;
+}
+
+void *dwtb200_image_devptr(dwtb200_image *im, size_t *pitch_bytes, size_t *frame_bytes)
+{
+    if (!im) return nullptr;
+    if (pitch_bytes) *pitch_bytes = (size_t)im->pitch * im->es;
+    if (frame_bytes) *frame_bytes = (size_t)im->frame * im->es;
+    return im->plane[im->cur];
+}
+
+int dwtb200_image_copy(dwtb200_image *dst, dwtb200_image *src)
+{
+    NEED_DEV();
+    if (!dst || !src || dst->kind != src->kind || dst->ox != src->ox || dst->oy != src->oy || dst->frames != src->frames)
+        return fail(DWTB200_EINVAL, "image_copy: shape mismatch");
+    CK(cudaMemcpyAsync(dst->plane[dst->cur], src->plane[src->cur], (size_t)src->frame * src->frames * src->es,
+                       cudaMemcpyDeviceToDevice, g.st));
+    return DWTB200_OK;
+}
+
+int dwtb200_image_last_launches(dwtb200_image *im) { return im ? im->last_launches : 0; }
+int dwtb200_image_last_path(dwtb200_image *im) { return im ? im->last_path : 0; }
+
+// ---- level plans -------------------------------------------------------------------------------
+namespace {
+
+struct Band {   // where an LL band lives
+    void *p;
+    int64_t pitch, frame;
+};
+
+// first level handled by the tail kernel (== J when there is none); -1 when the dense kernels cannot
+// take this pyramid (a level that is neither streamable nor small enough for the tail)
+int dense_tail_level(const dwtb200_image *im, int J)
+{
+    const int tmax = tail_max_elems(im->kind);
+    for (int j = 0; j < J; j++) {
+        const int w = cdiv_pow2(im->ox, j), h = cdiv_pow2(im->oy, j);
+        if ((int64_t)w * h <= tmax) return j;
+        if (w < 2 || h < 2) return -1;
+    }
+    return J;
+}
+
+Band ll_band(const dwtb200_image *im, int j)   // LL_j = output of level j, (w_{j+1} x h_{j+1})
+{
+    const int w = cdiv_pow2(im->ox, j + 1), h = cdiv_pow2(im->oy, j + 1);
+    Band b;
+    b.p = im->ll[j & 1];
+    b.pitch = align_up(w, 32);
+    b.frame = b.pitch * h;
+    return b;
+}
+
+void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p)
+{
+    const int W = cdiv_pow2(im->ox, j), H = cdiv_pow2(im->oy, j);
+    p.W = W;
+    p.H = H;
+    p.nLx = (W + 1) >> 1;
+    p.nHx = W >> 1;
+    p.nLy = (H + 1) >> 1;
+    p.nHy = H >> 1;
+    const int outw = stream_out_width(im->kind);
+    p.ncg = (W + outw - 1) / outw;
+    const int units = inverse ? (H >> 1) + 1 : p.nLy;   // row pairs to emit
+    int pps;
+    if (g.strip_rows > 0) {
+        pps = g.strip_rows / 2 > 0 ? g.strip_rows / 2 : 1;
+    } else {
+        // enough warps for ~16 per SM, but strips of at least 8 and at most 64 pairs (warm-up rows are
+        // re-read per strip: 3 pairs for 9/7 forward, 4 for inverse)
+        const int64_t want = (int64_t)g.sm_count * 16;
+        const int64_t per_col = (want + (int64_t)p.ncg * im->frames - 1) / ((int64_t)p.ncg * im->frames);
+        pps = (int)((units + per_col - 1) / per_col);
+        if (pps < 8) pps = 8;
+        if (pps > 64) pps = 64;
+    }
+    p.pps = pps;
+    p.nstrips = (units + pps - 1) / pps;
+    const int vec = im->es == 8 ? 2 : 4;
+    p.sub_aligned = (p.nLx % vec) == 0;
+}
+
+int run_fwd_dense(dwtb200_image *im, int J, int jt)
+{
+    char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
+    Band in = {src_plane, im->pitch, im->frame};
+    for (int j = 0; j < J; j++) {
+        if (j == jt) {
+            TailParams t;
+            t.src = in.p;
+            t.src_pitch = in.pitch;
+            t.src_frame = in.frame;
+            t.dst = dst_plane;
+            t.dst_pitch = im->pitch;
+            t.dst_frame = im->frame;
+            t.W0 = im->ox;
+            t.H0 = im->oy;
+            t.j0 = j;
+            t.j1 = J;
+            launch_fwd_tail(im->kind, t, im->frames, g.st);
+            g.launches++;
+            return 0;
+        }
+        LevelParams p;
+        memset(&p, 0, sizeof p);
+        level_geometry(im, j, false, p);
+        const Band out = (j == J - 1) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j);
+        p.src = in.p;
+        p.src_pitch = in.pitch;
+        p.src_frame = in.frame;
+        p.ll = out.p;
+        p.ll_pitch = out.pitch;
+        p.ll_frame = out.frame;
+        const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
+        p.hl = dst_plane + (size_t)odx * im->es;
+        p.lh = dst_plane + (size_t)ody * im->pitch * im->es;
+        p.hh = dst_plane + ((size_t)ody * im->pitch + odx) * im->es;
+        p.sub_pitch = im->pitch;
+        p.sub_frame = im->frame;
+        launch_fwd_level(im->kind, p, im->frames, g.st);
+        g.launches++;
+        in = out;
+    }
+    return 0;
+}
+
+int run_inv_dense(dwtb200_image *im, int J, int jt)
+{
+    char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
+    int jtop = J;   // levels jtop-1 .. 0 go through the streaming kernel
+    if (jt < J) {
+        const Band out = (jt == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, jt - 1);
+        TailParams t;
+        t.src = src_plane;
+        t.src_pitch = im->pitch;
+        t.src_frame = im->frame;
+        t.dst = out.p;
+        t.dst_pitch = out.pitch;
+        t.dst_frame = out.frame;
+        t.W0 = im->ox;
+        t.H0 = im->oy;
+        t.j0 = jt;
+        t.j1 = J;
+        launch_inv_tail(im->kind, t, im->frames, g.st);
+        g.launches++;
+        jtop = jt;
+    }
+    for (int j = jtop - 1; j >= 0; j--) {
+        LevelParams p;
+        memset(&p, 0, sizeof p);
+        level_geometry(im, j, true, p);
+        const Band in = (j == J - 1) ? Band{src_plane, im->pitch, im->frame} : ll_band(im, j);
+        const Band out = (j == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j - 1);
+        p.ll = in.p;
+        p.ll_pitch = in.pitch;
+        p.ll_frame = in.frame;
+        const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
+        p.hl = src_plane + (size_t)odx * im->es;
+        p.lh = src_plane + (size_t)ody * im->pitch * im->es;
+        p.hh = src_plane + ((size_t)ody * im->pitch + odx) * im->es;
+        p.sub_pitch = im->pitch;
+        p.sub_frame = im->frame;
+        p.dst = out.p;
+        p.dst_pitch = out.pitch;
+        p.dst_frame = out.frame;
+        launch_inv_level(im->kind, p, im->frames, g.st);
+        g.launches++;
+    }
+    return 0;
+}
+
+// one generic pass A -> B over the level's outer region, then the second pass B -> A; a pass the
+// reference skips is replaced by nothing, and the result is copied back so that A is always complete
+void generic_level(dwtb200_image *im, bool inverse, bool first_along_x, bool do_first, bool do_second, int region_w,
+                   int region_h, int Nx, int Ny, int offx, int offy)
+{
+    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];
+    auto pass = [&](char *s, char *d, bool along_x) {
+        PassParams p;
+        p.src = s;
+        p.dst = d;
+        p.src_pitch = p.dst_pitch = im->pitch;
+        p.src_frame = p.dst_frame = im->frame;
+        p.region_w = region_w;
+        p.region_h = region_h;
+        p.along_x = along_x ? 1 : 0;
+        p.N = along_x ? Nx : Ny;
+        p.off_h = along_x ? offx : offy;
+        if (inverse) launch_pass_inv(im->kind, p, im->frames, g.st);
+        else launch_pass_fwd(im->kind, p, im->frames, g.st);
+        g.launches++;
+    };
+    auto copy_back = [&]() {
+        launch_copy2d((int)im->es, A, im->pitch, B, im->pitch, region_w, region_h, im->frame, im->frame, im->frames, g.st);
+        g.launches++;
+    };
+    if (do_first && do_second) {
+        pass(A, B, first_along_x);
+        pass(B, A, !first_along_x);
+    } else if (do_first) {
+        pass(A, B, first_along_x);
+        copy_back();
+    } else if (do_second) {
+        pass(A, B, !first_along_x);
+        copy_back();
+    }
+}
+
+void run_fwd_generic(dwtb200_image *im, int ix, int iy, int J, int zero_padding)
+{
+    const bool gd = guard(im->kind);
+    for (int j = 0; j < J; j++) {
+        const int osx = cdiv_pow2(im->ox, j), osy = cdiv_pow2(im->oy, j);
+        const int odx = cdiv_pow2(im->ox, j + 1), ody = cdiv_pow2(im->oy, j + 1);
+        const int isx = cdiv_pow2(ix, j), isy = cdiv_pow2(iy, j);
+        generic_level(im, false, true, !gd || osx > 1, !gd || osy > 1, osx, osy, isx, isy, odx, ody);
+        if (zero_padding) {   // src/libdwt.c:12896-12916
+            ZeroParams z;
+            z.buf = im->plane[im->cur];
+            z.pitch = im->pitch;
+            z.frame = im->frame;
+            z.region_w = osx;
+            z.region_h = osy;
+            z.x0a = (isx + 1) >> 1;
+            z.x0b = odx;
+            z.x1a = odx + (isx >> 1);
+            z.x1b = osx;
+            z.y0a = (isy + 1) >> 1;
+            z.y0b = ody;
+            z.y1a = ody + (isy >> 1);
+            z.y1b = osy;
+            launch_zero(im->kind, z, im->frames, g.st);
+            g.launches++;
+        }
+    }
+}
+
+void run_inv_generic(dwtb200_image *im, int ix, int iy, int J, int zero_padding)
+{
+    const bool gd = guard(im->kind), cf = inv_cols_first(im->kind);
+    for (int j = J; j > 0; j--) {
+        const int osx = cdiv_pow2(im->ox, j), osy = cdiv_pow2(im->oy, j);
+        const int odx = cdiv_pow2(im->ox, j - 1), ody = cdiv_pow2(im->oy, j - 1);
+        const int idx = cdiv_pow2(ix, j - 1), idy = cdiv_pow2(iy, j - 1);
+        if (cf) generic_level(im, true, false, true, true, odx, ody, idx, idy, osx, osy);
+        else generic_level(im, true, true, !gd || odx > 1, !gd || ody > 1, odx, ody, idx, idy, osx, osy);
+        if (zero_padding) {   // src/libdwt.c:17156-17176
+            ZeroParams z;
+            z.buf = im->plane[im->cur];
+            z.pitch = im->pitch;
+            z.frame = im->frame;
+            z.region_w = odx;
+            z.region_h = ody;
+            z.x0a = idx;
+            z.x0b = odx;
+            z.x1a = z.x1b = 0;
+            z.y0a = idy;
+            z.y0b = ody;
+            z.y1a = z.y1b = 0;
+            launch_zero(im->kind, z, im->frames, g.st);
+            g.launches++;
+        }
+    }
+}
+
+int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_padding)
+{
+    if (ix < 1 || iy < 1 || ix > im->ox || iy > im->oy) return fail(DWTB200_EINVAL, "inner size %d x %d outside outer %d x %d", ix, iy, im->ox, im->oy);
+    im->last_launches = 0;
+    if (J == 0) return DWTB200_OK;
+    const bool dense_shape = ix == im->ox && iy == im->oy && !g.force_generic;
+    const int jt = dense_shape ? dense_tail_level(im, J) : -1;
+    const bool dense = jt >= 0;
+
+    const dwtb200_image::Key key(inverse, ix, iy, J, zero_padding, im->cur, g.force_generic, g.strip_rows, 0);
+    auto it = g.use_graph ? im->graphs.find(key) : im->graphs.end();
+    if (it == im->graphs.end()) {
+        g.launches = 0;
+        cudaGraph_t graph = nullptr;
+        if (g.use_graph) CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
+        if (dense) {
+            if (inverse) run_inv_dense(im, J, jt);
+            else run_fwd_dense(im, J, jt);
+        } else {
+            if (inverse) run_inv_generic(im, ix, iy, J, zero_padding);
+            else run_fwd_generic(im, ix, iy, J, zero_padding);
+        }
+        const cudaError_t le = cudaGetLastError();
+        if (g.use_graph) {
+            const cudaError_t ce = cudaStreamEndCapture(g.st, &graph);
+            if (le != cudaSuccess || ce != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                return fail(DWTB200_ECUDA, "launch/capture failed: %s / %s", cudaGetErrorString(le), cudaGetErrorString(ce));
+            }
+            dwtb200_image::Entry e;
+            e.launches = g.launches;
+            e.path = dense ? 0 : 1;
+            e.flips = dense ? 1 : 0;
+            const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(DWTB200_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+            it = im->graphs.emplace(key, e).first;
+        } else {
+            if (le != cudaSuccess) return fail(DWTB200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(le));
+            im->last_launches = g.launches;
+            im->last_path = dense ? 0 : 1;
+            if (dense) im->cur ^= 1;
+            return DWTB200_OK;
+        }
+    }
+    CK(cudaGraphLaunch(it->second.exec, g.st));
+    im->last_launches = it->second.launches;
+    im->last_path = it->second.path;
+    if (it->second.flips) im->cur ^= 1;
+    return DWTB200_OK;
+}
+}  // namespace
+
+int dwtb200_image_fwd2(dwtb200_image *im, int ix, int iy, int *j_max_ptr, int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!im || !j_max_ptr) return fail(DWTB200_EINVAL, "image_fwd2: null argument");
+    *j_max_ptr = dwtb200_clamp_j(*j_max_ptr, im->ox, im->oy, decompose_one);   // src/libdwt.c:12807-12810
+    return transform(im, false, ix, iy, *j_max_ptr, zero_padding);
+}
+
+int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!im) return fail(DWTB200_EINVAL, "image_inv2: null argument");
+    const int J = dwtb200_clamp_j(j_max, im->ox, im->oy, decompose_one);   // src/libdwt.c:17063-17066
+    return transform(im, true, ix, iy, J, zero_padding);
+}
+
+int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
+{
+    if (g.dev < 0 || !a || !b || a->kind != b->kind || a->ox != b->ox || a->oy != b->oy || a->frames != b->frames) {
+        fail(DWTB200_EINVAL, "image_diff: shape mismatch");
+        return -1;
+    }
+    unsigned long long *d = nullptr, h = 0;
+    if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
+    cudaMemsetAsync(d, 0, 16, g.st);
+    launch_compare((int)a->es, a->plane[a->cur], b->plane[b->cur], a->pitch, a->frame, a->ox, a->oy, a->frames,
+                   a->kind == DWTB200_CDF97_F64 ? 2 : a->kind == DWTB200_CDF97_F32 ? 1 : 0, d, g.st);
+    cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g.st);
+    const cudaError_t e = cudaStreamSynchronize(g.st);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        fail(DWTB200_ECUDA, "image_diff: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return (int64_t)h;
+}
+
+double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
+{
+    if (g.dev < 0 || !a || !b || a->kind != b->kind || a->ox != b->ox || a->oy != b->oy || a->frames != b->frames) {
+        fail(DWTB200_EINVAL, "image_maxabs: shape mismatch");
+        return -1.0;
+    }
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    if (cudaMalloc(&d, 16) != cudaSuccess) return -1.0;
+    cudaMemsetAsync(d, 0, 16, g.st);
+    launch_compare((int)a->es, a->plane[a->cur], b->plane[b->cur], a->pitch, a->frame, a->ox, a->oy, a->frames,
+                   a->kind == DWTB200_CDF97_F64 ? 2 : a->kind == DWTB200_CDF97_F32 ? 1 : 0, d, g.st);
+    cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, g.st);
+    const cudaError_t e = cudaStreamSynchronize(g.st);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        fail(DWTB200_ECUDA, "image_maxabs: %s", cudaGetErrorString(e));
+        return -1.0;
+    }
+    double r;
+    memcpy(&r, &h[1], 8);
+    return r;
+}
+
+// =====================================================================================================
+// host-memory entry points with the reference's semantics
+// =====================================================================================================
+namespace {
+dwtb200_image *g_host_img = nullptr;   // cached between calls of the same shape (the reference mallocs its temps per call)
+
+dwtb200_image *host_image(int kind, int ox, int oy)
+{
+    if (g_host_img && g_host_img->kind == kind && g_host_img->ox == ox && g_host_img->oy == oy) return g_host_img;
+    if (g_host_img) dwtb200_image_destroy(g_host_img);
+    g_host_img = dwtb200_image_create(kind, ox, oy, 1);
+    return g_host_img;
+}
+}  // namespace
+
+int dwtb200_fwd2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
+                      int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!ptr || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_host: null argument");
+    dwtb200_image *im = host_image(kind, ox, oy);
+    if (!im) return DWTB200_ENOMEM;
+    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
+    if (!r) r = dwtb200_image_fwd2(im, ix, iy, j_max_ptr, decompose_one, zero_padding);
+    if (!r) r = dwtb200_image_download(im, 0, ptr, sx, sy);
+    return r;
+}
+
+int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
+                      int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!ptr) return fail(DWTB200_EINVAL, "inv2_host: null argument");
+    dwtb200_image *im = host_image(kind, ox, oy);
+    if (!im) return DWTB200_ENOMEM;
+    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
+    if (!r) r = dwtb200_image_inv2(im, ix, iy, j_max, decompose_one, zero_padding);
+    if (!r) r = dwtb200_image_download(im, 0, ptr, sx, sy);
+    return r;
+}
+
+// =====================================================================================================
+// 3-D, one level, interleaved subbands
+// =====================================================================================================
+dwtb200_volume *dwtb200_volume_create(int nx, int ny, int nz)
+{
+    if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
+    if (nx < 1 || ny < 1 || nz < 1) {
+        fail(DWTB200_EINVAL, "volume_create: bad size");
+        return nullptr;
+    }
+    dwtb200_volume *v = new dwtb200_volume;
+    v->nx = nx;
+    v->ny = ny;
+    v->nz = nz;
+    v->pitch = align_up(nx, 32);
+    v->slice = v->pitch * ny;
+    const size_t bytes = (size_t)v->slice * nz * sizeof(float);
+    if (cudaMalloc(&v->buf[0], bytes) != cudaSuccess || cudaMalloc(&v->buf[1], bytes) != cudaSuccess) {
+        fail(DWTB200_ENOMEM, "volume_create(%d,%d,%d): %s", nx, ny, nz, cudaGetErrorString(cudaGetLastError()));
+        dwtb200_volume_destroy(v);
+        return nullptr;
+    }
+    return v;
+}
+void dwtb200_volume_destroy(dwtb200_volume *v)
+{
+    if (!v) return;
+    if (g.st) cudaStreamSynchronize(g.st);
+    for (int i = 0; i < 2; i++)
+        if (v->buf[i]) cudaFree(v->buf[i]);
+    delete v;
+}
+
+static int volume_xfer(dwtb200_volume *v, void *host, size_t sx, size_t sy, size_t sz, bool up)
+{
+    if (!v || !host) return fail(DWTB200_EINVAL, "volume transfer: null argument");
+    if (sx != sizeof(float)) return fail(DWTB200_EINVAL, "volume transfer: stride_x must be sizeof(float)");
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    // pitched pointers: host rows are sy bytes apart, slices sz bytes apart (sz must be a multiple of sy
+    // for cudaMemcpy3D; otherwise fall back to one 2-D copy per slice)
+    float *d = v->buf[v->cur];
+    if (sz % sy == 0) {
+        p.srcPtr = up ? make_cudaPitchedPtr(host, sy, v->nx, sz / sy) : make_cudaPitchedPtr(d, v->pitch * 4, v->nx, v->ny);
+        p.dstPtr = up ? make_cudaPitchedPtr(d, v->pitch * 4, v->nx, v->ny) : make_cudaPitchedPtr(host, sy, v->nx, sz / sy);
+        p.extent = make_cudaExtent((size_t)v->nx * 4, v->ny, v->nz);
+        p.kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CK(cudaMemcpy3DAsync(&p, g.st));
+    } else {
+        for (int z = 0; z < v->nz; z++) {
+            char *hp = (char *)host + (size_t)z * sz;
+            float *dp = d + (size_t)z * v->slice;
+            if (up) CK(cudaMemcpy2DAsync(dp, v->pitch * 4, hp, sy, (size_t)v->nx * 4, v->ny, cudaMemcpyHostToDevice, g.st));
+            else CK(cudaMemcpy2DAsync(hp, sy, dp, v->pitch * 4, (size_t)v->nx * 4, v->ny, cudaMemcpyDeviceToHost, g.st));
+        }
+    }
+    if (!up) CK(cudaStreamSynchronize(g.st));
+    return DWTB200_OK;
+}
+int dwtb200_volume_upload(dwtb200_volume *v, const void *host, size_t sx, size_t sy, size_t sz)
+{
+    NEED_DEV();
+    return volume_xfer(v, (void *)host, sx, sy, sz, true);
+}
+int dwtb200_volume_download(dwtb200_volume *v, void *host, size_t sx, size_t sy, size_t sz)
+{
+    NEED_DEV();
+    return volume_xfer(v, host, sx, sy, sz, false);
+}
+int dwtb200_volume_fill(dwtb200_volume *v)
+{
+    NEED_DEV();
+    if (!v) return fail(DWTB200_EINVAL, "volume_fill: null");
+    launch_volume_fill(v->buf[v->cur], v->pitch, v->slice, v->nx, v->ny, v->nz, g.st);
+    CK(cudaGetLastError());
+    return DWTB200_OK;
+}
+
+static int volume_axes(dwtb200_volume *v, int inverse)
+{
+    // x, then y, then z in both directions (src/volume-dwt.c:727-770, 1115-1150); each pass is out of
+    // place between the two buffers.  The reference's inverse skips an axis of size 1 (libdwt.c:17182).
+    for (int axis = 0; axis < 3; axis++) {
+        Axis3Params p;
+        p.src = v->buf[v->cur];
+        p.dst = v->buf[v->cur ^ 1];
+        const int64_t sx = 1, sy = v->pitch, sz = v->slice;
+        if (axis == 0) { p.n0 = v->ny; p.n1 = v->nz; p.N = v->nx; p.s_line0 = sy; p.s_line1 = sz; p.s_elem = sx; }
+        else if (axis == 1) { p.n0 = v->nx; p.n1 = v->nz; p.N = v->ny; p.s_line0 = sx; p.s_line1 = sz; p.s_elem = sy; }
+        else { p.n0 = v->nx; p.n1 = v->ny; p.N = v->nz; p.s_line0 = sx; p.s_line1 = sy; p.s_elem = sz; }
+        p.d_line0 = p.s_line0;
+        p.d_line1 = p.s_line1;
+        p.d_elem = p.s_elem;
+        launch_axis3(p, inverse, g.st);
+        v->cur ^= 1;
+    }
+    CK(cudaGetLastError());
+    return DWTB200_OK;
+}
+int dwtb200_volume_fwd3(dwtb200_volume *v)
+{
+    NEED_DEV();
+    if (!v) return fail(DWTB200_EINVAL, "volume_fwd3: null");
+    if (v->nx < 5 || v->ny < 5 || v->nz < 5) return fail(DWTB200_EINVAL, "volume_fwd3: every size must be >= 5 (src/dwt-simple.c:2172)");
+    return volume_axes(v, 0);
+}
+int dwtb200_volume_inv3(dwtb200_volume *v)
+{
+    NEED_DEV();
+    if (!v) return fail(DWTB200_EINVAL, "volume_inv3: null");
+    return volume_axes(v, 1);
+}
+
+int dwtb200_fwd3_host(const void *src, size_t ssx, size_t ssy, size_t ssz, void *dst, size_t dsx, size_t dsy, size_t dsz,
+                      int nx, int ny, int nz)
+{
+    NEED_DEV();
+    dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
+    if (!v) return DWTB200_ENOMEM;
+    int r = dwtb200_volume_upload(v, src, ssx, ssy, ssz);
+    if (!r) r = dwtb200_volume_fwd3(v);
+    if (!r) r = dwtb200_volume_download(v, dst, dsx, dsy, dsz);
+    dwtb200_volume_destroy(v);
+    return r;
+}
+int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny, int nz)
+{
+    NEED_DEV();
+    dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
+    if (!v) return DWTB200_ENOMEM;
+    int r = dwtb200_volume_upload(v, vol, sx, sy, sz);
+    if (!r) r = dwtb200_volume_inv3(v);
+    if (!r) r = dwtb200_volume_download(v, vol, sx, sy, sz);
+    dwtb200_volume_destroy(v);
+    return r;
+}
+
+// =====================================================================================================
+// timing
+// =====================================================================================================
+int dwtb200_sync(void)
+{
+    NEED_DEV();
+    CK(cudaStreamSynchronize(g.st));
+    return DWTB200_OK;
+}
+int dwtb200_timer_start(void)
+{
+    NEED_DEV();
+    CK(cudaEventRecord(g.e0, g.st));
+    return DWTB200_OK;
+}
+double dwtb200_timer_stop_ms(void)
+{
+    if (g.dev < 0) return -1.0;
+    if (cudaEventRecord(g.e1, g.st) != cudaSuccess || cudaEventSynchronize(g.e1) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, g.e0, g.e1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+void *dwtb200_stream(void) { return (void *)g.st; }
+
+int dwtb200_flush_l2(size_t bytes)
+{
+    NEED_DEV();
+    if (bytes > g.flush_bytes) {
+        if (g.flush) cudaFree(g.flush);
+        g.flush = nullptr;
+        g.flush_bytes = 0;
+        CK(cudaMalloc(&g.flush, bytes));
+        g.flush_bytes = bytes;
+    }
+    CK(cudaMemsetAsync(g.flush, 0x5a, bytes, g.st));
+    return DWTB200_OK;
+}
+
+}  // extern "C"

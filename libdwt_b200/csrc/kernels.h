@@ -1,0 +1,90 @@
+// kernels.h -- parameter blocks and launchers of the sm_100a kernels (internal to libdwtb200.so).
+//
+// All pitches / strides / offsets are in ELEMENTS of the plane's type.  Every kernel takes a frame
+// index from gridDim.z (or .y where noted) so a batch of independent frames is one launch.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dwtb200 {
+
+// ---- streaming level kernels (dense planes): one launch = one decomposition level ---------------
+// Forward: reads the level's LL input (W x H) once, writes LL' (to `ll`) and HL/LH/HH (Mallat
+// positions inside the output plane) once.  Inverse is the mirror image.
+struct LevelParams {
+    const void *src;      // fwd: level input plane;      inv: unused
+    void *dst;            // fwd: unused;                  inv: level output plane (W x H)
+    void *ll, *hl, *lh, *hh;   // fwd: outputs; inv: inputs.  hl/lh/hh share `sub_pitch`
+    int64_t src_pitch, dst_pitch, ll_pitch, sub_pitch;
+    int64_t src_frame, dst_frame, ll_frame, sub_frame;   // frame strides
+    int W, H;             // size of the full-resolution side of this level
+    int nLx, nHx, nLy, nHy;   // ceil/floor halves
+    int ncg;              // column groups (one warp wide each)
+    int nstrips;          // row strips
+    int pps;              // output row pairs (fwd) / iterations (inv) per strip
+    int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
+};
+void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
+void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
+int stream_out_width(int kind);   // output columns per warp
+
+// ---- tail kernels: all remaining coarse levels of a plane inside one CTA's shared memory -----------
+struct TailParams {
+    const void *src;   // fwd: LL input of level j0 (w0 x h0); inv: Mallat plane holding the subbands
+    void *dst;         // fwd: Mallat plane receiving subbands + final LL; inv: receives LL of level j0
+    int64_t src_pitch, dst_pitch, src_frame, dst_frame;
+    int W0, H0;        // full image size (level 0) -> Mallat offsets
+    int j0, j1;        // levels j0 .. j1-1 are transformed (fwd ascending, inv descending)
+};
+void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st);
+void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st);
+int tail_max_elems(int kind);
+
+// ---- generic pass kernels: exact reference semantics for sparse (outer != inner) layouts ------
+struct PassParams {
+    const void *src;
+    void *dst;
+    int64_t src_pitch, dst_pitch, src_frame, dst_frame;
+    int region_w, region_h;   // outer extent of this level (everything inside is rewritten in dst)
+    int along_x;              // 1: lines are rows, 0: lines are columns
+    int N;                    // inner line length
+    int off_h;                // position of the H half along the line
+};
+void launch_pass_fwd(int kind, const PassParams &p, int frames, cudaStream_t st);
+void launch_pass_inv(int kind, const PassParams &p, int frames, cudaStream_t st);
+
+struct ZeroParams {
+    void *buf;
+    int64_t pitch, frame;
+    int region_w, region_h;
+    // zero x in [x0a,x0b) U [x1a,x1b) for every row of the region, y likewise for every column
+    int x0a, x0b, x1a, x1b, y0a, y0b, y1a, y1b;
+};
+void launch_zero(int kind, const ZeroParams &p, int frames, cudaStream_t st);
+
+// ---- utilities -------------------------------------------------------------------------------
+// test patterns of dwt_util_test_image_fill{,2}_{s,d,i}  (/root/reference/src/libdwt.c:1112-1244)
+void launch_fill(int kind, void *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type,
+                 int rnd_frame_mod, int frames, cudaStream_t st);
+// strided element gather/scatter between a byte-addressed staging copy of the caller's layout and a
+// dense plane (dwt_util_memcpy_stride_* semantics, src/system.c:90-180)
+void launch_repack(int elem_size, void *plane, int64_t pitch_elems, void *staged, int64_t stride_x_bytes,
+                   int64_t stride_y_bytes, int nx, int ny, int to_plane, cudaStream_t st);
+void launch_copy2d(int elem_size, void *dst, int64_t dpitch, const void *src, int64_t spitch, int w, int h,
+                   int64_t dframe, int64_t sframe, int frames, cudaStream_t st);
+
+void launch_compare(int elem_size, const void *a, const void *b, int64_t pitch, int64_t frame, int nx, int ny, int frames,
+                    int mode, unsigned long long *out, cudaStream_t st);
+void launch_volume_fill(float *buf, int64_t pitch, int64_t slice, int nx, int ny, int nz, cudaStream_t st);
+
+// ---- 3-D (one level, interleaved, in place): lifting along one axis --------------------------
+struct Axis3Params {
+    const float *src;
+    float *dst;
+    int64_t s_line0, s_line1, s_elem;   // src strides (elements): two line-index axes and the lifting axis
+    int64_t d_line0, d_line1, d_elem;
+    int n0, n1, N;
+};
+void launch_axis3(const Axis3Params &p, int inverse, cudaStream_t st);
+
+}  // namespace dwtb200

@@ -1,0 +1,397 @@
+// kernels_stream.cu -- the hot kernels: one decomposition level per launch, row and column lifting
+// fused in registers (sm_100a).
+//
+// Replaces, per level, the two OpenMP line loops of the reference drivers
+// (/root/reference/src/libdwt.c:12837-12893, 17098-17154, 16342-16361, 18178-18195) and the
+// gather / 4 sweeps / scatter of every 1-D line call beneath them.
+//
+// Shape of the computation (forward; the inverse is its mirror image):
+//   * a WARP owns a column group of 30*VPL output columns and a strip of output row pairs; lanes 0
+//     and 31 are halo lanes (they hold the lifting-depth overlap with the neighbouring groups and
+//     store nothing), so every lane runs the same instruction stream and every 16-byte load/store
+//     of the 30 producing lanes is aligned: 32*VPL columns loaded, 30*VPL produced (6.25 % overlap,
+//     served by L1/L2 because neighbouring groups run in neighbouring warps);
+//   * the warp streams DOWN its strip two rows at a time.  Row lifting happens in registers with one
+//     __shfl per lifting step for the +-1 neighbour in the adjacent lane; column lifting is a
+//     register pipeline carried from row pair to row pair (NS state values per column), so a
+//     sample is read from HBM once and each of the four subband samples is written once -- no
+//     shared memory, no intermediate plane;
+//   * image borders: whole-sample mirror on the row index of the load and, for groups touching the
+//     left/right border, per-lane mirrored column indices (warp-uniform slow path);
+//   * the next row pair is prefetched into registers while the current one is lifted.
+// Bit-exactness: every sample still sees "row lifting + scale, then column lifting + scale" in the
+// reference's operation order (int inverse: columns first), only the schedule differs.
+#include "kernels.h"
+#include "lifting.cuh"
+
+namespace dwtb200 {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <class T, int VPL> struct Row {
+    T v[VPL];
+};
+
+// ---- 16-byte vector access -----------------------------------------------------------------------
+template <class T, int N> __device__ __forceinline__ void ld_vec(const T *p, T *v)
+{
+    constexpr int PER = 16 / sizeof(T);
+    static_assert(N % PER == 0, "vector width");
+#pragma unroll
+    for (int i = 0; i < N / PER; i++) {
+        const int4 r = __ldg(reinterpret_cast<const int4 *>(p) + i);
+        *reinterpret_cast<int4 *>(v + i * PER) = r;
+    }
+}
+template <class T, int N> __device__ __forceinline__ void st_vec(T *p, const T *v)
+{
+    constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+    for (int i = 0; i < N / PER; i++) reinterpret_cast<int4 *>(p)[i] = *reinterpret_cast<const int4 *>(v + i * PER);
+}
+
+// ---- row lifting in registers: lane holds VPL consecutive samples, v[0] at an even column ------
+template <class WV, int S, int VPL, bool INV> __device__ __forceinline__ void hstep_odd(typename WV::T (&v)[VPL])
+{
+    using T = typename WV::T;
+    const T nxt = __shfl_down_sync(FULL, v[0], 1);
+#pragma unroll
+    for (int i = 1; i < VPL; i += 2) {
+        const T r = (i + 1 < VPL) ? v[(i + 1) % VPL] : nxt;
+        v[i] = INV ? WV::template i<S>(v[i], v[i - 1], r) : WV::template f<S>(v[i], v[i - 1], r);
+    }
+}
+template <class WV, int S, int VPL, bool INV> __device__ __forceinline__ void hstep_even(typename WV::T (&v)[VPL])
+{
+    using T = typename WV::T;
+    const T prv = __shfl_up_sync(FULL, v[VPL - 1], 1);
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+        const T l = i ? v[(i + VPL - 1) % VPL] : prv;
+        v[i] = INV ? WV::template i<S>(v[i], l, v[i + 1]) : WV::template f<S>(v[i], l, v[i + 1]);
+    }
+}
+template <class WV, int VPL> __device__ __forceinline__ void hfwd(typename WV::T (&v)[VPL])
+{
+    hstep_odd<WV, 0, VPL, false>(v);
+    hstep_even<WV, 1, VPL, false>(v);
+    if constexpr (WV::NS == 4) {
+        hstep_odd<WV, 2, VPL, false>(v);
+        hstep_even<WV, 3, VPL, false>(v);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+        v[i] = WV::fse(v[i]);
+        v[i + 1] = WV::fso(v[i + 1]);
+    }
+}
+template <class WV, int VPL> __device__ __forceinline__ void hinv(typename WV::T (&v)[VPL])
+{
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+        v[i] = WV::ise(v[i]);
+        v[i + 1] = WV::iso(v[i + 1]);
+    }
+    hstep_even<WV, 0, VPL, true>(v);
+    hstep_odd<WV, 1, VPL, true>(v);
+    if constexpr (WV::NS == 4) {
+        hstep_even<WV, 2, VPL, true>(v);
+        hstep_odd<WV, 3, VPL, true>(v);
+    }
+}
+
+// =====================================================================================================
+// forward level
+// =====================================================================================================
+template <class WV, int VPL> __global__ void __launch_bounds__(128, 4) k_fwd_level(const LevelParams p)
+{
+    using T = typename WV::T;
+    constexpr int OUTW = 30 * VPL, HV = VPL / 2;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= p.ncg * p.nstrips) return;
+    const int cg = gw % p.ncg, strip = gw / p.ncg;
+    const int xl = cg * OUTW - VPL + lane * VPL;   // first column held by this lane (even)
+    const int k0 = strip * p.pps, k1 = min(k0 + p.pps, p.nLy);
+    const int W = p.W, H = p.H;
+
+    const T *src = (const T *)p.src + (int64_t)blockIdx.y * p.src_frame;
+    const bool fast = __all_sync(FULL, xl >= 0 && xl + VPL <= W);
+    int cx[VPL];
+    if (!fast) {
+#pragma unroll
+        for (int i = 0; i < VPL; i++) cx[i] = reflect(xl + i, W);
+    }
+    auto load = [&](int r, T(&v)[VPL]) {
+        const T *rp = src + (int64_t)reflect(r, H) * p.src_pitch;
+        if (fast) {
+            ld_vec<T, VPL>(rp + xl, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VPL; i++) v[i] = __ldg(rp + cx[i]);
+        }
+    };
+
+    // destinations: even columns -> L half (ll / lh), odd columns -> H half (hl / hh)
+    const int cb = xl >> 1;
+    const bool producer = lane >= 1 && lane <= 30 && xl < W;
+    const bool whole = xl + VPL <= W;   // all VPL/2 L and H columns exist
+    T *ll = (T *)p.ll + (int64_t)blockIdx.y * p.ll_frame + cb;
+    T *hl = (T *)p.hl + (int64_t)blockIdx.y * p.sub_frame + cb;
+    T *lh = (T *)p.lh + (int64_t)blockIdx.y * p.sub_frame + cb;
+    T *hh = (T *)p.hh + (int64_t)blockIdx.y * p.sub_frame + cb;
+    const bool vec_sub = whole && p.sub_aligned;
+    auto put = [&](T *base, int64_t pitch, int row, const T(&o)[HV], int limit, bool vec) {
+        T *q = base + (int64_t)row * pitch;
+        if (vec) {
+            st_vec<T, HV>(q, o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < HV; i++)
+                if (cb + i < limit) q[i] = o[i];
+        }
+    };
+
+    constexpr int NSTATE = WV::NS;   // carried values per column
+    T st[NSTATE][VPL];               // NS==4: xe, d1, s1, d2     NS==2: xe, d1
+    T a[VPL], b[VPL], na[VPL], nb[VPL];
+
+    constexpr int WARM = WV::NS / 2 + (WV::NS == 4 ? 1 : 0);   // warm-up iterations: 3 (9/7) or 1 (5/3)
+    constexpr int DELAY = WV::NS / 2 - 1;                      // iteration m emits pair m - DELAY
+    const int m0 = k0 + DELAY - WARM;                          // first iteration
+    const int m1 = k1 - 1 + DELAY;                             // last iteration (inclusive)
+
+    load(2 * m0, st[0]);
+    hfwd<WV, VPL>(st[0]);
+    load(2 * m0 + 1, na);
+    load(2 * m0 + 2, nb);
+#pragma unroll
+    for (int s = 1; s < NSTATE; s++)
+#pragma unroll
+        for (int i = 0; i < VPL; i++) st[s][i] = T(0);
+
+    for (int m = m0; m <= m1; m++) {
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+            a[i] = na[i];
+            b[i] = nb[i];
+        }
+        if (m < m1) {   // prefetch the next pair while this one is lifted
+            load(2 * m + 3, na);
+            load(2 * m + 4, nb);
+        }
+        hfwd<WV, VPL>(a);
+        hfwd<WV, VPL>(b);
+
+        T oL[VPL], oH[VPL];   // column-lifted low / high outputs of this iteration
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+            if constexpr (WV::NS == 4) {
+                const T d1n = WV::template f<0>(a[i], st[0][i], b[i]);
+                const T s1n = WV::template f<1>(st[0][i], st[1][i], d1n);
+                const T d2n = WV::template f<2>(st[1][i], st[2][i], s1n);
+                const T s2n = WV::template f<3>(st[2][i], st[3][i], d2n);
+                oL[i] = WV::fse(s2n);
+                oH[i] = WV::fso(d2n);
+                st[0][i] = b[i];
+                st[1][i] = d1n;
+                st[2][i] = s1n;
+                st[3][i] = d2n;
+            } else {
+                const T d1n = WV::template f<0>(a[i], st[0][i], b[i]);
+                const T s1n = WV::template f<1>(st[0][i], st[1][i], d1n);
+                oL[i] = WV::fse(s1n);
+                oH[i] = WV::fso(d1n);
+                st[0][i] = b[i];
+                st[1][i] = d1n;
+            }
+        }
+        const int kk = m - DELAY;
+        if (kk >= k0 && producer) {
+            T o[HV];
+#pragma unroll
+            for (int i = 0; i < HV; i++) o[i] = oL[2 * i];
+            put(ll, p.ll_pitch, kk, o, p.nLx, whole);
+#pragma unroll
+            for (int i = 0; i < HV; i++) o[i] = oL[2 * i + 1];
+            put(hl, p.sub_pitch, kk, o, p.nHx, vec_sub);
+            if (kk < p.nHy) {
+#pragma unroll
+                for (int i = 0; i < HV; i++) o[i] = oH[2 * i];
+                put(lh, p.sub_pitch, kk, o, p.nLx, whole);
+#pragma unroll
+                for (int i = 0; i < HV; i++) o[i] = oH[2 * i + 1];
+                put(hh, p.sub_pitch, kk, o, p.nHx, vec_sub);
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// inverse level
+// =====================================================================================================
+template <class WV, int VPL> __global__ void __launch_bounds__(128, 4) k_inv_level(const LevelParams p)
+{
+    using T = typename WV::T;
+    constexpr int OUTW = 30 * VPL, HV = VPL / 2;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= p.ncg * p.nstrips) return;
+    const int cg = gw % p.ncg, strip = gw / p.ncg;
+    const int xl = cg * OUTW - VPL + lane * VPL;   // first OUTPUT column of this lane (even)
+    const int cb = xl >> 1;                        // first subband column
+    const int W = p.W, H = p.H;
+
+    const T *ll = (const T *)p.ll + (int64_t)blockIdx.y * p.ll_frame;
+    const T *hl = (const T *)p.hl + (int64_t)blockIdx.y * p.sub_frame;
+    const T *lh = (const T *)p.lh + (int64_t)blockIdx.y * p.sub_frame;
+    const T *hh = (const T *)p.hh + (int64_t)blockIdx.y * p.sub_frame;
+    T *dst = (T *)p.dst + (int64_t)blockIdx.y * p.dst_frame;
+
+    const bool inside = xl >= 0 && xl + VPL <= W;
+    const bool fast = __all_sync(FULL, inside);
+    const bool fast_sub = fast && p.sub_aligned;
+    int cL[HV], cH[HV];   // mirrored subband columns for the border path
+    if (!fast_sub) {
+#pragma unroll
+        for (int i = 0; i < HV; i++) {
+            cL[i] = reflect(xl + 2 * i, W) >> 1;
+            cH[i] = reflect(xl + 2 * i + 1, W) >> 1;
+        }
+    }
+    // one interleaved row: even positions from `lo` (L half), odd positions from `hi` (H half)
+    auto load = [&](const T *lo, int64_t lpitch, const T *hi, int64_t hpitch, int row, T(&v)[VPL]) {
+        const T *lp = lo + (int64_t)row * lpitch, *hp = hi + (int64_t)row * hpitch;
+        T l[HV], h[HV];
+        if (fast) {
+            ld_vec<T, HV>(lp + cb, l);
+        } else {
+#pragma unroll
+            for (int i = 0; i < HV; i++) l[i] = __ldg(lp + cL[i]);
+        }
+        if (fast_sub) {
+            ld_vec<T, HV>(hp + cb, h);
+        } else if (fast) {
+#pragma unroll
+            for (int i = 0; i < HV; i++) h[i] = __ldg(hp + cb + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < HV; i++) h[i] = __ldg(hp + cH[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < HV; i++) {
+            v[2 * i] = l[i];
+            v[2 * i + 1] = h[i];
+        }
+    };
+    // iteration k consumes interleaved rows 2k (an L row) and 2k+1 (an H row), mirrored
+    auto load_pair = [&](int k, T(&a)[VPL], T(&b)[VPL]) {
+        const int ra = reflect(2 * k, H) >> 1, rb = reflect(2 * k + 1, H) >> 1;
+        load(ll, p.ll_pitch, hl, p.sub_pitch, ra, a);
+        load(lh, p.sub_pitch, hh, p.sub_pitch, rb, b);
+    };
+    const bool producer = lane >= 1 && lane <= 30 && xl < W;
+    const bool whole = xl + VPL <= W;
+    auto put = [&](int row, const T(&o)[VPL]) {
+        if (row < 0 || row >= H || !producer) return;
+        T *q = dst + (int64_t)row * p.dst_pitch + xl;
+        if (whole) {
+            st_vec<T, VPL>(q, o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VPL; i++)
+                if (xl + i < W) q[i] = o[i];
+        }
+    };
+
+    constexpr int NSTATE = WV::NS;
+    T st[NSTATE][VPL];   // NS==4: d2p, s1p, d1p, xep      NS==2: cp, xep
+    T a[VPL], b[VPL], na[VPL], nb[VPL];
+    constexpr int DELAY = WV::NS / 2 - 1;   // iteration k emits rows 2(k-DELAY)-1 and 2(k-DELAY)
+    constexpr int WARM = WV::NS;            // warm-up iterations
+    const int q0 = strip * p.pps, q1 = min(q0 + p.pps, (H >> 1) + 1);   // emitted q = k - DELAY in [q0, q1)
+    const int ka = q0 + DELAY - WARM, kb = q1 - 1 + DELAY;
+
+#pragma unroll
+    for (int s = 0; s < NSTATE; s++)
+#pragma unroll
+        for (int i = 0; i < VPL; i++) st[s][i] = T(0);
+    load_pair(ka, na, nb);
+
+    for (int k = ka; k <= kb; k++) {
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+            a[i] = na[i];
+            b[i] = nb[i];
+        }
+        if (k < kb) load_pair(k + 1, na, nb);
+        if constexpr (!WV::INV_COLS_FIRST) {   // rows first (float / double): libdwt.c:17098 then 17127
+            hinv<WV, VPL>(a);
+            hinv<WV, VPL>(b);
+        }
+        T oO[VPL], oE[VPL];   // output rows 2q-1 (odd) and 2q (even)
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+            if constexpr (WV::NS == 4) {
+                const T s2k = WV::ise(a[i]), d2k = WV::iso(b[i]);
+                const T s1k = WV::template i<0>(s2k, st[0][i], d2k);
+                const T d1m = WV::template i<1>(st[0][i], st[1][i], s1k);
+                const T xen = WV::template i<2>(st[1][i], st[2][i], d1m);
+                const T xo = WV::template i<3>(st[2][i], st[3][i], xen);
+                oO[i] = xo;
+                oE[i] = xen;
+                st[0][i] = d2k;
+                st[1][i] = s1k;
+                st[2][i] = d1m;
+                st[3][i] = xen;
+            } else {
+                const T ck = WV::ise(a[i]), cn = WV::iso(b[i]);
+                const T xen = WV::template i<0>(ck, st[0][i], cn);
+                const T xo = WV::template i<1>(st[0][i], st[1][i], xen);
+                oO[i] = xo;
+                oE[i] = xen;
+                st[0][i] = cn;
+                st[1][i] = xen;
+            }
+        }
+        const int q = k - DELAY;
+        if (q >= q0) {   // warp-uniform
+            if constexpr (WV::INV_COLS_FIRST) {   // columns first (int): libdwt.c:18178 then 18187
+                hinv<WV, VPL>(oO);
+                hinv<WV, VPL>(oE);
+            }
+            put(2 * q - 1, oO);
+            put(2 * q, oE);
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+template <class WV, int VPL> static void go_fwd(const LevelParams &p, int frames, cudaStream_t st)
+{
+    const int warps = p.ncg * p.nstrips;
+    const dim3 grid((warps + 3) / 4, frames);
+    k_fwd_level<WV, VPL><<<grid, 128, 0, st>>>(p);
+}
+template <class WV, int VPL> static void go_inv(const LevelParams &p, int frames, cudaStream_t st)
+{
+    const int warps = p.ncg * p.nstrips;
+    const dim3 grid((warps + 3) / 4, frames);
+    k_inv_level<WV, VPL><<<grid, 128, 0, st>>>(p);
+}
+int stream_out_width(int kind) { return kind == K_CDF97_F64 ? 30 * 4 : 30 * 8; }
+
+void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st)
+{
+    if (kind == K_CDF97_F32) go_fwd<W97F, 8>(p, frames, st);
+    else if (kind == K_CDF97_F64) go_fwd<W97D, 4>(p, frames, st);
+    else go_fwd<W53I, 8>(p, frames, st);
+}
+void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st)
+{
+    if (kind == K_CDF97_F32) go_inv<W97F, 8>(p, frames, st);
+    else if (kind == K_CDF97_F64) go_inv<W97D, 4>(p, frames, st);
+    else go_inv<W53I, 8>(p, frames, st);
+}
+
+}  // namespace dwtb200

@@ -1,0 +1,162 @@
+// lifting.cuh -- per-wavelet lifting arithmetic shared by every kernel (sm_100a).
+//
+// Each `Wxx` struct is the arithmetic of one reference line function, written as single lifting
+// steps so that the same code serves the streaming level kernels, the tail kernel and the generic
+// pass kernels.  Everything is evaluated with explicitly rounded intrinsics (__fadd_rn/__fmul_rn,
+// __dadd_rn/__dmul_rn): the compiler may not contract them into FMAs, so a sample goes through
+// exactly the operations of the reference's x86-64 SSE2 build and float/double output is
+// bit-identical, not merely within tolerance.
+//
+//   W97F  dwt_cdf97_f_ex_stride_s / dwt_cdf97_i_ex_stride_s   /root/reference/src/libdwt.c:10744, 11530
+//         (core accel_lift_op4s_main_s :2264, edges :9510 :9844 :10199)
+//   W97D  dwt_cdf97_f_ex_stride_d / dwt_cdf97_i_ex_stride_d   src/libdwt.c:2024, 11424
+//   W53I  dwt_cdf53_f_ex_stride_i / dwt_cdf53_i_ex_stride_i   src/libdwt.c:10950, 11749
+//   constants                                                  src/inline.h:310-341
+//
+// Step numbering: forward step S (0..NS-1) updates ODD samples when S is even and EVEN samples when
+// S is odd; inverse step S updates EVEN samples when S is even.  A step is x' = step(x, left, right).
+// Boundaries are whole-sample mirrors (t[-1]=t[1], t[N]=t[N-2]); the reference writes the edge as
+// (2c)*nb, which equals c*(nb+nb) bit for bit, and for int ((nb+nb)>>1)==nb, ((2nb+2)>>2)==((nb+1)>>1)
+// as long as 2*nb does not overflow int32 (documented domain: |coefficient| < 2^30).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dwtb200 {
+
+enum Kind : int { K_CDF97_F32 = 0, K_CDF97_F64 = 1, K_CDF53_I32 = 2 };
+
+struct W97F {
+    using T = float;
+    static constexpr int NS = 4;       // lifting steps
+    static constexpr int HALO = 4;     // input samples needed either side of an output sample
+    static constexpr bool HAS_ONE = true;   // a line of length 1 is scaled (libdwt.c:10757, 11546)
+    static constexpr bool GUARD = true;     // driver skips a pass when the line count is <= 1 (libdwt.c:12837)
+    static constexpr bool INV_COLS_FIRST = false;
+    // double literals rounded to float, exactly as `static const float x = <double literal>` does
+    static constexpr float P1 = (float)1.58613434342059, U1 = (float)-0.0529801185729;
+    static constexpr float P2 = (float)-0.8829110755309, U2 = (float)0.4435068520439;
+    static constexpr float Z = (float)1.1496043988602;
+    static constexpr float IZ = 1.0f / Z;                          // 1/zeta evaluated in float (libdwt.c:2289)
+    static constexpr float S2 = (float)(1 / 1.1496043988602);      // dwt_cdf97_s2_s, 1 ulp above IZ
+    template <int S> static __device__ __forceinline__ T cf() { return S == 0 ? -P1 : S == 1 ? U1 : S == 2 ? -P2 : U2; }
+    template <int S> static __device__ __forceinline__ T ci() { return S == 0 ? -U2 : S == 1 ? P2 : S == 2 ? -U1 : P1; }
+    template <int S> static __device__ __forceinline__ T f(T x, T l, T r) { return __fadd_rn(x, __fmul_rn(cf<S>(), __fadd_rn(l, r))); }
+    template <int S> static __device__ __forceinline__ T i(T x, T l, T r) { return __fadd_rn(x, __fmul_rn(ci<S>(), __fadd_rn(l, r))); }
+    static __device__ __forceinline__ T fse(T x) { return __fmul_rn(x, Z); }    // forward scale, even sample
+    static __device__ __forceinline__ T fso(T x) { return __fmul_rn(x, IZ); }   // forward scale, odd sample
+    static __device__ __forceinline__ T ise(T x) { return __fmul_rn(x, IZ); }
+    static __device__ __forceinline__ T iso(T x) { return __fmul_rn(x, Z); }
+    static __device__ __forceinline__ T one_f(T x) { return __fmul_rn(x, Z); }
+    static __device__ __forceinline__ T one_i(T x) { return __fmul_rn(x, S2); }
+};
+
+struct W97D {
+    using T = double;
+    static constexpr int NS = 4;
+    static constexpr int HALO = 4;
+    static constexpr bool HAS_ONE = true;    // libdwt.c:2036, 11437
+    static constexpr bool GUARD = false;     // libdwt.c:12481: no `lines > 1` test
+    static constexpr bool INV_COLS_FIRST = false;
+    static constexpr double P1 = 1.58613434342059, U1 = -0.0529801185729;
+    static constexpr double P2 = -0.8829110755309, U2 = 0.4435068520439;
+    static constexpr double Z = 1.1496043988602;
+    static constexpr double S2 = 1 / 1.1496043988602;
+    template <int S> static __device__ __forceinline__ T cf() { return S == 0 ? -P1 : S == 1 ? U1 : S == 2 ? -P2 : U2; }
+    template <int S> static __device__ __forceinline__ T ci() { return S == 0 ? -U2 : S == 1 ? P2 : S == 2 ? -U1 : P1; }
+    template <int S> static __device__ __forceinline__ T f(T x, T l, T r) { return __dadd_rn(x, __dmul_rn(cf<S>(), __dadd_rn(l, r))); }
+    template <int S> static __device__ __forceinline__ T i(T x, T l, T r) { return __dadd_rn(x, __dmul_rn(ci<S>(), __dadd_rn(l, r))); }
+    static __device__ __forceinline__ T fse(T x) { return __dmul_rn(x, Z); }
+    static __device__ __forceinline__ T fso(T x) { return __dmul_rn(x, S2); }
+    static __device__ __forceinline__ T ise(T x) { return __dmul_rn(x, S2); }
+    static __device__ __forceinline__ T iso(T x) { return __dmul_rn(x, Z); }
+    static __device__ __forceinline__ T one_f(T x) { return __dmul_rn(x, Z); }
+    static __device__ __forceinline__ T one_i(T x) { return __dmul_rn(x, S2); }
+};
+
+struct W53I {
+    using T = int32_t;
+    static constexpr int NS = 2;
+    static constexpr int HALO = 2;
+    static constexpr bool HAS_ONE = false;   // libdwt.c:10961: N < 2 leaves the line untouched
+    static constexpr bool GUARD = false;
+    static constexpr bool INV_COLS_FIRST = true;   // libdwt.c:18178, 18187
+    static __device__ __forceinline__ T wadd(T a, T b) { return (T)((uint32_t)a + (uint32_t)b); }
+    static __device__ __forceinline__ T wsub(T a, T b) { return (T)((uint32_t)a - (uint32_t)b); }
+    template <int S> static __device__ __forceinline__ T f(T x, T l, T r)
+    {
+        if (S == 0) return wsub(x, wadd(l, r) >> 1);          // predict, odd samples
+        return wadd(x, wadd(wadd(l, r), 2) >> 2);             // update, even samples
+    }
+    template <int S> static __device__ __forceinline__ T i(T x, T l, T r)
+    {
+        if (S == 0) return wsub(x, wadd(wadd(l, r), 2) >> 2); // undo update, even samples
+        return wadd(x, wadd(l, r) >> 1);                      // undo predict, odd samples
+    }
+    static __device__ __forceinline__ T fse(T x) { return x; }
+    static __device__ __forceinline__ T fso(T x) { return x; }
+    static __device__ __forceinline__ T ise(T x) { return x; }
+    static __device__ __forceinline__ T iso(T x) { return x; }
+    static __device__ __forceinline__ T one_f(T x) { return x; }
+    static __device__ __forceinline__ T one_i(T x) { return x; }
+};
+
+// Whole-sample mirror of index i into [0, n), n >= 2; period 2(n-1) so windows wider than the
+// line (tiny coarse levels) fold repeatedly, exactly like the reference's N = 2, 3, 4 cases.
+__device__ __forceinline__ int reflect(int i, int n)
+{
+    if ((unsigned)i < (unsigned)n) return i;
+    const int p = 2 * (n - 1);
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - i;
+}
+
+// ---- window evaluation: one (even, odd) output pair from a 2*HALO+2 sample window -------------
+// forward:  w[q] = x[2k-HALO+q]  ->  L[k] (even), H[k] (odd)
+// inverse:  w[q] = c[2k-HALO+q]  (interleaved coefficients)  ->  x[2k], x[2k+1]
+template <class WV> __device__ __forceinline__ void window_fwd(typename WV::T (&w)[2 * WV::HALO + 2], typename WV::T &L, typename WV::T &H)
+{
+    if constexpr (WV::NS == 4) {
+#pragma unroll
+        for (int q = 1; q <= 7; q += 2) w[q] = WV::template f<0>(w[q], w[q - 1], w[q + 1]);
+#pragma unroll
+        for (int q = 2; q <= 6; q += 2) w[q] = WV::template f<1>(w[q], w[q - 1], w[q + 1]);
+#pragma unroll
+        for (int q = 3; q <= 5; q += 2) w[q] = WV::template f<2>(w[q], w[q - 1], w[q + 1]);
+        w[4] = WV::template f<3>(w[4], w[3], w[5]);
+        L = WV::fse(w[4]);
+        H = WV::fso(w[5]);
+    } else {
+        w[1] = WV::template f<0>(w[1], w[0], w[2]);
+        w[3] = WV::template f<0>(w[3], w[2], w[4]);
+        w[2] = WV::template f<1>(w[2], w[1], w[3]);
+        L = WV::fse(w[2]);
+        H = WV::fso(w[3]);
+    }
+}
+template <class WV> __device__ __forceinline__ void window_inv(typename WV::T (&w)[2 * WV::HALO + 2], typename WV::T &E, typename WV::T &O)
+{
+    constexpr int N = 2 * WV::HALO + 2;
+#pragma unroll
+    for (int q = 0; q < N; q += 2) { w[q] = WV::ise(w[q]); w[q + 1] = WV::iso(w[q + 1]); }
+    if constexpr (WV::NS == 4) {
+#pragma unroll
+        for (int q = 2; q <= 8; q += 2) w[q] = WV::template i<0>(w[q], w[q - 1], w[q + 1]);
+#pragma unroll
+        for (int q = 3; q <= 7; q += 2) w[q] = WV::template i<1>(w[q], w[q - 1], w[q + 1]);
+#pragma unroll
+        for (int q = 4; q <= 6; q += 2) w[q] = WV::template i<2>(w[q], w[q - 1], w[q + 1]);
+        w[5] = WV::template i<3>(w[5], w[4], w[6]);
+        E = w[4];
+        O = w[5];
+    } else {
+        w[2] = WV::template i<0>(w[2], w[1], w[3]);
+        w[4] = WV::template i<0>(w[4], w[3], w[5]);
+        w[3] = WV::template i<1>(w[3], w[2], w[4]);
+        E = w[2];
+        O = w[3];
+    }
+}
+
+}  // namespace dwtb200

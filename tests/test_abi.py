@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/dwtb200.h declares, and
+its compute entry points fail loudly (no fallback) when no CUDA device is present."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols(path):
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dwtb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    import libdwt_b200 as d
+    L = d.lib()
+    declared = header_symbols(os.path.join(ROOT, "include", "dwtb200.h"))
+    assert len(declared) >= 35
+    bound = {n for n, _, _ in d.api.SYMBOLS}
+    for name in declared:
+        assert hasattr(L.c, name), f"{name} declared in include/dwtb200.h but not exported"
+        assert name in bound, f"{name} has no ctypes prototype"
+    assert isinstance(L.c, ctypes.CDLL)
+
+
+def test_level_arithmetic_matches_oracle(oracle):
+    import libdwt_b200 as d
+    L = d.lib()
+    for x in list(range(1, 70)) + [127, 128, 129, 4095, 4096, 4097, 65536]:
+        assert L.c.dwtb200_ceil_log2(x) == oracle.ceil_log2(x)
+    # src/libdwt.c:12807-12810
+    assert L.c.dwtb200_clamp_j(-1, 512, 512, 0) == 9
+    assert L.c.dwtb200_clamp_j(-1, 7919, 6007, 0) == 13
+    assert L.c.dwtb200_clamp_j(99, 64, 3, 0) == 2
+    assert L.c.dwtb200_clamp_j(-1, 64, 3, 1) == 6
+    assert L.c.dwtb200_clamp_j(3, 64, 64, 0) == 3
+
+
+def test_compute_fails_loudly_without_gpu():
+    import numpy as np
+    import libdwt_b200 as d
+    L = d.lib()
+    if L.c.dwtb200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    img = np.zeros((8, 8), np.float32)
+    with pytest.raises(d.DwtError):
+        d.fwd2(img, "97", "s")
+    with pytest.raises(d.DwtError):
+        d.DeviceImage(d.CDF97_F32, 8, 8)

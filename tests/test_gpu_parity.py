@@ -1,0 +1,318 @@
+"""GPU (B200): the CUDA path, called through the C ABI (libdwtb200.so), against the oracle on the same
+inputs -- bit-exact for int 5/3 AND for float/double 9/7 (the kernels use explicitly rounded,
+non-contracted arithmetic in the reference's operation order, so the tolerance is 0 ulp; the
+reference's own tolerance is 1e-3 / 1e-6, src/libdwt.c:1604, 1513) -- and against the committed golden
+digests of the compiled reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import (DENSE_SHAPES, DEPTHS, DT, KINDS, SPARSE, bits, case_id, dense_cases, describe_mismatch, digest,
+                   sparse_cases)
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+KIDS = [k[0] + k[1] for k in KINDS]
+
+
+def both(dev, oracle, w, t, ox, oy, j, d1, zp=0, inner=None, row_bytes=None, rand=0, type_=0):
+    """Run forward + inverse on the device path and on the oracle; returns a list of failure strings."""
+    from oracle.orc import strided_image
+    a = strided_image((oy, ox), t, row_bytes)
+    b = strided_image((oy, ox), t, row_bytes)
+    oracle.fill(a, t, rand=rand, type_=type_)
+    b[...] = a
+    fails = []
+    tag = f"{w}{t} {ox}x{oy} j={j} d1={d1} zp={zp} inner={inner} row_bytes={row_bytes}"
+    Ja = oracle.fwd2(a, w, t, j_max=j, decompose_one=d1, zero_padding=zp, inner=inner)
+    Jb = dev.fwd2(b, w, t, j_max=j, decompose_one=d1, zero_padding=zp, inner=inner)
+    if Ja != Jb:
+        fails.append(f"{tag}: J {Jb} != {Ja}")
+    if not (bits(a, t) == bits(b, t)).all():
+        fails.append(f"{tag}: FORWARD " + describe_mismatch(b, a, t))
+        b[...] = a   # continue from the right coefficients so the inverse is judged on its own
+    oracle.inv2(a, w, t, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=inner)
+    dev.inv2(b, w, t, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=inner)
+    if not (bits(a, t) == bits(b, t)).all():
+        fails.append(f"{tag}: INVERSE " + describe_mismatch(b, a, t))
+    return fails
+
+
+def report(fails):
+    assert not fails, f"{len(fails)} failures:\n" + "\n".join(fails[:12])
+
+
+def test_device_present_and_is_blackwell(dev):
+    L = dev.lib()
+    assert L.c.dwtb200_device_count() >= 1
+    assert L.c.dwtb200_device() >= 0
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_test_pattern_matches_oracle(dev, oracle, kind):
+    w, t = kind
+    for (ox, oy, rnd, typ) in ((517, 301, 0, 0), (64, 64, 3, 0), (300, 200, 0, 2), (4096, 2100, 0, 0)):
+        if t == "d" and typ != 0:
+            continue
+        img = dev.DeviceImage(dev.kind_of(w, t), ox, oy)
+        img.fill(rnd, typ)
+        got = img.download()
+        want = oracle.fill(np.zeros((oy, ox), DT[t]), t, rand=rnd, type_=typ)
+        assert (bits(got, t) == bits(want, t)).all(), describe_mismatch(got, want, t)
+        img.close()
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+@pytest.mark.parametrize("shape", [(16, 16), (128, 128), (31, 33), (64, 3)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_tail_only_shapes(dev, oracle, kind, shape):
+    w, t = kind
+    fails = []
+    for (j, d1) in DEPTHS:
+        fails += both(dev, oracle, w, t, shape[0], shape[1], j, d1)
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_one_streamed_level(dev, oracle, kind):
+    w, t = kind
+    fails = []
+    for (ox, oy) in ((256, 256), (300, 200), (241, 250), (479, 33), (129, 127)):
+        fails += both(dev, oracle, w, t, ox, oy, 1, 0)
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+@pytest.mark.parametrize("shape", DENSE_SHAPES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_dense_parity(dev, oracle, kind, shape):
+    w, t = kind
+    ox, oy = shape
+    fails = []
+    for c in dense_cases():
+        if c[:4] == (w, t, ox, oy):
+            fails += both(dev, oracle, w, t, ox, oy, c[4], c[5])
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_sparse_parity(dev, oracle, kind):
+    w, t = kind
+    fails = []
+    for c in sparse_cases():
+        if c[:2] == (w, t):
+            _, _, ox, oy, ix, iy, j, d1, zp = c
+            fails += both(dev, oracle, w, t, ox, oy, j, d1, zp=zp, inner=(iy, ix))
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_generic_kernels_on_dense_shapes(dev, oracle, kind):
+    w, t = kind
+    L = dev.lib()
+    L.c.dwtb200_force_generic(1)
+    try:
+        fails = []
+        for (ox, oy) in ((517, 301), (64, 3), (5, 1000), (256, 256), (1, 9)):
+            for (j, d1) in ((-1, 0), (-1, 1), (2, 0)):
+                fails += both(dev, oracle, w, t, ox, oy, j, d1)
+    finally:
+        L.c.dwtb200_force_generic(0)
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_strip_boundaries(dev, oracle, kind):
+    """Every strip height must give the same bits: strips re-derive their lifting state from a halo."""
+    w, t = kind
+    L = dev.lib()
+    fails = []
+    try:
+        for rows in (2, 4, 6, 16, 34, 128, 1000):
+            L.c.dwtb200_set_strip_rows(rows)
+            for (ox, oy) in ((517, 301), (300, 200), (256, 257)):
+                fails += [f"strip_rows={rows}: " + f for f in both(dev, oracle, w, t, ox, oy, -1, 0)]
+    finally:
+        L.c.dwtb200_set_strip_rows(0)
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_unaligned_and_channel_strides(dev, oracle, ref_opt_stride, kind):
+    """dwt_util_get_opt_stride() hands out prime row strides (2053 B for 512 floats): rows are not even
+    element-aligned; cvdwt.cpp passes stride_y = pixel size of an interleaved multi-channel image."""
+    w, t = kind
+    es = np.dtype(DT[t]).itemsize
+    fails = []
+    for (ox, oy) in ((512, 512), (517, 301), (100, 77)):
+        fails += both(dev, oracle, w, t, ox, oy, -1, 0, row_bytes=ref_opt_stride(ox * es))
+    # 3-channel interleaved: transform channel 1 in place, the other channels must survive
+    oy, ox, ch = 120, 200, 3
+    base = np.zeros((oy, ox, ch), DT[t])
+    for c in range(ch):
+        plane = np.zeros((oy, ox), DT[t])
+        oracle.fill(plane, t, rand=c)
+        base[:, :, c] = plane
+    a, b = base.copy(), base.copy()
+    Ja = oracle.fwd2(a[:, :, 1], w, t)
+    Jb = dev.fwd2(b[:, :, 1], w, t)
+    if Ja != Jb or not (a.view(np.uint8) == b.view(np.uint8)).all():
+        fails.append("channel-strided forward: " + describe_mismatch(b[:, :, 1], a[:, :, 1], t))
+    b[...] = a
+    oracle.inv2(a[:, :, 1], w, t, j_max=Ja)
+    dev.inv2(b[:, :, 1], w, t, j_max=Ja)
+    if not (a.view(np.uint8) == b.view(np.uint8)).all():
+        fails.append("channel-strided inverse: " + describe_mismatch(b[:, :, 1], a[:, :, 1], t))
+    report(fails)
+
+
+@pytest.fixture(scope="module")
+def ref_opt_stride():
+    # dwt_util_get_opt_stride (src/libdwt.c:20655): next prime >= row bytes on x86-64
+    def is_prime(n):
+        if n < 2:
+            return False
+        i = 2
+        while i * i <= n:
+            if n % i == 0:
+                return False
+            i += 1
+        return True
+
+    def f(n):
+        while not is_prime(n):
+            n += 1
+        return n
+    assert f(2048) == 2053
+    return f
+
+
+def test_golden_digests_of_the_reference(dev, oracle):
+    """CUDA output against digests the compiled reference produced (tests/golden/make_golden.py)."""
+    bad = []
+    for c in dense_cases() + sparse_cases():
+        if len(c) == 6:
+            w, t, ox, oy, j, d1 = c
+            ix, iy, zp = ox, oy, 0
+        else:
+            w, t, ox, oy, ix, iy, j, d1, zp = c
+        img = np.zeros((oy, ox), DT[t])
+        oracle.fill(img, t)
+        J = dev.fwd2(img, w, t, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        g = GOLD[case_id(c)]
+        f = digest(img)
+        dev.inv2(img, w, t, j_max=J, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        if (J, f, digest(img)) != (g["J"], g["fwd"], g["inv"]):
+            bad.append(case_id(c))
+    assert not bad, f"{len(bad)} cases differ from the reference digests: {bad[:20]}"
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_device_resident_batch(dev, oracle, kind):
+    """frames > 1: one launch per level for the whole batch; frame k is filled with rand = k % 6."""
+    w, t = kind
+    ox, oy, frames = 300, 260, 7
+    img = dev.DeviceImage(dev.kind_of(w, t), ox, oy, frames)
+    img.fill(0, 0, 6)
+    J = img.fwd2()
+    fails = []
+    wants = []
+    for k in range(frames):
+        want = oracle.fill(np.zeros((oy, ox), DT[t]), t, rand=k % 6)
+        x0 = want.copy()
+        Jo = oracle.fwd2(want, w, t)
+        got = img.download(frame=k)
+        if J != Jo or not (bits(got, t) == bits(want, t)).all():
+            fails.append(f"frame {k} forward: " + describe_mismatch(got, want, t))
+        wants.append(x0)
+    assert img.last_path == 0 and 1 <= img.last_launches <= J
+    img.inv2(J)
+    for k in range(frames):
+        got = img.download(frame=k)
+        ref_rt = wants[k].copy()
+        oracle.fwd2(ref_rt, w, t)
+        oracle.inv2(ref_rt, w, t, j_max=J)
+        if not (bits(got, t) == bits(ref_rt, t)).all():
+            fails.append(f"frame {k} inverse: " + describe_mismatch(got, ref_rt, t))
+    img.close()
+    report(fails)
+
+
+# ---- BASELINE.json configs at full size ---------------------------------------------------------------
+FULL = [("53", "i", 4096, 4096), ("97", "s", 8192, 8192), ("97", "s", 7919, 6007), ("97", "d", 4096, 4096),
+        ("97", "s", 2048, 2048)]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=lambda c: f"{c[0]}{c[1]}-{c[2]}x{c[3]}")
+def test_full_size_configs(dev, oracle, cfg):
+    w, t, ox, oy = cfg
+    a = np.zeros((oy, ox), DT[t])
+    oracle.fill(a, t)
+    x0 = a.copy()
+    img = dev.DeviceImage(dev.kind_of(w, t), ox, oy)
+    img.fill(0, 0)
+    got = img.download()
+    assert (bits(got, t) == bits(a, t)).all(), "pattern: " + describe_mismatch(got, a, t)
+    Ja = oracle.fwd2(a, w, t)
+    Jb = img.fwd2()
+    assert Ja == Jb == dev.lib().c.dwtb200_ceil_log2(min(ox, oy))
+    got = img.download()
+    assert (bits(got, t) == bits(a, t)).all(), "forward: " + describe_mismatch(got, a, t)
+    oracle.inv2(a, w, t, j_max=Ja)
+    img.inv2(Jb)
+    got = img.download()
+    assert (bits(got, t) == bits(a, t)).all(), "inverse: " + describe_mismatch(got, a, t)
+    err = np.abs(got.astype(np.float64) - x0.astype(np.float64)).max()
+    # reconstruction error of forward-then-inverse (the reference's own self-test bound)
+    assert err <= {"i": 0, "s": 1e-3, "d": 1e-6}[t], err
+    img.close()
+
+
+def test_properties_at_full_size(dev):
+    """Size-independent checks on the device, no oracle: int round trip is exact, float round trip is
+    within the reference's eps, and the transform of a frame does not depend on its batch position."""
+    img = dev.DeviceImage(dev.CDF53_I32, 4096, 4096, 2)
+    keep = dev.DeviceImage(dev.CDF53_I32, 4096, 4096, 2)
+    img.fill(0, 2, 0)
+    keep.copy_from(img)
+    J = img.fwd2()
+    assert img.diff(keep) > 0
+    img.inv2(J)
+    assert img.diff(keep) == 0
+    a, b = img.download(frame=0), img.download(frame=1)
+    assert (a == b).all()
+    img.close(); keep.close()
+    f = dev.DeviceImage(dev.CDF97_F32, 8192, 8192)
+    k = dev.DeviceImage(dev.CDF97_F32, 8192, 8192)
+    f.fill(0, 0, 0)
+    k.copy_from(f)
+    J = f.fwd2()
+    assert J == 13
+    f.inv2(J)
+    assert f.maxabs(k) < 1e-3
+    f.close(); k.close()
+
+
+# ---- 3-D ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(16, 16, 16), (33, 20, 9), (64, 48, 40), (5, 5, 5), (100, 37, 21)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_volume_parity(dev, oracle, shape):
+    nx, ny, nz = shape
+    a = oracle.volume_fill(np.zeros((nz, ny, nx), np.float32))
+    want = np.zeros_like(a)
+    oracle.fwd3(a, want)
+    got = np.zeros_like(a)
+    dev.fwd3(a, got)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all(), f"{(got != want).sum()} voxels differ (forward)"
+    key = f"vol-{nx}-{ny}-{nz}"
+    if key in GOLD:
+        assert digest(got) == GOLD[key]["fwd"]
+    oracle.inv3(want)
+    dev.inv3(got)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all(), f"{(got != want).sum()} voxels differ (inverse)"
+    assert np.abs(got - a).max() < 1e-3
+    v = dev.DeviceVolume(nx, ny, nz)
+    v.fill()
+    assert (v.download().view(np.uint32) == a.view(np.uint32)).all()
+    v.close()

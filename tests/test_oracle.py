@@ -1,0 +1,124 @@
+"""CPU: the oracle (oracle/dwt_oracle.c) against the golden vectors produced by the compiled reference
+(tests/golden/make_golden.py) and, when oracle/_ref is present, against the reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import DT, bits, case_id, dense_cases, describe_mismatch, digest, sparse_cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+VEC = np.load(os.path.join(HERE, "golden", "vectors.npz"))
+
+
+def unpack(c):
+    if len(c) == 6:
+        w, t, ox, oy, j, d1 = c
+        return w, t, ox, oy, ox, oy, j, d1, 0
+    return c
+
+
+def run_impl(impl, c, fill):
+    w, t, ox, oy, ix, iy, j, d1, zp = unpack(c)
+    img = np.zeros((oy, ox), dtype=DT[t])
+    fill.fill(img, t, rand=0, type_=0)
+    J = impl.fwd2(img, w, t, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+    fwd = img.copy()
+    impl.inv2(img, w, t, j_max=J, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+    return J, fwd, img
+
+
+def test_oracle_matches_golden_digests(oracle):
+    bad = []
+    for c in dense_cases() + sparse_cases():
+        J, fwd, inv = run_impl(oracle, c, oracle)
+        g = GOLD[case_id(c)]
+        if (J, digest(fwd), digest(inv)) != (g["J"], g["fwd"], g["inv"]):
+            bad.append(case_id(c))
+    assert not bad, f"{len(bad)} cases differ from the reference's golden digests: {bad[:10]}"
+
+
+def test_oracle_matches_golden_vectors(oracle):
+    for key in VEC.files:
+        if not key.endswith("/in") or key.startswith("vol"):
+            continue
+        name = key[:-3]
+        c = next(cc for cc in dense_cases() + sparse_cases() if case_id(cc) == name)
+        w, t, ox, oy, ix, iy, j, d1, zp = unpack(c)
+        img = VEC[key].copy()
+        J = oracle.fwd2(img, w, t, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        assert (bits(img, t) == bits(VEC[name + "/fwd"], t)).all(), describe_mismatch(img, VEC[name + "/fwd"], t)
+        oracle.inv2(img, w, t, j_max=J, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        assert (bits(img, t) == bits(VEC[name + "/inv"], t)).all(), describe_mismatch(img, VEC[name + "/inv"], t)
+
+
+def test_oracle_type2_and_volume_golden(oracle):
+    for (w, t) in (("53", "i"), ("97", "s")):
+        img = np.zeros((301, 517), dtype=DT[t])
+        oracle.fill(img, t, rand=0, type_=2)
+        J = oracle.fwd2(img, w, t)
+        g = GOLD[f"type2-{w}-{t}-517-301"]
+        assert (J, digest(img)) == (g["J"], g["fwd"])
+        oracle.inv2(img, w, t, j_max=J)
+        assert digest(img) == g["inv"]
+    for (nx, ny, nz) in ((16, 16, 16), (33, 20, 9), (64, 48, 40), (5, 5, 5)):
+        a = np.zeros((nz, ny, nx), dtype=np.float32)
+        oracle.volume_fill(a)
+        b = np.zeros_like(a)
+        oracle.fwd3(a, b)
+        g = GOLD[f"vol-{nx}-{ny}-{nz}"]
+        assert digest(b) == g["fwd"]
+        oracle.inv3(b)
+        assert digest(b) == g["inv"]
+    assert (VEC["vol-16-16-16/in"].view(np.uint32) == oracle.volume_fill(np.zeros((16, 16, 16), np.float32)).view(np.uint32)).all()
+
+
+def test_int_roundtrip_is_exact_and_float_roundtrip_is_close(oracle):
+    # the reference's own self-test criterion (src/libdwt.c:1548, 1604, 1513)
+    for (w, t, eps) in (("53", "i", 0), ("97", "s", 1e-3), ("97", "d", 1e-6)):
+        img = np.zeros((301, 517), dtype=DT[t])
+        oracle.fill(img, t)
+        x0 = img.copy()
+        J = oracle.fwd2(img, w, t)
+        oracle.inv2(img, w, t, j_max=J)
+        assert np.abs(img.astype(np.float64) - x0.astype(np.float64)).max() <= eps
+
+
+# ---- against the compiled reference itself (build container only) ---------------------------------
+@pytest.mark.parametrize("kind", [("97", "s"), ("97", "d"), ("53", "i")], ids=lambda k: k[0] + k[1])
+def test_oracle_vs_reference_strided(oracle, ref, kind):
+    from oracle.orc import strided_image
+    w, t = kind
+    es = np.dtype(DT[t]).itemsize
+    for (ox, oy) in ((512, 512), (517, 301), (64, 3), (100, 77)):
+        for row_bytes in (ox * es, ref.opt_stride(ox * es)):
+            for (j, d1) in ((-1, 0), (2, 0), (-1, 1)):
+                a = strided_image((oy, ox), t, row_bytes)
+                b = strided_image((oy, ox), t, row_bytes)
+                ref.fill(a, t)
+                oracle.fill(b, t)
+                assert (bits(a, t) == bits(b, t)).all(), "test pattern"
+                Ja = ref.fwd2(a, w, t, j_max=j, decompose_one=d1)
+                Jb = oracle.fwd2(b, w, t, j_max=j, decompose_one=d1)
+                assert Ja == Jb
+                assert (bits(a, t) == bits(b, t)).all(), describe_mismatch(b, a, t)
+                ref.inv2(a, w, t, j_max=Ja, decompose_one=d1)
+                oracle.inv2(b, w, t, j_max=Jb, decompose_one=d1)
+                assert (bits(a, t) == bits(b, t)).all(), describe_mismatch(b, a, t)
+
+
+def test_oracle_vs_reference_config_sizes(oracle, ref):
+    # BASELINE.json configs the reference can address: 4096^2 int (wrapped pattern), 2048^2 float
+    for (w, t, n) in (("53", "i", 4096), ("97", "s", 2048)):
+        a = np.zeros((n, n), dtype=DT[t])
+        b = np.zeros((n, n), dtype=DT[t])
+        ref.fill(a, t)
+        oracle.fill(b, t)
+        assert (bits(a, t) == bits(b, t)).all()
+        Ja, Jb = ref.fwd2(a, w, t), oracle.fwd2(b, w, t)
+        assert Ja == Jb and (bits(a, t) == bits(b, t)).all()
+        ref.inv2(a, w, t, j_max=Ja)
+        oracle.inv2(b, w, t, j_max=Jb)
+        assert (bits(a, t) == bits(b, t)).all()
