@@ -5,7 +5,7 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxa
 CSRC = libdwt_b200/csrc
 OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/dwtb200.o
 
-all: libdwt_b200/libdwtb200.so oracle
+all: libdwt_b200/libdwtb200.so libdwt_b200/libdwt_compat.so oracle examples
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kernels.h $(CSRC)/lifting.cuh include/dwtb200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(CSRC)/$*.ptxas.log || (cat $(CSRC)/$*.ptxas.log; false)
@@ -13,10 +13,26 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kernels.h $(CSRC)/lifting.cuh include/dwtb200.
 libdwt_b200/libdwtb200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart shared
 
+libdwt_b200/libdwt_compat.so: $(CSRC)/libdwt_compat.c include/libdwt_compat.h include/dwtb200.h libdwt_b200/libdwtb200.so
+	gcc -std=c99 -O2 -fPIC -Wall -Wextra -shared -o $@ $< -Llibdwt_b200 -ldwtb200 -Wl,-rpath,'$$ORIGIN'
+
+# The reference's UNMODIFIED example programs, compiled from where they lie and linked against the
+# B200 library first and the compiled reference (for everything outside the hot path) second.
+# Build container only (needs $(REF)); the binaries travel to the GPU box in build/ (git-ignored).
+REF ?= /root/reference
+EXAMPLES = simple simple-int simple-double
+examples: libdwt_b200/libdwt_compat.so oracle
+	@if [ -d $(REF)/examples ]; then mkdir -p build/examples; for e in $(EXAMPLES); do \
+	  src=$(REF)/examples/$$e/simple.c; \
+	  gcc -std=c99 -O2 -D_POSIX_C_SOURCE=199309L -D_GNU_SOURCE -I$(REF)/src $$src -o build/examples/$$e \
+	    -Llibdwt_b200 -ldwt_compat -ldwtb200 -Loracle/_ref -l:libdwt_ref.so -lm -lrt -fopenmp \
+	    -Wl,-rpath,'$$ORIGIN/../../libdwt_b200:$$ORIGIN/../../oracle/_ref' || exit 1; done; \
+	 else echo "examples: $(REF) absent, keeping prebuilt build/examples (if any)"; fi
+
 oracle:
 	$(MAKE) -s -C oracle
 
 clean:
-	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log libdwt_b200/libdwtb200.so
+	rm -f $(CSRC)/*.o $(CSRC)/*.ptxas.log libdwt_b200/libdwtb200.so libdwt_b200/libdwt_compat.so
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean examples

@@ -50,6 +50,8 @@ def algorithmic_bytes(w, h, j, es):
 
 
 class ClockSampler:
+    """nvidia-smi sampled every 20 ms from before the warm-up; samples whose power draw shows the GPU under
+    load (>= 60 % of the maximum seen) are the ones summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -57,7 +59,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -73,18 +75,23 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        good = []
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                good.append((float(r[0]), float(r[1]), float(r[2]), r[3:7]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+        if not good:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        pmax = max(g[2] for g in good)
+        load = [g for g in good if g[2] >= 0.6 * pmax] or good
+        reasons = set()
+        for g in load:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), g[3]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([g[0] for g in load])), "sm_max_mhz": float(max(g[1] for g in good)),
+                "reasons": sorted(reasons), "samples": len(good), "samples_under_load": len(load), "power_w_max": pmax}
 
 
 # ======================================================================================================
@@ -195,10 +202,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)   # let nvidia-smi start sampling
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     L.check(L.c.dwtb200_timer_start())
     for s in range(args.steps):
         step(count=(s == 0))
@@ -348,7 +357,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 3 if args.impl == "reference" else 20
+        args.steps = 3 if args.impl == "reference" else 100
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -65,6 +65,12 @@ int dwtb200_fwd2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, i
 int dwtb200_inv2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
                       int size_i_big_x, int size_i_big_y, int j_max, int decompose_one, int zero_padding);
 
+/* device time (CUDA events on the library stream) of the transform inside the last *_host call, in
+ * milliseconds, host<->device copies excluded; replaces dwt_util_get_clock() brackets (src/libdwt.c:18701) */
+double dwtb200_last_transform_ms(void);
+/* the *_host calls keep a device mirror per sample type between calls; this frees them */
+void dwtb200_release_host_cache(void);
+
 /* ---- device-resident images (what the roofline numbers are measured on) ---------------------------
  * A dwtb200_image is `frames` independent planes of size_o_big_x x size_o_big_y samples living in
  * HBM (two ping-pong planes plus LL scratch).  fwd2/inv2 have the semantics above, leave the result

@@ -1,0 +1,62 @@
+/*
+ * libdwt_compat.h -- the reference's own symbol names for the hot path, implemented on the B200 by
+ * libdwt_compat.so (libdwt_b200/csrc/libdwt_compat.c, plain C99) on top of the C ABI in dwtb200.h.
+ *
+ * Every prototype is the reference's, verbatim in meaning and argument order (paths relative to the
+ * libdwt tree, /root/reference/): existing programs keep including the reference's libdwt.h and are
+ * linked against libdwt_compat.so ahead of the reference library.
+ *
+ * Semantics kept: byte strides (possibly unaligned / multi-channel), outer and inner sizes, j_max in/out,
+ * decompose_one, zero_padding, symmetric boundary extension, Mallat subband layout, synchronous
+ * in-place update of the caller's host buffer, void return, errors -> message on stderr + abort()
+ * (src/libdwt.c:20410-20421, 19200-19215).  There is no CPU fallback.
+ */
+#ifndef LIBDWT_COMPAT_H
+#define LIBDWT_COMPAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/libdwt.h:562-573, 867-878 (src/libdwt.c:12776, 17040) */
+void dwt_cdf97_2f_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2i_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* src/libdwt.h:526-537, 831-842 (src/libdwt.c:12451, 16884) */
+void dwt_cdf97_2f_d(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2i_d(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* src/libdwt.h:686-697, 981-992 (src/libdwt.c:16304, 18142) */
+void dwt_cdf53_2f_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf53_2i_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+
+/* src/libdwt.h:1382-1409 (src/libdwt.c:1437, 1482): page-locked host memory instead of memalign(16, ...) */
+void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y);
+void dwt_util_free_image(void **pptr);
+
+/* src/volume.h:14-24 */
+struct volume_t {
+    int size_x, size_y, size_z;
+    size_t stride_x, stride_y, stride_z; /* sizeof(pixel), sizeof(row), sizeof(slice) */
+    void *data;
+};
+/* src/volume-dwt.h:21, 38 and the inverse (src/volume-dwt.c:727, 677, 1115) */
+void cdf97_3f_op_sep_horizontal_s(struct volume_t *src, struct volume_t *dst);
+void cdf97_3f_ip_sep_horizontal_s(struct volume_t *volume);
+void cdf97_3i_ip_sep_horizontal_s(struct volume_t *volume);
+
+/* device-event timing around the transforms (replaces dwt_util_get_clock in benchmarks, src/libdwt.c:18701):
+ * milliseconds the device spent in the last transform call, excluding host<->device copies */
+double dwt_b200_last_transform_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

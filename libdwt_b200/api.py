@@ -28,6 +28,7 @@ SYMBOLS = [
     ("dwtb200_ceil_log2", _i, [_i]), ("dwtb200_clamp_j", _i, [_i, _i, _i, _i]),
     ("dwtb200_fwd2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
     ("dwtb200_inv2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
     ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
     ("dwtb200_image_upload", _i, [_vp, _i, _vp, _i64, _i64]), ("dwtb200_image_download", _i, [_vp, _i, _vp, _i64, _i64]),
     ("dwtb200_image_fill", _i, [_vp, _i, _i, _i]),

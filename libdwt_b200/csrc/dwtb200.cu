@@ -140,6 +140,10 @@ int dwtb200_init(int device)
     if (prop.major < 10)
         return fail(DWTB200_ENODEV, "device %d is sm_%d%d; libdwtb200 is built for sm_100a only", device, prop.major, prop.minor);
     g.sm_count = prop.multiProcessorCount;
+    CK(preload_stream());
+    CK(preload_tail());
+    CK(preload_generic());
+    CK(preload_util());
     CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&g.e0));
     CK(cudaEventCreate(&g.e1));
@@ -149,10 +153,12 @@ int dwtb200_init(int device)
     return DWTB200_OK;
 }
 
+void dwtb200_release_host_cache(void);
 void dwtb200_finish(void)
 {
     if (g.dev < 0) return;
     cudaStreamSynchronize(g.st);
+    dwtb200_release_host_cache();
     if (g.flush) cudaFree(g.flush);
     if (g.stage) cudaFree(g.stage);
     g.flush = g.stage = nullptr;
@@ -693,28 +699,63 @@ double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
 // host-memory entry points with the reference's semantics
 // =====================================================================================================
 namespace {
-dwtb200_image *g_host_img = nullptr;   // cached between calls of the same shape (the reference mallocs its temps per call)
+// device mirror of the caller's host image, cached per sample type between calls of the same shape (the
+// reference mallocs its temps per call, src/libdwt.c:12801; here the planes and the captured graphs persist)
+dwtb200_image *g_host_img[3] = {nullptr, nullptr, nullptr};
+cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+float g_last_ms = -1.f;
 
 dwtb200_image *host_image(int kind, int ox, int oy)
 {
-    if (g_host_img && g_host_img->kind == kind && g_host_img->ox == ox && g_host_img->oy == oy) return g_host_img;
-    if (g_host_img) dwtb200_image_destroy(g_host_img);
-    g_host_img = dwtb200_image_create(kind, ox, oy, 1);
-    return g_host_img;
+    if (kind < 0 || kind > 2) {
+        fail(DWTB200_EINVAL, "bad kind %d", kind);
+        return nullptr;
+    }
+    dwtb200_image *&im = g_host_img[kind];
+    if (im && im->ox == ox && im->oy == oy) return im;
+    if (im) dwtb200_image_destroy(im);
+    im = dwtb200_image_create(kind, ox, oy, 1);
+    return im;
+}
+
+int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_io,
+                   int decompose_one, int zero_padding)
+{
+    dwtb200_image *im = host_image(kind, ox, oy);
+    if (!im) return DWTB200_ENOMEM;
+    if (!g_t0) {
+        CK(cudaEventCreate(&g_t0));
+        CK(cudaEventCreate(&g_t1));
+    }
+    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
+    if (r) return r;
+    CK(cudaEventRecord(g_t0, g.st));
+    r = inverse ? dwtb200_image_inv2(im, ix, iy, *j_io, decompose_one, zero_padding)
+                : dwtb200_image_fwd2(im, ix, iy, j_io, decompose_one, zero_padding);
+    if (r) return r;
+    CK(cudaEventRecord(g_t1, g.st));
+    r = dwtb200_image_download(im, 0, ptr, sx, sy);   // synchronises the stream
+    if (r) return r;
+    CK(cudaEventElapsedTime(&g_last_ms, g_t0, g_t1));
+    return DWTB200_OK;
 }
 }  // namespace
+
+double dwtb200_last_transform_ms(void) { return (double)g_last_ms; }
+void dwtb200_release_host_cache(void)
+{
+    for (int k = 0; k < 3; k++) {
+        if (g_host_img[k]) dwtb200_image_destroy(g_host_img[k]);
+        g_host_img[k] = nullptr;
+    }
+}
 
 int dwtb200_fwd2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
                       int decompose_one, int zero_padding)
 {
     NEED_DEV();
     if (!ptr || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_host: null argument");
-    dwtb200_image *im = host_image(kind, ox, oy);
-    if (!im) return DWTB200_ENOMEM;
-    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
-    if (!r) r = dwtb200_image_fwd2(im, ix, iy, j_max_ptr, decompose_one, zero_padding);
-    if (!r) r = dwtb200_image_download(im, 0, ptr, sx, sy);
-    return r;
+    return host_transform(false, kind, ptr, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one, zero_padding);
 }
 
 int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
@@ -722,12 +763,7 @@ int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int o
 {
     NEED_DEV();
     if (!ptr) return fail(DWTB200_EINVAL, "inv2_host: null argument");
-    dwtb200_image *im = host_image(kind, ox, oy);
-    if (!im) return DWTB200_ENOMEM;
-    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
-    if (!r) r = dwtb200_image_inv2(im, ix, iy, j_max, decompose_one, zero_padding);
-    if (!r) r = dwtb200_image_download(im, 0, ptr, sx, sy);
-    return r;
+    return host_transform(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
 }
 
 // =====================================================================================================

@@ -8,6 +8,12 @@
 
 namespace dwtb200 {
 
+// force-load the kernels of each translation unit (lazy loading is illegal during stream capture)
+cudaError_t preload_stream();
+cudaError_t preload_tail();
+cudaError_t preload_generic();
+cudaError_t preload_util();
+
 // ---- streaming level kernels (dense planes): one launch = one decomposition level ---------------
 // Forward: reads the level's LL input (W x H) once, writes LL' (to `ll`) and HL/LH/HH (Mallat
 // positions inside the output plane) once.  Inverse is the mirror image.

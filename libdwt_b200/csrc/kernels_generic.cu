@@ -95,6 +95,23 @@ template <class T> __global__ void __launch_bounds__(256) k_zero(ZeroParams p)
     if (zx || zy) ((T *)p.buf)[(int64_t)blockIdx.z * p.frame + (int64_t)y * p.pitch + x] = T(0);
 }
 
+template <class K> static cudaError_t touch(K kern)
+{
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kern);
+}
+cudaError_t preload_generic()
+{
+    cudaError_t e = touch(k_pass_fwd<W97F>);
+    if (e == cudaSuccess) e = touch(k_pass_fwd<W97D>);
+    if (e == cudaSuccess) e = touch(k_pass_fwd<W53I>);
+    if (e == cudaSuccess) e = touch(k_pass_inv<W97F>);
+    if (e == cudaSuccess) e = touch(k_pass_inv<W97D>);
+    if (e == cudaSuccess) e = touch(k_pass_inv<W53I>);
+    if (e == cudaSuccess) e = touch(k_zero<double>);
+    if (e == cudaSuccess) e = touch(k_zero<int32_t>);
+    return e;
+}
 static dim3 grid2(int w, int h, int frames, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, frames); }
 
 void launch_pass_fwd(int kind, const PassParams &p, int frames, cudaStream_t st)

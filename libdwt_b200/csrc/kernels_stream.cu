@@ -379,6 +379,21 @@ template <class WV, int VPL> static void go_inv(const LevelParams &p, int frames
     const dim3 grid((warps + 3) / 4, frames);
     k_inv_level<WV, VPL><<<grid, 128, 0, st>>>(p);
 }
+template <class K> static cudaError_t touch(K kern)
+{
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kern);
+}
+cudaError_t preload_stream()
+{
+    cudaError_t e = touch(k_fwd_level<W97F, 8>);
+    if (e == cudaSuccess) e = touch(k_fwd_level<W97D, 4>);
+    if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 8>);
+    if (e == cudaSuccess) e = touch(k_inv_level<W97F, 8>);
+    if (e == cudaSuccess) e = touch(k_inv_level<W97D, 4>);
+    if (e == cudaSuccess) e = touch(k_inv_level<W53I, 8>);
+    return e;
+}
 int stream_out_width(int kind) { return kind == K_CDF97_F64 ? 30 * 4 : 30 * 8; }
 
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st)

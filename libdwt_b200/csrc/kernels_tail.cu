@@ -227,27 +227,38 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(c
 
 int tail_max_elems(int kind) { return TAIL_BUF_BYTES / (kind == K_CDF97_F64 ? 8 : 4); }
 
-template <class K> static void set_smem(K kern)
+// Kernels are loaded lazily by the CUDA runtime; loading (and cudaFuncSetAttribute) is not allowed while
+// a stream is being captured, so dwtb200_init() calls this once before any graph is built.
+template <class K> static cudaError_t prep(K kern)
 {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TAIL_BUF_BYTES);
-        done = true;
-    }
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kern);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TAIL_BUF_BYTES);
+    return e;
+}
+cudaError_t preload_tail()
+{
+    cudaError_t e = prep(k_fwd_tail<W97F>);
+    if (e == cudaSuccess) e = prep(k_fwd_tail<W97D>);
+    if (e == cudaSuccess) e = prep(k_fwd_tail<W53I>);
+    if (e == cudaSuccess) e = prep(k_inv_tail<W97F>);
+    if (e == cudaSuccess) e = prep(k_inv_tail<W97D>);
+    if (e == cudaSuccess) e = prep(k_inv_tail<W53I>);
+    return e;
 }
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { set_smem(k_fwd_tail<W97F>); k_fwd_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else if (kind == K_CDF97_F64) { set_smem(k_fwd_tail<W97D>); k_fwd_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else { set_smem(k_fwd_tail<W53I>); k_fwd_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    if (kind == K_CDF97_F32) { k_fwd_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    else if (kind == K_CDF97_F64) { k_fwd_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    else { k_fwd_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
 }
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { set_smem(k_inv_tail<W97F>); k_inv_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else if (kind == K_CDF97_F64) { set_smem(k_inv_tail<W97D>); k_inv_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else { set_smem(k_inv_tail<W53I>); k_inv_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    if (kind == K_CDF97_F32) { k_inv_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    else if (kind == K_CDF97_F64) { k_inv_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    else { k_inv_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
 }
 
 }  // namespace dwtb200

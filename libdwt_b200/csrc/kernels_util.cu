@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(256) k_copy2d(T *dst, int64_t dp, const T *src
     if (x >= w || y >= h) return;
     dst[(int64_t)blockIdx.z * df + (int64_t)y * dp + x] = src[(int64_t)blockIdx.z * sf + (int64_t)y * sp + x];
 }
+cudaError_t preload_util()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, k_copy2d<double>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_copy2d<int32_t>);
+    return e;
+}
 void launch_copy2d(int es, void *dst, int64_t dp, const void *src, int64_t sp, int w, int h, int64_t df, int64_t sf,
                    int frames, cudaStream_t st)
 {

@@ -1,0 +1,73 @@
+/*
+ * libdwt_compat.c -- the reference's hot-path entry points (C99), forwarding to libdwtb200.so.
+ * See include/libdwt_compat.h for the list and the reference lines each one replaces.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/dwtb200.h"
+#include "../../include/libdwt_compat.h"
+
+/* the reference's error convention: log + abort (src/libdwt.c:20410-20421, 19200-19215) */
+static void die(const char *what, int rc)
+{
+    fprintf(stderr, "ERROR: %s failed (%d): %s\n", what, rc, dwtb200_last_error());
+    abort();
+}
+
+#define FWD(NAME, KIND)                                                                                          \
+    void NAME(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,      \
+              int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)                            \
+    {                                                                                                            \
+        const int rc = dwtb200_fwd2_host(KIND, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, \
+                                         size_i_big_y, j_max_ptr, decompose_one, zero_padding);                 \
+        if (rc) die(#NAME, rc);                                                                                  \
+    }
+#define INV(NAME, KIND)                                                                                          \
+    void NAME(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,      \
+              int size_i_big_y, int j_max, int decompose_one, int zero_padding)                                 \
+    {                                                                                                            \
+        const int rc = dwtb200_inv2_host(KIND, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, \
+                                         size_i_big_y, j_max, decompose_one, zero_padding);                     \
+        if (rc) die(#NAME, rc);                                                                                  \
+    }
+
+FWD(dwt_cdf97_2f_s, DWTB200_CDF97_F32)
+INV(dwt_cdf97_2i_s, DWTB200_CDF97_F32)
+FWD(dwt_cdf97_2f_d, DWTB200_CDF97_F64)
+INV(dwt_cdf97_2i_d, DWTB200_CDF97_F64)
+FWD(dwt_cdf53_2f_i, DWTB200_CDF53_I32)
+INV(dwt_cdf53_2i_i, DWTB200_CDF53_I32)
+
+void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y)
+{
+    (void)stride_y;
+    (void)size_o_big_x;
+    /* the reference sizes the block as stride_x * size_y in `int` (src/libdwt.c:1419); 64-bit here */
+    *pptr = dwtb200_host_alloc((size_t)stride_x * (size_t)size_o_big_y);
+    if (!*pptr) die("dwt_util_alloc_image", DWTB200_ENOMEM);
+}
+
+void dwt_util_free_image(void **pptr)
+{
+    dwtb200_host_free(*pptr);
+    *pptr = NULL;
+}
+
+void cdf97_3f_op_sep_horizontal_s(struct volume_t *src, struct volume_t *dst)
+{
+    const int rc = dwtb200_fwd3_host(src->data, src->stride_x, src->stride_y, src->stride_z, dst->data, dst->stride_x,
+                                     dst->stride_y, dst->stride_z, src->size_x, src->size_y, src->size_z);
+    if (rc) die("cdf97_3f_op_sep_horizontal_s", rc);
+}
+void cdf97_3f_ip_sep_horizontal_s(struct volume_t *v)
+{
+    cdf97_3f_op_sep_horizontal_s(v, v);
+}
+void cdf97_3i_ip_sep_horizontal_s(struct volume_t *v)
+{
+    const int rc = dwtb200_inv3_host(v->data, v->stride_x, v->stride_y, v->stride_z, v->size_x, v->size_y, v->size_z);
+    if (rc) die("cdf97_3i_ip_sep_horizontal_s", rc);
+}
+
+double dwt_b200_last_transform_ms(void) { return dwtb200_last_transform_ms(); }

@@ -51,3 +51,16 @@ def test_compute_fails_loudly_without_gpu():
         d.fwd2(img, "97", "s")
     with pytest.raises(d.DwtError):
         d.DeviceImage(d.CDF97_F32, 8, 8)
+
+
+def test_compat_library_exports_the_reference_symbols():
+    import ctypes
+    src = open(os.path.join(ROOT, "include", "libdwt_compat.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b((?:dwt_|cdf97_3)[a-z0-9_]+)\s*\(", src)))
+    assert {"dwt_cdf97_2f_s", "dwt_cdf97_2i_s", "dwt_cdf97_2f_d", "dwt_cdf97_2i_d", "dwt_cdf53_2f_i", "dwt_cdf53_2i_i",
+            "dwt_util_alloc_image", "dwt_util_free_image", "cdf97_3f_op_sep_horizontal_s",
+            "cdf97_3i_ip_sep_horizontal_s"} <= set(names)
+    so = ctypes.CDLL(os.path.join(ROOT, "libdwt_b200", "libdwt_compat.so"))
+    for n in names:
+        assert hasattr(so, n), n
