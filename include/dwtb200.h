@@ -103,6 +103,13 @@ int dwtb200_image_last_path(dwtb200_image *img);
 void dwtb200_force_generic(int on);
 /* tuning hook: output rows per strip of the streaming kernels (0 = heuristic) */
 void dwtb200_set_strip_rows(int rows);
+/* tuning hooks for the kernel selection per level (defaults in parentheses):
+ *   DWTB200_TUNE_TILE_MAX  a level with <= value samples over all frames takes the tile kernels, larger
+ *                          levels the streaming kernels (2048*2048)
+ *   DWTB200_TUNE_TAIL_MAX  the single-launch tail starts at the first level with <= value samples per
+ *                          frame (32*32; 0 disables the tail) */
+enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1 };
+int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t
  * src/volume.h:14-24: stride_x = pixel, stride_y = row, stride_z = slice, all in bytes) -------- */

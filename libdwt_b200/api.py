@@ -38,6 +38,7 @@ SYMBOLS = [
     ("dwtb200_image_copy", _i, [_vp, _vp]),
     ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
     ("dwtb200_force_generic", None, [_i]), ("dwtb200_set_strip_rows", None, [_i]),
+    ("dwtb200_set_tuning", _i, [_i, C.c_longlong]),
     ("dwtb200_fwd3_host", _i, [_vp, _sz, _sz, _sz, _vp, _sz, _sz, _sz, _i, _i, _i]),
     ("dwtb200_inv3_host", _i, [_vp, _sz, _sz, _sz, _i, _i, _i]),
     ("dwtb200_volume_create", _vp, [_i, _i, _i]), ("dwtb200_volume_destroy", None, [_vp]),

@@ -50,6 +50,12 @@ struct Ctx {
     void *stage = nullptr;   // device staging for strided repack
     size_t stage_bytes = 0;
     int sm_count = 148;
+    // tuning (dwtb200_set_tuning): a level with at most tile_max samples (all frames) takes the tile
+    // kernels instead of the streaming ones; the tail kernel starts at the first level with at most
+    // tail_max samples per frame
+    int64_t tile_max = (int64_t)2048 * 2048;
+    int tail_max = 32 * 32;
+    int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
 
 int fail(int code, const char *fmt, ...)
@@ -144,6 +150,7 @@ int dwtb200_init(int device)
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
+    CK(preload_tile());
     CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&g.e0));
     CK(cudaEventCreate(&g.e1));
@@ -211,6 +218,19 @@ int dwtb200_clamp_j(int j_max, int ox, int oy, int decompose_one)
 
 void dwtb200_force_generic(int on) { g.force_generic = on; }
 void dwtb200_set_strip_rows(int rows) { g.strip_rows = rows; }
+int dwtb200_set_tuning(int key, long long value)
+{
+    switch (key) {
+    case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
+    case DWTB200_TUNE_TAIL_MAX:
+        if (value < 0 || value > tail_max_elems(DWTB200_CDF97_F64)) return fail(DWTB200_EINVAL, "tail_max out of range");
+        g.tail_max = (int)value;
+        break;
+    default: return fail(DWTB200_EINVAL, "unknown tuning key %d", key);
+    }
+    g.epoch++;
+    return DWTB200_OK;
+}
 
 // =====================================================================================================
 // images
@@ -350,7 +370,8 @@ struct Band {   // where an LL band lives
 // take this pyramid (a level that is neither streamable nor small enough for the tail)
 int dense_tail_level(const dwtb200_image *im, int J)
 {
-    const int tmax = tail_max_elems(im->kind);
+    const int cap = tail_max_elems(im->kind);
+    const int tmax = g.tail_max < cap ? g.tail_max : cap;
     for (int j = 0; j < J; j++) {
         const int w = cdiv_pow2(im->ox, j), h = cdiv_pow2(im->oy, j);
         if ((int64_t)w * h <= tmax) return j;
@@ -436,7 +457,8 @@ int run_fwd_dense(dwtb200_image *im, int J, int jt)
         p.hh = dst_plane + ((size_t)ody * im->pitch + odx) * im->es;
         p.sub_pitch = im->pitch;
         p.sub_frame = im->frame;
-        launch_fwd_level(im->kind, p, im->frames, g.st);
+        if ((int64_t)p.W * p.H * im->frames <= g.tile_max) launch_fwd_tile(im->kind, p, im->frames, g.st);
+        else launch_fwd_level(im->kind, p, im->frames, g.st);
         g.launches++;
         in = out;
     }
@@ -482,7 +504,8 @@ int run_inv_dense(dwtb200_image *im, int J, int jt)
         p.dst = out.p;
         p.dst_pitch = out.pitch;
         p.dst_frame = out.frame;
-        launch_inv_level(im->kind, p, im->frames, g.st);
+        if ((int64_t)p.W * p.H * im->frames <= g.tile_max) launch_inv_tile(im->kind, p, im->frames, g.st);
+        else launch_inv_level(im->kind, p, im->frames, g.st);
         g.launches++;
     }
     return 0;
@@ -591,7 +614,7 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
     const int jt = dense_shape ? dense_tail_level(im, J) : -1;
     const bool dense = jt >= 0;
 
-    const dwtb200_image::Key key(inverse, ix, iy, J, zero_padding, im->cur, g.force_generic, g.strip_rows, 0);
+    const dwtb200_image::Key key(inverse, ix, iy, J, zero_padding, im->cur, g.force_generic, g.strip_rows, g.epoch);
     auto it = g.use_graph ? im->graphs.find(key) : im->graphs.end();
     if (it == im->graphs.end()) {
         g.launches = 0;

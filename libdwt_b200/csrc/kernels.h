@@ -13,6 +13,7 @@ cudaError_t preload_stream();
 cudaError_t preload_tail();
 cudaError_t preload_generic();
 cudaError_t preload_util();
+cudaError_t preload_tile();
 
 // ---- streaming level kernels (dense planes): one launch = one decomposition level ---------------
 // Forward: reads the level's LL input (W x H) once, writes LL' (to `ll`) and HL/LH/HH (Mallat
@@ -33,6 +34,9 @@ struct LevelParams {
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 int stream_out_width(int kind);   // output columns per warp
+// tile kernels (kernels_tile.cu): same LevelParams (ncg/nstrips/pps/sub_aligned unused), low latency
+void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
+void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 
 // ---- tail kernels: all remaining coarse levels of a plane inside one CTA's shared memory -----------
 struct TailParams {

@@ -96,6 +96,32 @@ def test_dense_parity(dev, oracle, kind, shape):
     report(fails)
 
 
+# kernel selection per level: (DWTB200_TUNE_TILE_MAX, DWTB200_TUNE_TAIL_MAX)
+FAMILIES = {"stream+bigtail": (0, 16384), "tile+tail": (1 << 40, 1024), "tile-only": (1 << 40, 0), "stream-only": (0, 0),
+            "tile+tinytail": (1 << 40, 16)}
+
+
+@pytest.mark.parametrize("family", list(FAMILIES), ids=list(FAMILIES))
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_every_kernel_family_gives_the_same_bits(dev, oracle, kind, family):
+    """Streaming, tile and tail kernels are interchangeable per level: force each mix."""
+    w, t = kind
+    L = dev.lib()
+    tile_max, tail_max = FAMILIES[family]
+    L.check(L.c.dwtb200_set_tuning(0, tile_max))
+    L.check(L.c.dwtb200_set_tuning(1, tail_max))
+    fails = []
+    try:
+        for (ox, oy) in ((512, 512), (517, 301), (1000, 37), (5, 1000), (241, 250), (129, 127), (64, 3), (31, 33),
+                         (1025, 1023), (2, 2), (3, 7), (65, 33), (66, 34), (63, 31)):
+            for (j, d1) in ((-1, 0), (2, 0), (-1, 1)):
+                fails += both(dev, oracle, w, t, ox, oy, j, d1)
+    finally:
+        L.check(L.c.dwtb200_set_tuning(0, 2048 * 2048))
+        L.check(L.c.dwtb200_set_tuning(1, 1024))
+    report(fails)
+
+
 @pytest.mark.parametrize("kind", KINDS, ids=KIDS)
 def test_sparse_parity(dev, oracle, kind):
     w, t = kind
