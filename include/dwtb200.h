@@ -107,8 +107,10 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_TILE_MAX  a level with <= value samples over all frames takes the tile kernels, larger
  *                          levels the streaming kernels (2048*2048)
  *   DWTB200_TUNE_TAIL_MAX  the single-launch tail starts at the first level with <= value samples per
- *                          frame (32*32; 0 disables the tail) */
-enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1 };
+ *                          frame (32*32; 0 disables the tail)
+ *   DWTB200_TUNE_MID_MAX   levels with <= value samples over all frames (and <= TILE_MAX) are fused, together
+ *                          with the tail, into ONE persistent cooperative launch (2048*2048; 0 = off) */
+enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2 };
 int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t

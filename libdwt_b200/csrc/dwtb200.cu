@@ -54,6 +54,8 @@ struct Ctx {
     // kernels instead of the streaming ones; the tail kernel starts at the first level with at most
     // tail_max samples per frame
     int64_t tile_max = (int64_t)2048 * 2048;
+    int64_t mid_max = (int64_t)2048 * 2048;   // levels this small (and <= tile_max) share ONE persistent launch; 0 = off
+    int mid_ctas_per_sm = 4;
     int tail_max = 32 * 32;
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
@@ -150,7 +152,7 @@ int dwtb200_init(int device)
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
-    CK(preload_tile());
+    CK(preload_tile(g.sm_count, g.mid_ctas_per_sm));
     CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&g.e0));
     CK(cudaEventCreate(&g.e1));
@@ -222,8 +224,9 @@ int dwtb200_set_tuning(int key, long long value)
 {
     switch (key) {
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
+    case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
     case DWTB200_TUNE_TAIL_MAX:
-        if (value < 0 || value > tail_max_elems(DWTB200_CDF97_F64)) return fail(DWTB200_EINVAL, "tail_max out of range");
+        if (value < 0 || value > tail_max_elems(DWTB200_CDF97_F32)) return fail(DWTB200_EINVAL, "tail_max out of range");
         g.tail_max = (int)value;
         break;
     default: return fail(DWTB200_EINVAL, "unknown tuning key %d", key);
@@ -366,18 +369,50 @@ struct Band {   // where an LL band lives
     int64_t pitch, frame;
 };
 
-// first level handled by the tail kernel (== J when there is none); -1 when the dense kernels cannot
-// take this pyramid (a level that is neither streamable nor small enough for the tail)
-int dense_tail_level(const dwtb200_image *im, int J)
+// ---- kernel selection for the dense path -----------------------------------------------------------
+// Level j (input w_j x h_j, all frames) is handled by
+//   STREAM  kernels_stream.cu   big, HBM-bound levels: one launch per level
+//   TILE    kernels_tile.cu     one launch per level, small tiles (only when the persistent kernel is off)
+//   MID     kernels_tile.cu     L2-resident levels: ALL of them plus the tail in ONE cooperative launch
+//   TAIL    kernels_tail.cu     every remaining level once the LL band fits one CTA's shared memory
+enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2 };
+struct DensePlan {
+    int jt;                 // first level of the tail (== J: no tail); -1: the dense kernels cannot take this pyramid
+    int jm;                 // first level of the persistent launch (== jt when it holds no tile level)
+    bool tail_in_mid;       // the tail runs inside the persistent launch
+    int type[40];
+};
+
+DensePlan dense_plan(const dwtb200_image *im, int J)
 {
-    const int cap = tail_max_elems(im->kind);
-    const int tmax = g.tail_max < cap ? g.tail_max : cap;
+    DensePlan pl;
+    const bool mid_on = g.mid_max > 0;
+    int cap = mid_on ? mid_tail_max_elems(im->kind) : tail_max_elems(im->kind);
+    if (g.tail_max < cap) cap = g.tail_max;
+    pl.jt = J;
     for (int j = 0; j < J; j++) {
         const int w = cdiv_pow2(im->ox, j), h = cdiv_pow2(im->oy, j);
-        if ((int64_t)w * h <= tmax) return j;
-        if (w < 2 || h < 2) return -1;
+        if ((int64_t)w * h <= cap) {
+            pl.jt = j;
+            break;
+        }
+        if (w < 2 || h < 2) {
+            pl.jt = -1;
+            return pl;
+        }
     }
-    return J;
+    pl.jm = pl.jt;
+    for (int j = 0; j < pl.jt; j++) {
+        const int64_t n = (int64_t)cdiv_pow2(im->ox, j) * cdiv_pow2(im->oy, j) * im->frames;
+        if (mid_on && n <= g.mid_max && n <= g.tile_max && pl.jt - j <= MID_MAX_LEVELS) {
+            pl.type[j] = PLAN_MID;
+            if (j < pl.jm) pl.jm = j;
+        } else {
+            pl.type[j] = n <= g.tile_max ? PLAN_TILE : PLAN_STREAM;
+        }
+    }
+    pl.tail_in_mid = mid_on && pl.jt < J && pl.jm < pl.jt;
+    return pl;
 }
 
 Band ll_band(const dwtb200_image *im, int j)   // LL_j = output of level j, (w_{j+1} x h_{j+1})
@@ -420,56 +455,100 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.sub_aligned = (p.nLx % vec) == 0;
 }
 
-int run_fwd_dense(dwtb200_image *im, int J, int jt)
+// parameters of forward level j reading `in` (LL_{j-1} or the source plane); returns where LL_j goes
+Band fwd_level_params(const dwtb200_image *im, int j, int J, const Band &in, char *dst_plane, LevelParams &p)
+{
+    memset(&p, 0, sizeof p);
+    level_geometry(im, j, false, p);
+    const Band out = (j == J - 1) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j);
+    p.src = in.p;
+    p.src_pitch = in.pitch;
+    p.src_frame = in.frame;
+    p.ll = out.p;
+    p.ll_pitch = out.pitch;
+    p.ll_frame = out.frame;
+    const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
+    p.hl = dst_plane + (size_t)odx * im->es;
+    p.lh = dst_plane + (size_t)ody * im->pitch * im->es;
+    p.hh = dst_plane + ((size_t)ody * im->pitch + odx) * im->es;
+    p.sub_pitch = im->pitch;
+    p.sub_frame = im->frame;
+    return out;
+}
+
+void inv_level_params(const dwtb200_image *im, int j, int J, char *src_plane, char *dst_plane, LevelParams &p)
+{
+    memset(&p, 0, sizeof p);
+    level_geometry(im, j, true, p);
+    const Band in = (j == J - 1) ? Band{src_plane, im->pitch, im->frame} : ll_band(im, j);
+    const Band out = (j == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j - 1);
+    p.ll = in.p;
+    p.ll_pitch = in.pitch;
+    p.ll_frame = in.frame;
+    const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
+    p.hl = src_plane + (size_t)odx * im->es;
+    p.lh = src_plane + (size_t)ody * im->pitch * im->es;
+    p.hh = src_plane + ((size_t)ody * im->pitch + odx) * im->es;
+    p.sub_pitch = im->pitch;
+    p.sub_frame = im->frame;
+    p.dst = out.p;
+    p.dst_pitch = out.pitch;
+    p.dst_frame = out.frame;
+}
+
+int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     Band in = {src_plane, im->pitch, im->frame};
+    auto tail_params = [&](int j, const Band &from) {
+        TailParams t;
+        t.src = from.p;
+        t.src_pitch = from.pitch;
+        t.src_frame = from.frame;
+        t.dst = dst_plane;
+        t.dst_pitch = im->pitch;
+        t.dst_frame = im->frame;
+        t.W0 = im->ox;
+        t.H0 = im->oy;
+        t.j0 = j;
+        t.j1 = J;
+        return t;
+    };
     for (int j = 0; j < J; j++) {
-        if (j == jt) {
-            TailParams t;
-            t.src = in.p;
-            t.src_pitch = in.pitch;
-            t.src_frame = in.frame;
-            t.dst = dst_plane;
-            t.dst_pitch = im->pitch;
-            t.dst_frame = im->frame;
-            t.W0 = im->ox;
-            t.H0 = im->oy;
-            t.j0 = j;
-            t.j1 = J;
-            launch_fwd_tail(im->kind, t, im->frames, g.st);
+        if (j == pl.jt) {   // stand-alone tail
+            launch_fwd_tail(im->kind, tail_params(j, in), im->frames, g.st);
+            g.launches++;
+            return 0;
+        }
+        if (pl.type[j] == PLAN_MID) {   // levels j .. jt-1 and the tail in one cooperative launch
+            MidParams mp;
+            memset(&mp, 0, sizeof mp);
+            mp.frames = im->frames;
+            mp.tail_elems = mid_tail_max_elems(im->kind);
+            for (; j < pl.jt; j++) in = fwd_level_params(im, j, J, in, dst_plane, mp.lv[mp.nlev++]);
+            if (pl.jt < J) {
+                mp.has_tail = 1;
+                mp.tail = tail_params(pl.jt, in);
+            }
+            const cudaError_t e = launch_fwd_mid(im->kind, mp, g.st);
+            if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch (forward): %s", cudaGetErrorString(e));
             g.launches++;
             return 0;
         }
         LevelParams p;
-        memset(&p, 0, sizeof p);
-        level_geometry(im, j, false, p);
-        const Band out = (j == J - 1) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j);
-        p.src = in.p;
-        p.src_pitch = in.pitch;
-        p.src_frame = in.frame;
-        p.ll = out.p;
-        p.ll_pitch = out.pitch;
-        p.ll_frame = out.frame;
-        const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
-        p.hl = dst_plane + (size_t)odx * im->es;
-        p.lh = dst_plane + (size_t)ody * im->pitch * im->es;
-        p.hh = dst_plane + ((size_t)ody * im->pitch + odx) * im->es;
-        p.sub_pitch = im->pitch;
-        p.sub_frame = im->frame;
-        if ((int64_t)p.W * p.H * im->frames <= g.tile_max) launch_fwd_tile(im->kind, p, im->frames, g.st);
+        in = fwd_level_params(im, j, J, in, dst_plane, p);
+        if (pl.type[j] == PLAN_TILE) launch_fwd_tile(im->kind, p, im->frames, g.st);
         else launch_fwd_level(im->kind, p, im->frames, g.st);
         g.launches++;
-        in = out;
     }
     return 0;
 }
 
-int run_inv_dense(dwtb200_image *im, int J, int jt)
+int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
-    int jtop = J;   // levels jtop-1 .. 0 go through the streaming kernel
-    if (jt < J) {
+    const int jt = pl.jt;
+    auto tail_params = [&]() {
         const Band out = (jt == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, jt - 1);
         TailParams t;
         t.src = src_plane;
@@ -482,29 +561,31 @@ int run_inv_dense(dwtb200_image *im, int J, int jt)
         t.H0 = im->oy;
         t.j0 = jt;
         t.j1 = J;
-        launch_inv_tail(im->kind, t, im->frames, g.st);
+        return t;
+    };
+    int jtop = jt < J ? jt : J;   // levels jtop-1 .. 0 remain after the tail
+    if (pl.jm < jt) {             // tail (if any) and levels jt-1 .. jm in one cooperative launch
+        MidParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.frames = im->frames;
+        mp.tail_elems = mid_tail_max_elems(im->kind);
+        if (jt < J) {
+            mp.has_tail = 1;
+            mp.tail = tail_params();
+        }
+        for (int j = jt - 1; j >= pl.jm; j--) inv_level_params(im, j, J, src_plane, dst_plane, mp.lv[mp.nlev++]);
+        const cudaError_t e = launch_inv_mid(im->kind, mp, g.st);
+        if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch (inverse): %s", cudaGetErrorString(e));
         g.launches++;
-        jtop = jt;
+        jtop = pl.jm;
+    } else if (jt < J) {
+        launch_inv_tail(im->kind, tail_params(), im->frames, g.st);
+        g.launches++;
     }
     for (int j = jtop - 1; j >= 0; j--) {
         LevelParams p;
-        memset(&p, 0, sizeof p);
-        level_geometry(im, j, true, p);
-        const Band in = (j == J - 1) ? Band{src_plane, im->pitch, im->frame} : ll_band(im, j);
-        const Band out = (j == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j - 1);
-        p.ll = in.p;
-        p.ll_pitch = in.pitch;
-        p.ll_frame = in.frame;
-        const int ody = cdiv_pow2(im->oy, j + 1), odx = cdiv_pow2(im->ox, j + 1);
-        p.hl = src_plane + (size_t)odx * im->es;
-        p.lh = src_plane + (size_t)ody * im->pitch * im->es;
-        p.hh = src_plane + ((size_t)ody * im->pitch + odx) * im->es;
-        p.sub_pitch = im->pitch;
-        p.sub_frame = im->frame;
-        p.dst = out.p;
-        p.dst_pitch = out.pitch;
-        p.dst_frame = out.frame;
-        if ((int64_t)p.W * p.H * im->frames <= g.tile_max) launch_inv_tile(im->kind, p, im->frames, g.st);
+        inv_level_params(im, j, J, src_plane, dst_plane, p);
+        if (pl.type[j] == PLAN_TILE) launch_inv_tile(im->kind, p, im->frames, g.st);
         else launch_inv_level(im->kind, p, im->frames, g.st);
         g.launches++;
     }
@@ -611,8 +692,10 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
     im->last_launches = 0;
     if (J == 0) return DWTB200_OK;
     const bool dense_shape = ix == im->ox && iy == im->oy && !g.force_generic;
-    const int jt = dense_shape ? dense_tail_level(im, J) : -1;
-    const bool dense = jt >= 0;
+    DensePlan pl;
+    pl.jt = -1;
+    if (dense_shape) pl = dense_plan(im, J);
+    const bool dense = pl.jt >= 0;
 
     const dwtb200_image::Key key(inverse, ix, iy, J, zero_padding, im->cur, g.force_generic, g.strip_rows, g.epoch);
     auto it = g.use_graph ? im->graphs.find(key) : im->graphs.end();
@@ -620,9 +703,9 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
         g.launches = 0;
         cudaGraph_t graph = nullptr;
         if (g.use_graph) CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
+        int rr = 0;
         if (dense) {
-            if (inverse) run_inv_dense(im, J, jt);
-            else run_fwd_dense(im, J, jt);
+            rr = inverse ? run_inv_dense(im, J, pl) : run_fwd_dense(im, J, pl);
         } else {
             if (inverse) run_inv_generic(im, ix, iy, J, zero_padding);
             else run_fwd_generic(im, ix, iy, J, zero_padding);
@@ -630,6 +713,10 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
         const cudaError_t le = cudaGetLastError();
         if (g.use_graph) {
             const cudaError_t ce = cudaStreamEndCapture(g.st, &graph);
+            if (rr) {
+                if (graph) cudaGraphDestroy(graph);
+                return rr;
+            }
             if (le != cudaSuccess || ce != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
                 return fail(DWTB200_ECUDA, "launch/capture failed: %s / %s", cudaGetErrorString(le), cudaGetErrorString(ce));
@@ -643,6 +730,7 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
             if (ie != cudaSuccess) return fail(DWTB200_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
             it = im->graphs.emplace(key, e).first;
         } else {
+            if (rr) return rr;
             if (le != cudaSuccess) return fail(DWTB200_ECUDA, "kernel launch failed: %s", cudaGetErrorString(le));
             im->last_launches = g.launches;
             im->last_path = dense ? 0 : 1;

@@ -13,8 +13,9 @@
 // 17098-17154 / 18178-18195 inverse): every sample sees "row lifting + scale, then column lifting +
 // scale" (int inverse: columns first) with whole-sample mirrored borders, so the result is
 // bit-identical to the reference whichever kernel family handles a level.
-#include "kernels.h"
-#include "lifting.cuh"
+#include <cooperative_groups.h>
+
+#include "tail_body.cuh"
 
 namespace dwtb200 {
 
@@ -28,18 +29,28 @@ template <class WV> struct TileCfg {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(const LevelParams p)
+template <class WV> struct TileSmem {
+    using T = typename WV::T;
+    using C = TileCfg<WV>;
+    static constexpr int BELEMS = (C::SH * C::TW > C::TH * C::SW) ? C::SH * C::TW : C::TH * C::SW;
+    T A[C::SH][C::SW];   // tile with halo (mirrored at the image borders)
+    T B[BELEMS];         // after the first pass
+};
+
+// one tile (bx, by) of frame bz; LD: see tail_body.cuh
+template <class WV, class LD>
+__device__ __forceinline__ void fwd_tile_body(const LevelParams &p, int bx, int by, int bz, TileSmem<WV> &sm, LD ld)
 {
     using T = typename WV::T;
     using C = TileCfg<WV>;
     constexpr int HALO = WV::HALO, TW = C::TW, TH = C::TH, SW = C::SW, SH = C::SH, WIN = 2 * HALO + 2;
-    __shared__ __align__(16) T A[SH][SW];   // input tile with halo (mirrored at the image borders)
-    __shared__ __align__(16) T B[SH][TW];   // after the row pass: [L half | H half] of every row
+    T(*A)[SW] = sm.A;
+    T(*B)[TW] = reinterpret_cast<T(*)[TW]>(sm.B);   // after the row pass: [L half | H half] of every row
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = bx * TW, y0 = by * TH;
     const int W = p.W, H = p.H;
-    const T *src = (const T *)p.src + (int64_t)blockIdx.z * p.src_frame;
+    const T *src = (const T *)p.src + (int64_t)bz * p.src_frame;
 
     const bool interior = x0 - HALO >= 0 && x0 + TW + HALO <= W && y0 - HALO >= 0 && y0 + TH + HALO <= H;
     if (interior) {
@@ -47,19 +58,19 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(c
         if constexpr (SW % PER == 0 && HALO % PER == 0) {
             for (int i = tid; i < SH * VW; i += TILE_THREADS) {
                 const int r = i / VW, v = i % VW;
-                const int4 q = __ldg(reinterpret_cast<const int4 *>(src + (int64_t)(y0 - HALO + r) * p.src_pitch + (x0 - HALO)) + v);
+                const int4 q = ld(reinterpret_cast<const int4 *>(src + (int64_t)(y0 - HALO + r) * p.src_pitch + (x0 - HALO)) + v);
                 *reinterpret_cast<int4 *>(&A[r][v * PER]) = q;
             }
         } else {
             for (int i = tid; i < SH * SW; i += TILE_THREADS) {
                 const int r = i / SW, c = i % SW;
-                A[r][c] = __ldg(src + (int64_t)(y0 - HALO + r) * p.src_pitch + (x0 - HALO + c));
+                A[r][c] = ld(src + (int64_t)(y0 - HALO + r) * p.src_pitch + (x0 - HALO + c));
             }
         }
     } else {
         for (int i = tid; i < SH * SW; i += TILE_THREADS) {
             const int r = i / SW, c = i % SW;
-            A[r][c] = __ldg(src + (int64_t)reflect(y0 - HALO + r, H) * p.src_pitch + reflect(x0 - HALO + c, W));
+            A[r][c] = ld(src + (int64_t)reflect(y0 - HALO + r, H) * p.src_pitch + reflect(x0 - HALO + c, W));
         }
     }
     __syncthreads();
@@ -78,10 +89,10 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(c
     __syncthreads();
 
     // columns: pair kk of column x <- window B[2kk .. 2kk+WIN)[x]; x < TW/2 is the L half (-> LL, LH)
-    T *ll = (T *)p.ll + (int64_t)blockIdx.z * p.ll_frame;
-    T *hl = (T *)p.hl + (int64_t)blockIdx.z * p.sub_frame;
-    T *lh = (T *)p.lh + (int64_t)blockIdx.z * p.sub_frame;
-    T *hh = (T *)p.hh + (int64_t)blockIdx.z * p.sub_frame;
+    T *ll = (T *)p.ll + (int64_t)bz * p.ll_frame;
+    T *hl = (T *)p.hl + (int64_t)bz * p.sub_frame;
+    T *lh = (T *)p.lh + (int64_t)bz * p.sub_frame;
+    T *hh = (T *)p.hh + (int64_t)bz * p.sub_frame;
     for (int i = tid; i < (TH / 2) * TW; i += TILE_THREADS) {
         const int kk = i / TW, x = i % TW;
         const bool low = x < TW / 2;
@@ -105,23 +116,23 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(c
 // =====================================================================================================
 // inverse
 // =====================================================================================================
-template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(const LevelParams p)
+template <class WV, class LD>
+__device__ __forceinline__ void inv_tile_body(const LevelParams &p, int bx, int by, int bz, TileSmem<WV> &sm, LD ld)
 {
     using T = typename WV::T;
     using C = TileCfg<WV>;
     constexpr int HALO = WV::HALO, TW = C::TW, TH = C::TH, SW = C::SW, SH = C::SH, WIN = 2 * HALO + 2;
-    constexpr int BELEMS = (SH * TW > TH * SW) ? SH * TW : TH * SW;
-    __shared__ __align__(16) T A[SH][SW];   // interleaved coefficients with halo (mirrored at the borders)
-    __shared__ __align__(16) T Bs[BELEMS];  // after the first pass
+    T(*A)[SW] = sm.A;   // interleaved coefficients with halo (mirrored at the borders)
+    T *Bs = sm.B;
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = bx * TW, y0 = by * TH;
     const int W = p.W, H = p.H;
-    const T *ll = (const T *)p.ll + (int64_t)blockIdx.z * p.ll_frame;
-    const T *hl = (const T *)p.hl + (int64_t)blockIdx.z * p.sub_frame;
-    const T *lh = (const T *)p.lh + (int64_t)blockIdx.z * p.sub_frame;
-    const T *hh = (const T *)p.hh + (int64_t)blockIdx.z * p.sub_frame;
-    T *dst = (T *)p.dst + (int64_t)blockIdx.z * p.dst_frame;
+    const T *ll = (const T *)p.ll + (int64_t)bz * p.ll_frame;
+    const T *hl = (const T *)p.hl + (int64_t)bz * p.sub_frame;
+    const T *lh = (const T *)p.lh + (int64_t)bz * p.sub_frame;
+    const T *hh = (const T *)p.hh + (int64_t)bz * p.sub_frame;
+    T *dst = (T *)p.dst + (int64_t)bz * p.dst_frame;
 
     // stage: local (r, c) <-> interleaved coefficient (y0-HALO+r, x0-HALO+c), mirrored; parity picks the
     // subband.  Consecutive threads take consecutive columns of ONE subband (coalesced).
@@ -138,7 +149,7 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(c
             base = (gx & 1) ? hl : ll;
             pitch = (gx & 1) ? p.sub_pitch : p.ll_pitch;
         }
-        A[r][c] = __ldg(base + (int64_t)(gy >> 1) * pitch + (gx >> 1));
+        A[r][c] = ld(base + (int64_t)(gy >> 1) * pitch + (gx >> 1));
     }
     __syncthreads();
 
@@ -198,6 +209,79 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(c
     }
 }
 
+// ---- stand-alone kernels: one tile per CTA ---------------------------------------------------------
+template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(const LevelParams p)
+{
+    __shared__ __align__(16) TileSmem<WV> sm;
+    fwd_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+}
+template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(const LevelParams p)
+{
+    __shared__ __align__(16) TileSmem<WV> sm;
+    inv_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+}
+
+// ---- persistent kernels: every level from the first L2-resident one to the end of the pyramid in ONE
+// cooperative launch.  A dependent kernel launch costs ~5 us on B200 however small the kernel, and the
+// last ~10 levels of an 8192^2 pyramid together hold 1.6 % of the samples: here they cost one launch,
+// with a grid-wide barrier (a few hundred ns) between levels instead.  CTAs loop over the tiles of a
+// level, synchronise, go on to the next level; the frames' tails run on one CTA each at the end (forward)
+// or the beginning (inverse).  Inputs written earlier in the same launch are read with ld.global.cg.
+template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_mid(const __grid_constant__ MidParams mp)
+{
+    using T = typename WV::T;
+    using C = TileCfg<WV>;
+    __shared__ __align__(16) TileSmem<WV> sm;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int l = 0; l < mp.nlev; l++) {
+        const LevelParams &p = mp.lv[l];
+        const int tx = (p.W + C::TW - 1) / C::TW, ty = (p.H + C::TH - 1) / C::TH;
+        const int ntiles = tx * ty * mp.frames;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int bz = t / (tx * ty), r = t % (tx * ty);
+            if (l == 0) fwd_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdNc());   // input written by an earlier launch
+            else fwd_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdCg());
+            __syncthreads();
+        }
+        if (l + 1 < mp.nlev || mp.has_tail) grid.sync();
+    }
+    if (mp.has_tail) {
+        T *bufA = reinterpret_cast<T *>(&sm), *bufB = bufA + mp.tail_elems;
+        for (int f = blockIdx.x; f < mp.frames; f += gridDim.x) {
+            if (mp.nlev) fwd_tail_body<WV>(mp.tail, f, bufA, bufB, LdCg());
+            else fwd_tail_body<WV>(mp.tail, f, bufA, bufB, LdNc());
+            __syncthreads();
+        }
+    }
+}
+template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_mid(const __grid_constant__ MidParams mp)
+{
+    using T = typename WV::T;
+    using C = TileCfg<WV>;
+    __shared__ __align__(16) TileSmem<WV> sm;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    if (mp.has_tail) {
+        T *bufA = reinterpret_cast<T *>(&sm), *bufB = bufA + mp.tail_elems;
+        for (int f = blockIdx.x; f < mp.frames; f += gridDim.x) {
+            inv_tail_body<WV>(mp.tail, f, bufA, bufB, LdNc());
+            __syncthreads();
+        }
+        if (mp.nlev) grid.sync();
+    }
+    for (int l = 0; l < mp.nlev; l++) {   // lv[] is in execution order: coarsest level first
+        const LevelParams &p = mp.lv[l];
+        const int tx = (p.W + C::TW - 1) / C::TW, ty = (p.H + C::TH - 1) / C::TH;
+        const int ntiles = tx * ty * mp.frames;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int bz = t / (tx * ty), r = t % (tx * ty);
+            // the subbands come from an earlier launch, the LL band from this one: one loader for both
+            inv_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdCg());
+            __syncthreads();
+        }
+        if (l + 1 < mp.nlev) grid.sync();
+    }
+}
+
 // ---- launchers -------------------------------------------------------------------------------
 template <class WV> static dim3 tile_grid(const LevelParams &p, int frames)
 {
@@ -216,19 +300,76 @@ void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st
     else if (kind == K_CDF97_F64) k_inv_tile<W97D><<<tile_grid<W97D>(p, frames), TILE_THREADS, 0, st>>>(p);
     else k_inv_tile<W53I><<<tile_grid<W53I>(p, frames), TILE_THREADS, 0, st>>>(p);
 }
+
+int mid_tail_max_elems(int kind)
+{
+    // the tail's two LL buffers alias the tile staging area of the persistent kernel
+    return kind == K_CDF97_F64 ? (int)(sizeof(TileSmem<W97D>) / 16) : kind == K_CDF97_F32 ? (int)(sizeof(TileSmem<W97F>) / 8)
+                                                                                          : (int)(sizeof(TileSmem<W53I>) / 8);
+}
+
+static int g_mid_ctas_per_sm[2][3];   // [inverse][kind], filled by preload_tile()
+static int g_sm_count = 0;
+
+template <class K> static cudaError_t launch_coop(K kern, const MidParams &mp, int ctas_per_sm, int work, cudaStream_t st)
+{
+    int grid = ctas_per_sm * g_sm_count;
+    if (grid > work) grid = work;
+    if (grid < 1) grid = 1;
+    void *args[] = {(void *)&mp};
+    return cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(TILE_THREADS), args, 0, st);
+}
+template <class WV> static int mid_work(const MidParams &mp)
+{
+    using C = TileCfg<WV>;
+    int work = mp.frames;
+    for (int l = 0; l < mp.nlev; l++) {
+        const int n = ((mp.lv[l].W + C::TW - 1) / C::TW) * ((mp.lv[l].H + C::TH - 1) / C::TH) * mp.frames;
+        if (n > work) work = n;
+    }
+    return work;
+}
+cudaError_t launch_fwd_mid(int kind, const MidParams &mp, cudaStream_t st)
+{
+    if (kind == K_CDF97_F32) return launch_coop(k_fwd_mid<W97F>, mp, g_mid_ctas_per_sm[0][0], mid_work<W97F>(mp), st);
+    if (kind == K_CDF97_F64) return launch_coop(k_fwd_mid<W97D>, mp, g_mid_ctas_per_sm[0][1], mid_work<W97D>(mp), st);
+    return launch_coop(k_fwd_mid<W53I>, mp, g_mid_ctas_per_sm[0][2], mid_work<W53I>(mp), st);
+}
+cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st)
+{
+    if (kind == K_CDF97_F32) return launch_coop(k_inv_mid<W97F>, mp, g_mid_ctas_per_sm[1][0], mid_work<W97F>(mp), st);
+    if (kind == K_CDF97_F64) return launch_coop(k_inv_mid<W97D>, mp, g_mid_ctas_per_sm[1][1], mid_work<W97D>(mp), st);
+    return launch_coop(k_inv_mid<W53I>, mp, g_mid_ctas_per_sm[1][2], mid_work<W53I>(mp), st);
+}
+
 template <class K> static cudaError_t touch(K kern)
 {
     cudaFuncAttributes a;
     return cudaFuncGetAttributes(&a, kern);
 }
-cudaError_t preload_tile()
+template <class K> static cudaError_t occupancy(K kern, int &out, int cap)
 {
+    cudaError_t e = touch(kern);
+    int n = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TILE_THREADS, 0);
+    out = n < cap ? n : cap;
+    return e;
+}
+cudaError_t preload_tile(int sm_count, int mid_ctas_per_sm)
+{
+    g_sm_count = sm_count;
     cudaError_t e = touch(k_fwd_tile<W97F>);
     if (e == cudaSuccess) e = touch(k_fwd_tile<W97D>);
     if (e == cudaSuccess) e = touch(k_fwd_tile<W53I>);
     if (e == cudaSuccess) e = touch(k_inv_tile<W97F>);
     if (e == cudaSuccess) e = touch(k_inv_tile<W97D>);
     if (e == cudaSuccess) e = touch(k_inv_tile<W53I>);
+    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W97F>, g_mid_ctas_per_sm[0][0], mid_ctas_per_sm);
+    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W97D>, g_mid_ctas_per_sm[0][1], mid_ctas_per_sm);
+    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W53I>, g_mid_ctas_per_sm[0][2], mid_ctas_per_sm);
+    if (e == cudaSuccess) e = occupancy(k_inv_mid<W97F>, g_mid_ctas_per_sm[1][0], mid_ctas_per_sm);
+    if (e == cudaSuccess) e = occupancy(k_inv_mid<W97D>, g_mid_ctas_per_sm[1][1], mid_ctas_per_sm);
+    if (e == cudaSuccess) e = occupancy(k_inv_mid<W53I>, g_mid_ctas_per_sm[1][2], mid_ctas_per_sm);
     return e;
 }
 

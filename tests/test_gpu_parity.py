@@ -96,9 +96,17 @@ def test_dense_parity(dev, oracle, kind, shape):
     report(fails)
 
 
-# kernel selection per level: (DWTB200_TUNE_TILE_MAX, DWTB200_TUNE_TAIL_MAX)
-FAMILIES = {"stream+bigtail": (0, 16384), "tile+tail": (1 << 40, 1024), "tile-only": (1 << 40, 0), "stream-only": (0, 0),
-            "tile+tinytail": (1 << 40, 16)}
+# kernel selection per level: (DWTB200_TUNE_TILE_MAX, DWTB200_TUNE_TAIL_MAX, DWTB200_TUNE_MID_MAX)
+BIG = 1 << 40
+FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-only": (BIG, 0, 0), "stream-only": (0, 0, 0),
+            "tile+tinytail": (BIG, 16, 0), "persistent+tail": (BIG, 1024, BIG), "persistent-notail": (BIG, 0, BIG),
+            "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256)}
+DEFAULT_TUNING = (2048 * 2048, 1024, 2048 * 2048)
+
+
+def set_tuning(L, t):
+    for key, v in zip((0, 1, 2), t):
+        L.check(L.c.dwtb200_set_tuning(key, v))
 
 
 @pytest.mark.parametrize("family", list(FAMILIES), ids=list(FAMILIES))
@@ -107,18 +115,37 @@ def test_every_kernel_family_gives_the_same_bits(dev, oracle, kind, family):
     """Streaming, tile and tail kernels are interchangeable per level: force each mix."""
     w, t = kind
     L = dev.lib()
-    tile_max, tail_max = FAMILIES[family]
-    L.check(L.c.dwtb200_set_tuning(0, tile_max))
-    L.check(L.c.dwtb200_set_tuning(1, tail_max))
+    set_tuning(L, FAMILIES[family])
     fails = []
     try:
         for (ox, oy) in ((512, 512), (517, 301), (1000, 37), (5, 1000), (241, 250), (129, 127), (64, 3), (31, 33),
                          (1025, 1023), (2, 2), (3, 7), (65, 33), (66, 34), (63, 31)):
             for (j, d1) in ((-1, 0), (2, 0), (-1, 1)):
                 fails += both(dev, oracle, w, t, ox, oy, j, d1)
+        if family.startswith("persistent"):   # batches: tiles of all frames share the persistent launch
+            img = dev.DeviceImage(dev.kind_of(w, t), 300, 260, 5)
+            img.fill(0, 0, 6)
+            J = img.fwd2()
+            nl = img.last_launches
+            for k in range(5):
+                want = oracle.fill(np.zeros((260, 300), DT[t]), t, rand=k % 6)
+                oracle.fwd2(want, w, t)
+                got = img.download(frame=k)
+                if not (bits(got, t) == bits(want, t)).all():
+                    fails.append(f"batch frame {k} forward: " + describe_mismatch(got, want, t))
+            if nl != 1:
+                fails.append(f"expected ONE launch for a 300x260 pyramid, got {nl}")
+            img.inv2(J)
+            for k in range(5):
+                want = oracle.fill(np.zeros((260, 300), DT[t]), t, rand=k % 6)
+                oracle.fwd2(want, w, t)
+                oracle.inv2(want, w, t, j_max=J)
+                got = img.download(frame=k)
+                if not (bits(got, t) == bits(want, t)).all():
+                    fails.append(f"batch frame {k} inverse: " + describe_mismatch(got, want, t))
+            img.close()
     finally:
-        L.check(L.c.dwtb200_set_tuning(0, 2048 * 2048))
-        L.check(L.c.dwtb200_set_tuning(1, 1024))
+        set_tuning(L, DEFAULT_TUNING)
     report(fails)
 
 
