@@ -176,26 +176,26 @@ def run_ours(args):
     M = args.images
 
     kinds = [(d.CDF97_F32, "97s", 4), (d.CDF53_I32, "53i", 4)]
+    # the M independent images of one sample type are ONE device-resident batch (dwtb200_image with M
+    # frames): every level of the pyramid is one launch over all frames
     imgs = {}
     for k, name, es in kinds:
-        imgs[name] = [d.DeviceImage(k, W, H) for _ in range(M)]
-        for m, im in enumerate(imgs[name]):
-            im.fill(m % 6, 0, 0)
+        imgs[name] = d.DeviceImage(k, W, H, M)
+        imgs[name].fill(0, 0, 6)
     L.check(L.c.dwtb200_sync())
 
     launches = [0]
 
     def step(count=False):
         for _, name, _ in kinds:
-            for im in imgs[name]:
-                j = im.fwd2()
-                assert j == J
-                if count:
-                    launches[0] += im.last_launches
-            for im in imgs[name]:
-                im.inv2(J)
-                if count:
-                    launches[0] += im.last_launches
+            im = imgs[name]
+            j = im.fwd2()
+            assert j == J
+            if count:
+                launches[0] += im.last_launches
+            im.inv2(J)
+            if count:
+                launches[0] += im.last_launches
 
     def barrier():
         if world > 1:
@@ -222,61 +222,80 @@ def run_ours(args):
     pix_step = 4 * M * PIX
     value = world * pix_step / (ms * 1e-3) / 1e9
 
-    # ---- per-transform breakdown (device events, same cycling of M images) ----
+    # ---- per-transform breakdown (device events): the batch of M, and a single image (frames = 1) ----
+    peak, peak_src = peaks()
     breakdown = {}
+
+    def time_dirs(im, frames, reps=5):
+        out = {}
+        tf = ti = 0.0
+        for _ in range(reps):
+            L.check(L.c.dwtb200_timer_start())
+            im.fwd2()
+            tf += L.c.dwtb200_timer_stop_ms()
+            L.check(L.c.dwtb200_timer_start())
+            im.inv2(J)
+            ti += L.c.dwtb200_timer_stop_ms()
+        for direction, t in (("fwd", tf), ("inv", ti)):
+            t = t / reps * 1e-3
+            b = algorithmic_bytes(W, H, J, 4) * frames
+            out[direction] = {"us_per_image": t / frames * 1e6, "gpixel_s": PIX * frames / t / 1e9, "gb_s": b / t / 1e9,
+                              "roofline_frac": b / t / 1e9 / peak}
+        return out
+
     for _, name, es in kinds:
-        for direction in ("fwd", "inv"):
-            # put the images into the right state first
-            if direction == "inv":
-                pass   # images hold coefficients after the forward loop below
-            L.check(L.c.dwtb200_sync())
-            reps = 3
-            tot = 0.0
-            for _ in range(reps):
-                if direction == "fwd":
-                    L.check(L.c.dwtb200_timer_start())
-                    for im in imgs[name]:
-                        im.fwd2()
-                    tot += L.c.dwtb200_timer_stop_ms()
-                    for im in imgs[name]:
-                        im.inv2(J)
-                else:
-                    for im in imgs[name]:
-                        im.fwd2()
-                    L.check(L.c.dwtb200_sync())
-                    L.check(L.c.dwtb200_timer_start())
-                    for im in imgs[name]:
-                        im.inv2(J)
-                    tot += L.c.dwtb200_timer_stop_ms()
-            t = tot / (reps * M) * 1e-3
-            b = algorithmic_bytes(W, H, J, es)
-            breakdown[f"{name}_{direction}"] = {"us": t * 1e6, "gpixel_s": PIX / t / 1e9, "gb_s": b / t / 1e9}
+        r = time_dirs(imgs[name], M)
+        breakdown[f"{name}_fwd_batch{M}"], breakdown[f"{name}_inv_batch{M}"] = r["fwd"], r["inv"]
+    for k, name, es in kinds:   # one image at a time: 3 images cycled so that none is L2-resident
+        singles = [d.DeviceImage(k, W, H, 1) for _ in range(3)]
+        for im in singles:
+            im.fill(0, 0, 0)
+            im.fwd2(); im.inv2(J)
+        L.check(L.c.dwtb200_sync())
+        tf = ti = 0.0
+        reps = 5
+        for _ in range(reps):
+            L.check(L.c.dwtb200_timer_start())
+            for im in singles:
+                im.fwd2()
+            tf += L.c.dwtb200_timer_stop_ms()
+            L.check(L.c.dwtb200_timer_start())
+            for im in singles:
+                im.inv2(J)
+            ti += L.c.dwtb200_timer_stop_ms()
+        for direction, t in (("fwd", tf), ("inv", ti)):
+            t = t / (reps * 3) * 1e-3
+            b = algorithmic_bytes(W, H, J, 4)
+            breakdown[f"{name}_{direction}_single"] = {"us_per_image": t * 1e6, "gpixel_s": PIX / t / 1e9, "gb_s": b / t / 1e9,
+                                                        "roofline_frac": b / t / 1e9 / peak, "launches": singles[0].last_launches}
+        for im in singles:
+            im.close()
 
     # ---- roofline of the dominant kernel: level 0 of the forward 9/7 float transform ----
-    # (one launch = one j_max=1 transform: reads the 8192^2 plane once, writes the four subbands once)
-    peak, peak_src = peaks()
-    ims = imgs["97s"]
-    for im in ims:
-        im.fwd2(1); im.inv2(1)
+    # one launch = one j_max=1 transform of the batch: reads M 8192^2 planes once, writes their four subbands once
+    im = imgs["97s"]
+    for _ in range(2):
+        im.fwd2(1)
     L.check(L.c.dwtb200_sync())
-    reps = 5
+    reps = 10
     L.check(L.c.dwtb200_timer_start())
     for _ in range(reps):
-        for im in ims:
-            im.fwd2(1)
-    t_fwd0 = L.c.dwtb200_timer_stop_ms() / (reps * M) * 1e-3
-    assert ims[0].last_launches == 1
-    bytes0 = 2 * 4 * PIX
-    for im in ims:            # leave the images in a defined state (coefficients of an odd number of j=1 passes are fine)
-        im.fill(0, 0, 0)
-    roof = {"bound": "hbm", "kernel": "k_fwd_level<W97F,8> (level 0 of dwt_cdf97_2f_s, 8192x8192)", "achieved": bytes0 / t_fwd0 / 1e9,
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes0 / t_fwd0 / 1e9 / peak, "traffic": None,
-            "algorithmic_bytes_per_launch": bytes0, "us_per_launch": t_fwd0 * 1e6,
-            "whole_pyramid_frac": {k: v["gb_s"] / peak for k, v in breakdown.items()}}
+        im.fwd2(1)
+    t_fwd0 = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
+    assert im.last_launches == 1
+    bytes0 = 2 * 4 * PIX * M
+    im.fill(0, 0, 6)
+    roof = {"bound": "hbm", "kernel": f"k_fwd_level<W97F,8> (level 0 of dwt_cdf97_2f_s, {M} frames of 8192x8192 per launch)",
+            "achieved": bytes0 / t_fwd0 / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "frac": bytes0 / t_fwd0 / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes0,
+            "us_per_launch": t_fwd0 * 1e6,
+            "whole_pyramid_frac": {k: v["roofline_frac"] for k, v in breakdown.items()}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get("k_fwd_level_w97f_level0_bytes")
+            per_frame = json.load(open(tr))["k_fwd_level_w97f_level0_dram_bytes_per_frame"]
+            roof["traffic"] = per_frame * M
+            roof["traffic_source"] = "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one 8192^2 frame) x frames"
         except Exception:
             pass
 
@@ -293,8 +312,7 @@ def run_ours(args):
             hp[name] = (p, arr)
         # fill host inputs by downloading the device pattern once
         for k, name, es in kinds:
-            imgs[name][0].fill(0, 0, 0)
-            imgs[name][0].download(hp[name][1])
+            imgs[name].download(hp[name][1], frame=0)
         fwd = {"97s": d.dwt_cdf97_2f_s, "53i": d.dwt_cdf53_2f_i}
         inv = {"97s": d.dwt_cdf97_2i_s, "53i": d.dwt_cdf53_2i_i}
 
@@ -336,8 +354,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": "8192x8192 full-depth (J=13) 2-D DWT, CDF 9/7 float32 + CDF 5/3 int32, forward+inverse",
                        "images_per_type_per_step": M, "transforms_per_step": 4 * M, "pixels_per_step": pix_step,
+                       "batching": f"the {M} images of a type are one device-resident batch: one kernel launch per pyramid level for all of them",
                        "pattern": "dwt_util_test_image_fill_{s,i}, rand = image index % 6",
-                       "l2": "each image is 256 MiB (> 126 MB L2) and M images are cycled: inputs larger than L2",
+                       "l2": "each batch is M x 256 MiB per plane (>> 126 MB L2): inputs larger than L2",
                        "sharding": "independent frames per GPU, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
             "breakdown": breakdown,

@@ -109,8 +109,11 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_TAIL_MAX  the single-launch tail starts at the first level with <= value samples per
  *                          frame (32*32; 0 disables the tail)
  *   DWTB200_TUNE_MID_MAX   levels with <= value samples over all frames (and <= TILE_MAX) are fused, together
- *                          with the tail, into ONE persistent cooperative launch (2048*2048; 0 = off) */
-enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2 };
+ *                          with the tail, into ONE persistent cooperative launch (0 = off: a grid-wide
+ *                          barrier measured ~5 us on B200, no better than a dependent launch)
+ *   DWTB200_TUNE_PDL       1: kernels of a pyramid are chained by programmatic dependent launch (0: measured no gain)
+ *   DWTB200_TUNE_NARROW    1: streaming kernels hold 16 instead of 32 bytes per lane: twice the warps per SM (0) */
+enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2, DWTB200_TUNE_PDL = 3, DWTB200_TUNE_NARROW = 4 };
 int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t

@@ -34,6 +34,10 @@
 
 using namespace dwtb200;
 
+namespace dwtb200 {
+int g_use_pdl = 0;
+}
+
 // ---- global context (the reference keeps process-global state too, src/libdwt.c:478-756) ----
 namespace {
 struct Ctx {
@@ -54,9 +58,10 @@ struct Ctx {
     // kernels instead of the streaming ones; the tail kernel starts at the first level with at most
     // tail_max samples per frame
     int64_t tile_max = (int64_t)2048 * 2048;
-    int64_t mid_max = (int64_t)2048 * 2048;   // levels this small (and <= tile_max) share ONE persistent launch; 0 = off
+    int64_t mid_max = 0;   // levels this small (and <= tile_max) share ONE persistent cooperative launch; 0 = off
     int mid_ctas_per_sm = 4;
     int tail_max = 32 * 32;
+    int narrow = 0;
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
 
@@ -225,6 +230,8 @@ int dwtb200_set_tuning(int key, long long value)
     switch (key) {
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
     case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
+    case DWTB200_TUNE_NARROW: g.narrow = value != 0; break;
+    case DWTB200_TUNE_PDL: dwtb200::g_use_pdl = value != 0; break;
     case DWTB200_TUNE_TAIL_MAX:
         if (value < 0 || value > tail_max_elems(DWTB200_CDF97_F32)) return fail(DWTB200_EINVAL, "tail_max out of range");
         g.tail_max = (int)value;
@@ -297,12 +304,12 @@ int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_upload: bad arguments");
     char *d = frame_ptr(im, im->cur, frame);
     if (sy == (int64_t)im->es && sx >= (int64_t)(im->ox * im->es)) {
-        CK(cudaMemcpy2DAsync(d, im->pitch * im->es, host, (size_t)sx, im->ox * im->es, im->oy, cudaMemcpyHostToDevice, g.st));
+        CK(cudaMemcpy2DAsync(d, im->pitch * im->es, host, (size_t)sx, im->ox * im->es, im->oy, cudaMemcpyDefault, g.st));
     } else {
         const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
         int r = ensure_stage(span);
         if (r) return r;
-        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyHostToDevice, g.st));
+        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
         launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 1, g.st);
         CK(cudaGetLastError());
     }
@@ -315,17 +322,17 @@ int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx,
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_download: bad arguments");
     char *d = frame_ptr(im, im->cur, frame);
     if (sy == (int64_t)im->es && sx >= (int64_t)(im->ox * im->es)) {
-        CK(cudaMemcpy2DAsync(host, (size_t)sx, d, im->pitch * im->es, im->ox * im->es, im->oy, cudaMemcpyDeviceToHost, g.st));
+        CK(cudaMemcpy2DAsync(host, (size_t)sx, d, im->pitch * im->es, im->ox * im->es, im->oy, cudaMemcpyDefault, g.st));
     } else {
         // bytes of the caller's buffer that do not belong to this image (other channels, padding) must
         // survive: stage the whole span, scatter the samples into it, copy the span back
         const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
         int r = ensure_stage(span);
         if (r) return r;
-        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyHostToDevice, g.st));
+        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
         launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 0, g.st);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(host, g.stage, span, cudaMemcpyDeviceToHost, g.st));
+        CK(cudaMemcpyAsync(host, g.stage, span, cudaMemcpyDefault, g.st));
     }
     CK(cudaStreamSynchronize(g.st));
     return DWTB200_OK;
@@ -434,7 +441,8 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.nHx = W >> 1;
     p.nLy = (H + 1) >> 1;
     p.nHy = H >> 1;
-    const int outw = stream_out_width(im->kind);
+    p.narrow = g.narrow;
+    const int outw = stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
     const int units = inverse ? (H >> 1) + 1 : p.nLy;   // row pairs to emit
     int pps;
@@ -443,16 +451,18 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     } else {
         // enough warps for ~16 per SM, but strips of at least 8 and at most 64 pairs (warm-up rows are
         // re-read per strip: 3 pairs for 9/7 forward, 4 for inverse)
-        const int64_t want = (int64_t)g.sm_count * 16;
-        const int64_t per_col = (want + (int64_t)p.ncg * im->frames - 1) / ((int64_t)p.ncg * im->frames);
+        const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow);
+        int64_t per_col = want / ((int64_t)p.ncg * im->frames);   // strips per column group: never more warps than fit at once
+        if (per_col < 1) per_col = 1;
         pps = (int)((units + per_col - 1) / per_col);
         if (pps < 8) pps = 8;
         if (pps > 64) pps = 64;
     }
     p.pps = pps;
     p.nstrips = (units + pps - 1) / pps;
-    const int vec = im->es == 8 ? 2 : 4;
+    const int vec = im->es == 8 ? 2 : (p.narrow ? 2 : 4);   // elements per subband store of a lane
     p.sub_aligned = (p.nLx % vec) == 0;
+
 }
 
 // parameters of forward level j reading `in` (LL_{j-1} or the source plane); returns where LL_j goes

@@ -30,10 +30,12 @@ struct LevelParams {
     int nstrips;          // row strips
     int pps;              // output row pairs (fwd) / iterations (inv) per strip
     int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
+    int narrow;           // 1: 16 bytes per lane instead of 32 (half the registers, twice the warps per SM)
 };
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
-int stream_out_width(int kind);   // output columns per warp
+int stream_out_width(int kind, int narrow);   // output columns per warp
+int stream_warps_per_sm(int kind, int narrow);
 // tile kernels (kernels_tile.cu): same LevelParams (ncg/nstrips/pps/sub_aligned unused), low latency
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);

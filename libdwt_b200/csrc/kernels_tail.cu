@@ -19,12 +19,14 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_fwd_tail(c
 {
     using T = typename WV::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_begin();
     fwd_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
 }
 template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(const TailParams p)
 {
     using T = typename WV::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_begin();
     inv_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
 }
 
@@ -52,16 +54,16 @@ cudaError_t preload_tail()
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { k_fwd_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else if (kind == K_CDF97_F64) { k_fwd_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else { k_fwd_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    if (kind == K_CDF97_F32) { launch_pdl(k_fwd_tail<W97F>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    else if (kind == K_CDF97_F64) { launch_pdl(k_fwd_tail<W97D>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    else { launch_pdl(k_fwd_tail<W53I>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
 }
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { k_inv_tail<W97F><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else if (kind == K_CDF97_F64) { k_inv_tail<W97D><<<frames, TAIL_THREADS, sm, st>>>(p); }
-    else { k_inv_tail<W53I><<<frames, TAIL_THREADS, sm, st>>>(p); }
+    if (kind == K_CDF97_F32) { launch_pdl(k_inv_tail<W97F>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    else if (kind == K_CDF97_F64) { launch_pdl(k_inv_tail<W97D>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    else { launch_pdl(k_inv_tail<W53I>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
 }
 
 }  // namespace dwtb200

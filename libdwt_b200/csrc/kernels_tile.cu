@@ -213,11 +213,13 @@ __device__ __forceinline__ void inv_tile_body(const LevelParams &p, int bx, int 
 template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(const LevelParams p)
 {
     __shared__ __align__(16) TileSmem<WV> sm;
+    pdl_begin();
     fwd_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
 }
 template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(const LevelParams p)
 {
     __shared__ __align__(16) TileSmem<WV> sm;
+    pdl_begin();
     inv_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
 }
 
@@ -290,15 +292,15 @@ template <class WV> static dim3 tile_grid(const LevelParams &p, int frames)
 }
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) k_fwd_tile<W97F><<<tile_grid<W97F>(p, frames), TILE_THREADS, 0, st>>>(p);
-    else if (kind == K_CDF97_F64) k_fwd_tile<W97D><<<tile_grid<W97D>(p, frames), TILE_THREADS, 0, st>>>(p);
-    else k_fwd_tile<W53I><<<tile_grid<W53I>(p, frames), TILE_THREADS, 0, st>>>(p);
+    if (kind == K_CDF97_F32) launch_pdl(k_fwd_tile<W97F>, tile_grid<W97F>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    else if (kind == K_CDF97_F64) launch_pdl(k_fwd_tile<W97D>, tile_grid<W97D>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    else launch_pdl(k_fwd_tile<W53I>, tile_grid<W53I>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
 }
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) k_inv_tile<W97F><<<tile_grid<W97F>(p, frames), TILE_THREADS, 0, st>>>(p);
-    else if (kind == K_CDF97_F64) k_inv_tile<W97D><<<tile_grid<W97D>(p, frames), TILE_THREADS, 0, st>>>(p);
-    else k_inv_tile<W53I><<<tile_grid<W53I>(p, frames), TILE_THREADS, 0, st>>>(p);
+    if (kind == K_CDF97_F32) launch_pdl(k_inv_tile<W97F>, tile_grid<W97F>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    else if (kind == K_CDF97_F64) launch_pdl(k_inv_tile<W97D>, tile_grid<W97D>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    else launch_pdl(k_inv_tile<W53I>, tile_grid<W53I>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
 }
 
 int mid_tail_max_elems(int kind)

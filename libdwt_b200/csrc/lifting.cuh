@@ -101,6 +101,31 @@ struct W53I {
     static __device__ __forceinline__ T one_i(T x) { return x; }
 };
 
+// Programmatic dependent launch: every dense-path kernel lets its successor be scheduled at once
+// (launch_dependents) and waits for its predecessor's results before touching memory (wait).  A
+// dependent launch then costs a fraction of the ~5 us of a fully serialised kernel boundary.
+__device__ __forceinline__ void pdl_begin()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+extern int g_use_pdl;   // dwtb200.cu (DWTB200_TUNE_PDL)
+
 // Whole-sample mirror of index i into [0, n), n >= 2; period 2(n-1) so windows wider than the
 // line (tiny coarse levels) fold repeatedly, exactly like the reference's N = 2, 3, 4 cases.
 __device__ __forceinline__ int reflect(int i, int n)

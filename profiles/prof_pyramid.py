@@ -11,6 +11,8 @@ kinds = sys.argv[2].split(",") if len(sys.argv) > 2 else ["97s", "53i"]
 K = {"97s": d.CDF97_F32, "53i": d.CDF53_I32, "97d": d.CDF97_F64}
 L = d.lib()
 L.init(0)
+if len(sys.argv) > 3:
+    L.check(L.c.dwtb200_set_tuning(4, int(sys.argv[3])))   # TMA fast path on/off
 for name in kinds:
     img = d.DeviceImage(K[name], n, n)
     img.fill(0, 0, 0)

@@ -101,7 +101,7 @@ BIG = 1 << 40
 FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-only": (BIG, 0, 0), "stream-only": (0, 0, 0),
             "tile+tinytail": (BIG, 16, 0), "persistent+tail": (BIG, 1024, BIG), "persistent-notail": (BIG, 0, BIG),
             "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256)}
-DEFAULT_TUNING = (2048 * 2048, 1024, 2048 * 2048)
+DEFAULT_TUNING = (2048 * 2048, 1024, 0)
 
 
 def set_tuning(L, t):
@@ -135,6 +135,9 @@ def test_every_kernel_family_gives_the_same_bits(dev, oracle, kind, family):
                     fails.append(f"batch frame {k} forward: " + describe_mismatch(got, want, t))
             if nl != 1:
                 fails.append(f"expected ONE launch for a 300x260 pyramid, got {nl}")
+            L.check(L.c.dwtb200_set_tuning(3, 0))   # and once without programmatic dependent launch
+            fails += both(dev, oracle, w, t, 517, 301, -1, 0)
+            L.check(L.c.dwtb200_set_tuning(3, 1))
             img.inv2(J)
             for k in range(5):
                 want = oracle.fill(np.zeros((260, 300), DT[t]), t, rand=k % 6)
@@ -182,12 +185,20 @@ def test_strip_boundaries(dev, oracle, kind):
     L = dev.lib()
     fails = []
     try:
-        for rows in (2, 4, 6, 16, 34, 128, 1000):
-            L.c.dwtb200_set_strip_rows(rows)
-            for (ox, oy) in ((517, 301), (300, 200), (256, 257)):
-                fails += [f"strip_rows={rows}: " + f for f in both(dev, oracle, w, t, ox, oy, -1, 0)]
+        set_tuning(L, (0, 1024, 0))   # streaming kernels on every level above the tail
+        for tma in (1, 0):            # 16 or 32 bytes per lane (DWTB200_TUNE_NARROW)
+            L.check(L.c.dwtb200_set_tuning(4, tma))
+            for rows in (2, 4, 6, 16, 34, 128, 1000):
+                L.c.dwtb200_set_strip_rows(rows)
+                for (ox, oy) in ((517, 301), (300, 200), (256, 257), (1000, 333)):
+                    fails += [f"narrow={tma} strip_rows={rows}: " + f for f in both(dev, oracle, w, t, ox, oy, -1, 0)]
+            L.c.dwtb200_set_strip_rows(0)
+            for (ox, oy) in ((2048, 1536), (1999, 1201)):
+                fails += [f"narrow={tma}: " + f for f in both(dev, oracle, w, t, ox, oy, -1, 0)]
     finally:
         L.c.dwtb200_set_strip_rows(0)
+        L.check(L.c.dwtb200_set_tuning(4, 0))
+        set_tuning(L, DEFAULT_TUNING)
     report(fails)
 
 
