@@ -84,6 +84,17 @@ int dwtb200_image_download(dwtb200_image *img, int frame, void *host, int64_t st
 /* dwt_util_test_image_fill{,2}_{s,d,i} on the device (src/libdwt.c:1247-1385); frame k uses
  * rand = (rand_mod > 0 ? k % rand_mod : rand), cf. volume_fill_s (src/volume.c:41) */
 int dwtb200_image_fill(dwtb200_image *img, int rand, int type, int rand_mod);
+/* the same with the pattern's row coordinate shifted by y_offset (a row strip of a larger image) and, with
+ * wide != 0, the products evaluated in 64 bits: the extension of the patterns to images the reference cannot
+ * address (src/libdwt.c:1154, 1216 overflow `int` from ~32768) */
+int dwtb200_image_fill_ex(dwtb200_image *img, int rand, int type, int rand_mod, int y_offset, int wide);
+/* rows [row0, row0+rows) of a frame <-> a dense buffer on the host, this device or a peer device (halo rows
+ * of a row-strip partition; replaces nothing in the reference, which has no multi-device code) */
+int dwtb200_image_copy_rows(dwtb200_image *img, int frame, int row0, int rows, void *buf, int64_t buf_pitch_bytes, int to_image);
+/* CUDA IPC handle (64 bytes) of the image's current plane, and mapping / unmapping it in another process */
+int dwtb200_image_ipc_export(dwtb200_image *img, void *handle64);
+void *dwtb200_ipc_open(const void *handle64);
+int dwtb200_ipc_close(void *ptr);
 int dwtb200_image_fwd2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one,
                        int zero_padding);
 int dwtb200_image_inv2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, int j_max, int decompose_one,

@@ -31,7 +31,9 @@ SYMBOLS = [
     ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
     ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
     ("dwtb200_image_upload", _i, [_vp, _i, _vp, _i64, _i64]), ("dwtb200_image_download", _i, [_vp, _i, _vp, _i64, _i64]),
-    ("dwtb200_image_fill", _i, [_vp, _i, _i, _i]),
+    ("dwtb200_image_fill", _i, [_vp, _i, _i, _i]), ("dwtb200_image_fill_ex", _i, [_vp, _i, _i, _i, _i, _i]),
+    ("dwtb200_image_copy_rows", _i, [_vp, _i, _i, _i, _vp, _i64, _i]),
+    ("dwtb200_image_ipc_export", _i, [_vp, _vp]), ("dwtb200_ipc_open", _vp, [_vp]), ("dwtb200_ipc_close", _i, [_vp]),
     ("dwtb200_image_fwd2", _i, [_vp, _i, _i, _ip, _i, _i]), ("dwtb200_image_inv2", _i, [_vp, _i, _i, _i, _i, _i]),
     ("dwtb200_image_devptr", _vp, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
@@ -189,8 +191,22 @@ class DeviceImage:
         self.L.check(self.L.c.dwtb200_image_download(self.h, frame, arr.ctypes.data, arr.strides[0], arr.strides[1]))
         return arr
 
-    def fill(self, rand=0, type_=0, rand_mod=0):
-        self.L.check(self.L.c.dwtb200_image_fill(self.h, rand, type_, rand_mod))
+    def fill(self, rand=0, type_=0, rand_mod=0, y_offset=0, wide=0):
+        self.L.check(self.L.c.dwtb200_image_fill_ex(self.h, rand, type_, rand_mod, y_offset, wide))
+
+    def copy_rows(self, row0, rows, buf_ptr, buf_pitch_bytes, to_image, frame=0):
+        """rows of the current plane <-> a dense buffer given by address (host, device or peer device)"""
+        self.L.check(self.L.c.dwtb200_image_copy_rows(self.h, frame, row0, rows, buf_ptr, buf_pitch_bytes, 1 if to_image else 0))
+
+    def devptr(self):
+        pitch, frame = C.c_size_t(), C.c_size_t()
+        p = self.L.c.dwtb200_image_devptr(self.h, C.byref(pitch), C.byref(frame))
+        return p, pitch.value, frame.value
+
+    def ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        self.L.check(self.L.c.dwtb200_image_ipc_export(self.h, buf))
+        return buf.raw
 
     def fwd2(self, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         iy, ix = inner if inner is not None else (self.size_y, self.size_x)

@@ -338,12 +338,56 @@ int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx,
     return DWTB200_OK;
 }
 
-int dwtb200_image_fill(dwtb200_image *im, int rnd, int type, int rand_mod)
+int dwtb200_image_fill_ex(dwtb200_image *im, int rnd, int type, int rand_mod, int y_offset, int wide)
 {
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_fill: null image");
-    launch_fill(im->kind, im->plane[im->cur], im->pitch, im->frame, im->ox, im->oy, rnd, type, rand_mod, im->frames, g.st);
+    launch_fill(im->kind, im->plane[im->cur], im->pitch, im->frame, im->ox, im->oy, rnd, type, rand_mod, im->frames, y_offset,
+                wide, g.st);
     CK(cudaGetLastError());
+    return DWTB200_OK;
+}
+int dwtb200_image_fill(dwtb200_image *im, int rnd, int type, int rand_mod) { return dwtb200_image_fill_ex(im, rnd, type, rand_mod, 0, 0); }
+
+// rows [row0, row0+rows) of one frame of the current plane <-> a dense device or host buffer (cudaMemcpyDefault):
+// the halo rows of a row-strip partition travel through this (peer-mapped pointers included)
+int dwtb200_image_copy_rows(dwtb200_image *im, int frame, int row0, int rows, void *buf, int64_t buf_pitch_bytes, int to_image)
+{
+    NEED_DEV();
+    if (!im || !buf || frame < 0 || frame >= im->frames || row0 < 0 || rows < 0 || row0 + rows > im->oy)
+        return fail(DWTB200_EINVAL, "image_copy_rows: bad arguments");
+    if (rows == 0) return DWTB200_OK;
+    char *d = (char *)im->plane[im->cur] + ((size_t)frame * im->frame + (size_t)row0 * im->pitch) * im->es;
+    if (to_image) CK(cudaMemcpy2DAsync(d, im->pitch * im->es, buf, (size_t)buf_pitch_bytes, im->ox * im->es, rows, cudaMemcpyDefault, g.st));
+    else CK(cudaMemcpy2DAsync(buf, (size_t)buf_pitch_bytes, d, im->pitch * im->es, im->ox * im->es, rows, cudaMemcpyDefault, g.st));
+    return DWTB200_OK;
+}
+
+// CUDA IPC: let another process on the same node map this image's current plane (NVLink P2P between ranks)
+int dwtb200_image_ipc_export(dwtb200_image *im, void *handle64)
+{
+    NEED_DEV();
+    if (!im || !handle64) return fail(DWTB200_EINVAL, "ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, im->plane[im->cur]));
+    return DWTB200_OK;
+}
+void *dwtb200_ipc_open(const void *handle64)
+{
+    if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
+    void *p = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fail(DWTB200_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+int dwtb200_ipc_close(void *ptr)
+{
+    NEED_DEV();
+    CK(cudaIpcCloseMemHandle(ptr));
     return DWTB200_OK;
 }
 

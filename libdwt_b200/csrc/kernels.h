@@ -90,7 +90,7 @@ void launch_zero(int kind, const ZeroParams &p, int frames, cudaStream_t st);
 // ---- utilities -------------------------------------------------------------------------------
 // test patterns of dwt_util_test_image_fill{,2}_{s,d,i}  (/root/reference/src/libdwt.c:1112-1244)
 void launch_fill(int kind, void *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type,
-                 int rnd_frame_mod, int frames, cudaStream_t st);
+                 int rnd_frame_mod, int frames, int y_offset, int wide, cudaStream_t st);
 // strided element gather/scatter between a byte-addressed staging copy of the caller's layout and a
 // dense plane (dwt_util_memcpy_stride_* semantics, src/system.c:90-180)
 void launch_repack(int elem_size, void *plane, int64_t pitch_elems, void *staged, int64_t stride_x_bytes,

@@ -11,7 +11,33 @@ namespace dwtb200 {
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
 __device__ __forceinline__ int32_t wadd32(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 
+// WIDE = true: the products are evaluated in 64 bits (no wrap): the documented extension of the patterns
+// to images the reference cannot address (>= 2 GiB, e.g. 65536^2), see oracle/dwt_oracle.c pat_*.
 template <class T> __device__ __forceinline__ T pattern(int x, int y, int rnd, int type);
+template <class T> __device__ __forceinline__ T pattern_wide(int x, int y, int rnd, int type);
+template <> __device__ __forceinline__ float pattern_wide<float>(int x, int y, int rnd, int type)
+{
+    x++;
+    y++;
+    if (type == 2) return __fdiv_rn((float)((x ^ y) & 0xff), 32.0f);
+    if (type == 3) return __fdiv_rn((float)((((x & 1) << 1) | (y & 1)) + 1), 4.0f);
+    x >>= rnd;
+    const long long num = 2ll * x * y, den = (long long)x * x + (long long)y * y + 1;
+    return __fdiv_rn(__ll2float_rn(num), __ll2float_rn(den));
+}
+template <> __device__ __forceinline__ double pattern_wide<double>(int x, int y, int rnd, int)
+{
+    x >>= rnd;
+    const long long num = 2ll * x * y, den = (long long)x * x + (long long)y * y + 1;
+    return __ddiv_rn(__ll2double_rn(num), __ll2double_rn(den));
+}
+template <> __device__ __forceinline__ int32_t pattern_wide<int32_t>(int x, int y, int rnd, int type)
+{
+    if (type == 2) return (x ^ y) & 0xff;
+    x >>= rnd;
+    const long long num = 255ll * (2ll * x * y), den = (long long)x * x + (long long)y * y + 1;
+    return (int32_t)(num / den);
+}
 template <> __device__ __forceinline__ float pattern<float>(int x, int y, int rnd, int type)
 {
     x++;
@@ -42,22 +68,24 @@ template <> __device__ __forceinline__ int32_t pattern<int32_t>(int x, int y, in
 }
 
 template <class T>
-__global__ void __launch_bounds__(256) k_fill(T *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type, int mod)
+__global__ void __launch_bounds__(256)
+k_fill(T *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type, int mod, int y_offset, int wide)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= nx || y >= ny) return;
     const int r = mod > 0 ? (int)(blockIdx.z % mod) : rnd;
-    buf[(int64_t)blockIdx.z * frame + (int64_t)y * pitch + x] = pattern<T>(x, y, r, type);
+    buf[(int64_t)blockIdx.z * frame + (int64_t)y * pitch + x] =
+        wide ? pattern_wide<T>(x, y + y_offset, r, type) : pattern<T>(x, y + y_offset, r, type);
 }
 
 void launch_fill(int kind, void *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type, int mod,
-                 int frames, cudaStream_t st)
+                 int frames, int y_offset, int wide, cudaStream_t st)
 {
     const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8, frames);
-    if (kind == K_CDF97_F32) k_fill<float><<<g, b, 0, st>>>((float *)buf, pitch, frame, nx, ny, rnd, type, mod);
-    else if (kind == K_CDF97_F64) k_fill<double><<<g, b, 0, st>>>((double *)buf, pitch, frame, nx, ny, rnd, type, mod);
-    else k_fill<int32_t><<<g, b, 0, st>>>((int32_t *)buf, pitch, frame, nx, ny, rnd, type, mod);
+    if (kind == K_CDF97_F32) k_fill<float><<<g, b, 0, st>>>((float *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
+    else if (kind == K_CDF97_F64) k_fill<double><<<g, b, 0, st>>>((double *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
+    else k_fill<int32_t><<<g, b, 0, st>>>((int32_t *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
 }
 
 // ---- repack: caller layout (arbitrary byte strides, staged verbatim on the device) <-> dense plane ----

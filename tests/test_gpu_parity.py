@@ -380,3 +380,31 @@ def test_volume_parity(dev, oracle, shape):
     v.fill()
     assert (v.download().view(np.uint32) == a.view(np.uint32)).all()
     v.close()
+
+
+# ---- row strips: all ranks emulated on one GPU (the multi-process driver is covered on CPU with gloo) ----
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_row_strip_partition_on_device(dev, oracle, kind):
+    from libdwt_b200 import strips
+    w, t = kind
+    eng = strips.NumpyEngine(lambda img, j: dev.fwd2(img, w, t, j_max=j), lambda img, j: dev.inv2(img, w, t, j_max=j))
+    for (W, H, G, Jd) in ((1024, 2048, 4, 3), (1000, 1500, 2, 2)):
+        img = oracle.fill(np.zeros((H, W), DT[t]), t)
+        want = img.copy()
+        J = oracle.fwd2(want, w, t)
+        got, J2 = strips.forward_strips_local(img, G, Jd, eng)
+        assert J == J2 and (bits(got, t) == bits(want, t)).all(), describe_mismatch(got, want, t)
+        back = strips.inverse_strips_local(want, G, Jd, eng, J)
+        oracle.inv2(want, w, t, j_max=J)
+        assert (bits(back, t) == bits(want, t)).all(), describe_mismatch(back, want, t)
+
+
+def test_wide_pattern_and_row_offset(dev, oracle):
+    """dwtb200_image_fill_ex: a strip of the 64-bit pattern equals the same rows of the oracle's 64-bit pattern."""
+    for t, k in (("s", dev.CDF97_F32), ("i", dev.CDF53_I32)):
+        full = oracle.fill(np.zeros((300, 200), DT[t]), t, wrap32=0)
+        img = dev.DeviceImage(k, 200, 100)
+        img.fill(0, 0, 0, y_offset=150, wide=1)
+        got = img.download()
+        assert (bits(got, t) == bits(full[150:250], t)).all()
+        img.close()
