@@ -1011,6 +1011,24 @@ int dwtb200_volume_fill(dwtb200_volume *v)
 
 static int volume_axes(dwtb200_volume *v, int inverse)
 {
+    if (v->nx >= 2 && v->ny >= 2 && v->nz >= 2 && !g.force_generic) {
+        // x and y fused per slice (buf[cur] -> buf[cur^1]), then z (buf[cur^1] -> buf[cur]): two passes over the volume
+        VolParams p;
+        memset(&p, 0, sizeof p);
+        p.nx = v->nx;
+        p.ny = v->ny;
+        p.nz = v->nz;
+        p.s_pitch = p.d_pitch = v->pitch;
+        p.s_slice = p.d_slice = v->slice;
+        p.src = v->buf[v->cur];
+        p.dst = v->buf[v->cur ^ 1];
+        launch_vol_xy(p, inverse, g.sm_count, g.st);
+        p.src = v->buf[v->cur ^ 1];
+        p.dst = v->buf[v->cur];
+        launch_vol_z(p, inverse, g.sm_count, g.st);
+        CK(cudaGetLastError());
+        return DWTB200_OK;
+    }
     // x, then y, then z in both directions (src/volume-dwt.c:727-770, 1115-1150); each pass is out of
     // place between the two buffers.  The reference's inverse skips an axis of size 1 (libdwt.c:17182).
     for (int axis = 0; axis < 3; axis++) {

@@ -103,6 +103,17 @@ void launch_compare(int elem_size, const void *a, const void *b, int64_t pitch, 
 void launch_volume_fill(float *buf, int64_t pitch, int64_t slice, int nx, int ny, int nz, cudaStream_t st);
 
 // ---- 3-D (one level, interleaved, in place): lifting along one axis --------------------------
+// fused 3-D passes (kernels_vol.cu): x+y per slice, then z; strides in elements
+struct VolParams {
+    const float *src;
+    float *dst;
+    int64_t s_pitch, s_slice, d_pitch, d_slice;
+    int nx, ny, nz;
+    int ncg, nstrips, pps;   // filled by the launchers
+};
+void launch_vol_xy(VolParams p, int inverse, int sm_count, cudaStream_t st);
+void launch_vol_z(VolParams p, int inverse, int sm_count, cudaStream_t st);
+
 struct Axis3Params {
     const float *src;
     float *dst;

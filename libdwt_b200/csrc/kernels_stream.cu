@@ -21,96 +21,9 @@
 //   * the next row pair is prefetched into registers while the current one is lifted.
 // Bit-exactness: every sample still sees "row lifting + scale, then column lifting + scale" in the
 // reference's operation order (int inverse: columns first), only the schedule differs.
-#include "kernels.h"
-#include "lifting.cuh"
+#include "stream_common.cuh"
 
 namespace dwtb200 {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-template <class T, int VPL> struct Row {
-    T v[VPL];
-};
-
-// ---- 16-byte vector access -----------------------------------------------------------------------
-template <class T, int N> __device__ __forceinline__ void ld_vec(const T *p, T *v)
-{
-    constexpr int BYTES = N * (int)sizeof(T);
-    static_assert(BYTES == 8 || BYTES % 16 == 0, "vector width");
-    if constexpr (BYTES == 8) {
-        const int2 r = __ldg(reinterpret_cast<const int2 *>(p));
-        *reinterpret_cast<int2 *>(v) = r;
-    } else {
-        constexpr int PER = 16 / sizeof(T);
-#pragma unroll
-        for (int i = 0; i < N / PER; i++) {
-            const int4 r = __ldg(reinterpret_cast<const int4 *>(p) + i);
-            *reinterpret_cast<int4 *>(v + i * PER) = r;
-        }
-    }
-}
-template <class T, int N> __device__ __forceinline__ void st_vec(T *p, const T *v)
-{
-    constexpr int BYTES = N * (int)sizeof(T);
-    static_assert(BYTES == 8 || BYTES % 16 == 0, "vector width");
-    if constexpr (BYTES == 8) {
-        *reinterpret_cast<int2 *>(p) = *reinterpret_cast<const int2 *>(v);
-    } else {
-        constexpr int PER = 16 / sizeof(T);
-#pragma unroll
-        for (int i = 0; i < N / PER; i++) reinterpret_cast<int4 *>(p)[i] = *reinterpret_cast<const int4 *>(v + i * PER);
-    }
-}
-
-// ---- row lifting in registers: lane holds VPL consecutive samples, v[0] at an even column ------
-template <class WV, int S, int VPL, bool INV> __device__ __forceinline__ void hstep_odd(typename WV::T (&v)[VPL])
-{
-    using T = typename WV::T;
-    const T nxt = __shfl_down_sync(FULL, v[0], 1);
-#pragma unroll
-    for (int i = 1; i < VPL; i += 2) {
-        const T r = (i + 1 < VPL) ? v[(i + 1) % VPL] : nxt;
-        v[i] = INV ? WV::template i<S>(v[i], v[i - 1], r) : WV::template f<S>(v[i], v[i - 1], r);
-    }
-}
-template <class WV, int S, int VPL, bool INV> __device__ __forceinline__ void hstep_even(typename WV::T (&v)[VPL])
-{
-    using T = typename WV::T;
-    const T prv = __shfl_up_sync(FULL, v[VPL - 1], 1);
-#pragma unroll
-    for (int i = 0; i < VPL; i += 2) {
-        const T l = i ? v[(i + VPL - 1) % VPL] : prv;
-        v[i] = INV ? WV::template i<S>(v[i], l, v[i + 1]) : WV::template f<S>(v[i], l, v[i + 1]);
-    }
-}
-template <class WV, int VPL> __device__ __forceinline__ void hfwd(typename WV::T (&v)[VPL])
-{
-    hstep_odd<WV, 0, VPL, false>(v);
-    hstep_even<WV, 1, VPL, false>(v);
-    if constexpr (WV::NS == 4) {
-        hstep_odd<WV, 2, VPL, false>(v);
-        hstep_even<WV, 3, VPL, false>(v);
-    }
-#pragma unroll
-    for (int i = 0; i < VPL; i += 2) {
-        v[i] = WV::fse(v[i]);
-        v[i + 1] = WV::fso(v[i + 1]);
-    }
-}
-template <class WV, int VPL> __device__ __forceinline__ void hinv(typename WV::T (&v)[VPL])
-{
-#pragma unroll
-    for (int i = 0; i < VPL; i += 2) {
-        v[i] = WV::ise(v[i]);
-        v[i + 1] = WV::iso(v[i + 1]);
-    }
-    hstep_even<WV, 0, VPL, true>(v);
-    hstep_odd<WV, 1, VPL, true>(v);
-    if constexpr (WV::NS == 4) {
-        hstep_even<WV, 2, VPL, true>(v);
-        hstep_odd<WV, 3, VPL, true>(v);
-    }
-}
 
 // =====================================================================================================
 // forward level

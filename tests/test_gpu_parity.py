@@ -359,7 +359,7 @@ def test_properties_at_full_size(dev):
 
 
 # ---- 3-D ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(16, 16, 16), (33, 20, 9), (64, 48, 40), (5, 5, 5), (100, 37, 21)],
+@pytest.mark.parametrize("shape", [(16, 16, 16), (33, 20, 9), (64, 48, 40), (5, 5, 5), (100, 37, 21), (520, 300, 70), (256, 257, 131)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_volume_parity(dev, oracle, shape):
     nx, ny, nz = shape
