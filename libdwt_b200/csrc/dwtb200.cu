@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <tuple>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/dwtb200.h"
@@ -62,6 +63,9 @@ struct Ctx {
     int mid_ctas_per_sm = 4;
     int tail_max = 32 * 32;
     int narrow = 0;
+    int dbg = 0;
+    int pfd = 1;
+    int pipeline = 1;   // pipelined host path for large dense images
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
 
@@ -230,6 +234,9 @@ int dwtb200_set_tuning(int key, long long value)
     switch (key) {
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
     case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
+    case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
+    case 98: g.pfd = (int)value; break;
+    case 99: g.dbg = (int)value; break;   // measurement only, see kernels.h
     case DWTB200_TUNE_NARROW: g.narrow = value != 0; break;
     case DWTB200_TUNE_PDL: dwtb200::g_use_pdl = value != 0; break;
     case DWTB200_TUNE_TAIL_MAX:
@@ -486,6 +493,8 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.nLy = (H + 1) >> 1;
     p.nHy = H >> 1;
     p.narrow = g.narrow;
+    p.dbg = g.dbg;
+    p.pfd = inverse ? 1 : g.pfd;
     const int outw = stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
     const int units = inverse ? (H >> 1) + 1 : p.nLy;   // row pairs to emit
@@ -495,7 +504,7 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     } else {
         // enough warps for ~16 per SM, but strips of at least 8 and at most 64 pairs (warm-up rows are
         // re-read per strip: 3 pairs for 9/7 forward, 4 for inverse)
-        const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow);
+        const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow, p.pfd);
         int64_t per_col = want / ((int64_t)p.ncg * im->frames);   // strips per column group: never more warps than fit at once
         if (per_col < 1) per_col = 1;
         pps = (int)((units + per_col - 1) / per_col);
@@ -550,10 +559,11 @@ void inv_level_params(const dwtb200_image *im, int j, int J, char *src_plane, ch
     p.dst_frame = out.frame;
 }
 
-int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl)
+int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     Band in = {src_plane, im->pitch, im->frame};
+    if (jstart > 0) in = ll_band(im, jstart - 1);   // levels below jstart were run by the caller (pipelined host path)
     auto tail_params = [&](int j, const Band &from) {
         TailParams t;
         t.src = from.p;
@@ -568,7 +578,7 @@ int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl)
         t.j1 = J;
         return t;
     };
-    for (int j = 0; j < J; j++) {
+    for (int j = jstart; j < J; j++) {
         if (j == pl.jt) {   // stand-alone tail
             launch_fwd_tail(im->kind, tail_params(j, in), im->frames, g.st);
             g.launches++;
@@ -598,7 +608,7 @@ int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl)
     return 0;
 }
 
-int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl)
+int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop = 0)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     const int jt = pl.jt;
@@ -636,7 +646,7 @@ int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl)
         launch_inv_tail(im->kind, tail_params(), im->frames, g.st);
         g.launches++;
     }
-    for (int j = jtop - 1; j >= 0; j--) {
+    for (int j = jtop - 1; j >= jstop; j--) {   // jstop > 0: the caller runs the levels below it (pipelined host path)
         LevelParams p;
         inv_level_params(im, j, J, src_plane, dst_plane, p);
         if (pl.type[j] == PLAN_TILE) launch_inv_tile(im->kind, p, im->frames, g.st);
@@ -883,6 +893,151 @@ dwtb200_image *host_image(int kind, int ox, int oy)
     return im;
 }
 
+// ---- pipelined host path ---------------------------------------------------------------------------------
+// A synchronous in-place call on host memory is PCIe-bound (2 x 256 MiB for an 8192^2 float image against
+// ~0.2 ms of kernels), so the large dense case overlaps the two directions of the link: level 0 is run strip
+// range by strip range while the image is still arriving, and each range's finished rows go back while the
+// next range is uploaded.  Forward: the H subbands of level 0 (3/4 of the output) leave early, then levels
+// 1..J run on the LL band and its quadrant follows.  Inverse: the LL quadrant goes first and is inverted down
+// to level 1, then the level-0 subbands arrive range by range and the reconstructed rows leave.  The call is
+// in place on the caller's buffer, so a download may only overwrite host rows whose old content has already
+// been uploaded; the waits below encode exactly that.
+struct Pipe {
+    cudaStream_t up = nullptr, dn = nullptr;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t get(size_t i)
+    {
+        while (ev.size() <= i) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            ev.push_back(e);
+        }
+        return ev[i];
+    }
+} g_pipe;
+
+bool pipeline_applies(const dwtb200_image *im, int64_t sx, int64_t sy, int ix, int iy, int J, DensePlan &pl)
+{
+    if (!g.pipeline || g.force_generic || im->frames != 1 || sy != (int64_t)im->es || ix != im->ox || iy != im->oy || J < 2) return false;
+    if ((int64_t)im->ox * im->oy * (int64_t)im->es < ((int64_t)32 << 20) || sx < (int64_t)im->ox * (int64_t)im->es) return false;
+    pl = dense_plan(im, J);
+    return pl.jt > 1 && pl.type[0] == PLAN_STREAM && pl.jm > 0;
+}
+
+int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int J, const DensePlan &pl)
+{
+    if (!g_pipe.up) {
+        CK(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_pipe.dn, cudaStreamNonBlocking));
+    }
+    const size_t es = im->es;
+    const int W = im->ox, H = im->oy;
+    const int nLx = (W + 1) >> 1, nLy = (H + 1) >> 1, nHy = H >> 1;
+    char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
+    const size_t dpitch = (size_t)im->pitch * es;
+    LevelParams lp;
+    if (inverse) inv_level_params(im, 0, J, src_plane, dst_plane, lp);
+    else fwd_level_params(im, 0, J, Band{src_plane, im->pitch, im->frame}, dst_plane, lp);
+    const int nstrips = lp.nstrips, pps = lp.pps;
+    const int nch = nstrips < 12 ? nstrips : 12;
+    auto h2d = [&](int r0, int r1, int c0, int c1, char *plane) -> cudaError_t {   // rows [r0,r1) x columns [c0,c1)
+        if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+        return cudaMemcpy2DAsync(plane + (size_t)r0 * dpitch + (size_t)c0 * es, dpitch, host + (size_t)r0 * sx + (size_t)c0 * es, (size_t)sx,
+                                 (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, g_pipe.up);
+    };
+    auto d2h = [&](int r0, int r1, int c0, int c1, char *plane) -> cudaError_t {
+        if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+        return cudaMemcpy2DAsync(host + (size_t)r0 * sx + (size_t)c0 * es, (size_t)sx, plane + (size_t)r0 * dpitch + (size_t)c0 * es, dpitch,
+                                 (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, g_pipe.dn);
+    };
+    std::vector<int> s_lo(nch + 1);
+    for (int c = 0; c <= nch; c++) s_lo[c] = (int)((int64_t)nstrips * c / nch);
+    // events: [0, nch) upload of chunk c done; [nch, 2 nch) kernel of chunk c done; 2 nch: previous work on g.st done
+    CK(cudaEventRecord(g_pipe.get(2 * nch), g.st));
+    CK(cudaStreamWaitEvent(g_pipe.up, g_pipe.get(2 * nch), 0));
+    CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(2 * nch), 0));
+    CK(cudaEventRecord(g_t0, g.st));
+
+    if (!inverse) {
+        std::vector<int> up_hi(nch);   // host rows < up_hi[c] have been uploaded once chunk c's upload is done
+        int row = 0;
+        for (int c = 0; c < nch; c++) {
+            const int k1 = std::min(s_lo[c + 1] * pps, nLy);
+            const int r1 = (c == nch - 1) ? H : std::min(H, 2 * k1 + 4);   // the range's kernel reads rows up to 2 k1 + 2
+            CK(h2d(row, r1, 0, W, src_plane));
+            row = std::max(row, r1);
+            up_hi[c] = row;
+            CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+        }
+        for (int c = 0; c < nch; c++) {
+            const int k0 = s_lo[c] * pps, k1 = std::min(s_lo[c + 1] * pps, nLy), kh = std::min(k1, nHy);
+            CK(cudaStreamWaitEvent(g.st, g_pipe.get(c), 0));
+            LevelParams q = lp;
+            q.strip0 = s_lo[c];
+            q.nstrips = s_lo[c + 1] - s_lo[c];
+            launch_fwd_level(im->kind, q, 1, g.st);
+            CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
+            CK(d2h(k0, k1, nLx, W, dst_plane));   // HL rows: these host rows were uploaded before the kernel ran
+            int cu = c;                            // LH | HH rows land in host rows [nLy + k0, nLy + kh): wait until those were uploaded
+            while (cu < nch - 1 && up_hi[cu] < nLy + kh) cu++;
+            if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(cu), 0));
+            CK(d2h(nLy + k0, nLy + kh, 0, W, dst_plane));
+        }
+        run_fwd_dense(im, J, pl, 1);   // levels 1 .. J-1 on the LL band (stream order after the last range)
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(g_t1, g.st));
+        CK(cudaStreamWaitEvent(g_pipe.dn, g_t1, 0));
+        CK(d2h(0, nLy, 0, nLx, dst_plane));
+    } else {
+        // LL quadrant first, inverted down to level 1
+        CK(h2d(0, nLy, 0, nLx, src_plane));
+        CK(cudaEventRecord(g_pipe.get(2 * nch + 1), g_pipe.up));
+        CK(cudaStreamWaitEvent(g.st, g_pipe.get(2 * nch + 1), 0));
+        run_inv_dense(im, J, pl, 1);
+        CK(cudaGetLastError());
+        const int units = (H >> 1) + 1;
+        std::vector<int> hl_hi(nch), hh_hi(nch);   // HL rows < hl_hi[c] / LH|HH rows < hh_hi[c] uploaded after chunk c
+        int a0 = 0, b0 = 0;
+        for (int c = 0; c < nch; c++) {
+            const int q1 = std::min(s_lo[c + 1] * pps, units);
+            const int a1 = (c == nch - 1) ? nLy : std::min(nLy, q1 + 2), b1 = (c == nch - 1) ? nHy : std::min(nHy, q1 + 2);
+            CK(h2d(a0, a1, nLx, W, src_plane));
+            CK(h2d(nLy + b0, nLy + b1, 0, W, src_plane));
+            a0 = std::max(a0, a1);
+            b0 = std::max(b0, b1);
+            hl_hi[c] = a0;
+            hh_hi[c] = b0;
+            CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+        }
+        for (int c = 0; c < nch; c++) {
+            const int q0 = s_lo[c] * pps, q1 = std::min(s_lo[c + 1] * pps, units);
+            CK(cudaStreamWaitEvent(g.st, g_pipe.get(c), 0));
+            LevelParams q = lp;
+            q.strip0 = s_lo[c];
+            q.nstrips = s_lo[c + 1] - s_lo[c];
+            launch_inv_level(im->kind, q, 1, g.st);
+            CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
+            const int r0 = std::max(0, 2 * q0 - 1), r1 = std::min(H, 2 * q1 - 1);   // rows this range reconstructs
+            // host row r still holds coefficients: HL row r (r < nLy) or LH|HH row r - nLy; overwrite only once uploaded
+            int cu = c;
+            while (cu < nch - 1 && (hl_hi[cu] < std::min(r1, nLy) || hh_hi[cu] < std::min(std::max(0, r1 - nLy), nHy))) cu++;
+            if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(cu), 0));
+            CK(d2h(r0, r1, 0, W, dst_plane));
+        }
+        CK(cudaEventRecord(g_t1, g.st));
+    }
+    CK(cudaStreamSynchronize(g_pipe.dn));
+    CK(cudaStreamSynchronize(g_pipe.up));
+    CK(cudaStreamSynchronize(g.st));
+    CK(cudaGetLastError());
+    CK(cudaEventElapsedTime(&g_last_ms, g_t0, g_t1));
+    im->cur ^= 1;
+    im->last_path = 0;
+    return DWTB200_OK;
+}
+
 int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_io,
                    int decompose_one, int zero_padding)
 {
@@ -891,6 +1046,14 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
     if (!g_t0) {
         CK(cudaEventCreate(&g_t0));
         CK(cudaEventCreate(&g_t1));
+    }
+    if (ix >= 1 && iy >= 1 && ix <= ox && iy <= oy) {
+        const int J = dwtb200_clamp_j(*j_io, ox, oy, decompose_one);
+        DensePlan pl;
+        if (pipeline_applies(im, sx, sy, ix, iy, J, pl)) {
+            if (!inverse) *j_io = J;
+            return host_pipelined(inverse, im, (char *)ptr, sx, J, pl);
+        }
     }
     int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
     if (r) return r;

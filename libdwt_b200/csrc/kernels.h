@@ -27,15 +27,18 @@ struct LevelParams {
     int W, H;             // size of the full-resolution side of this level
     int nLx, nHx, nLy, nHy;   // ceil/floor halves
     int ncg;              // column groups (one warp wide each)
-    int nstrips;          // row strips
+    int nstrips;          // row strips covered by this launch ...
+    int strip0;           // ... starting with this one (the host path pipelines level 0 strip range by strip range)
     int pps;              // output row pairs (fwd) / iterations (inv) per strip
     int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
+    int pfd;              // row pairs prefetched ahead in registers: 1 (4 CTAs/SM) or 2 (3 CTAs/SM)
+    int dbg;              // measurement only: 1 = no stores, 2 = no lifting arithmetic (forward streaming kernel)
     int narrow;           // 1: 16 bytes per lane instead of 32 (half the registers, twice the warps per SM)
 };
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 int stream_out_width(int kind, int narrow);   // output columns per warp
-int stream_warps_per_sm(int kind, int narrow);
+int stream_warps_per_sm(int kind, int narrow, int pfd);
 // tile kernels (kernels_tile.cu): same LevelParams (ncg/nstrips/pps/sub_aligned unused), low latency
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);

@@ -28,7 +28,8 @@ namespace dwtb200 {
 // =====================================================================================================
 // forward level
 // =====================================================================================================
-template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeof(typename WV::T) >= 32) ? 4 : 8) k_fwd_level(const LevelParams p)
+template <class WV, int VPL, int PFD = 1>
+__global__ void __launch_bounds__(128, PFD == 2 ? 3 : (VPL * sizeof(typename WV::T) >= 32) ? 4 : 8) k_fwd_level(const LevelParams p)
 {
     using T = typename WV::T;
     constexpr int OUTW = 30 * VPL, HV = VPL / 2;
@@ -36,7 +37,7 @@ template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeo
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= p.ncg * p.nstrips) return;
-    const int cg = gw % p.ncg, strip = gw / p.ncg;
+    const int cg = gw % p.ncg, strip = gw / p.ncg + p.strip0;
     const int xl = cg * OUTW - VPL + lane * VPL;   // first column held by this lane (even)
     const int k0 = strip * p.pps, k1 = min(k0 + p.pps, p.nLy);
     const int W = p.W, H = p.H;
@@ -91,6 +92,13 @@ template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeo
     hfwd<WV, VPL>(st[0]);
     load(2 * m0 + 1, na);
     load(2 * m0 + 2, nb);
+    T n2a[PFD == 2 ? VPL : 1], n2b[PFD == 2 ? VPL : 1];   // second pair in flight (PFD == 2)
+    if constexpr (PFD == 2) {
+        if (m0 < m1) {
+            load(2 * m0 + 3, n2a);
+            load(2 * m0 + 4, n2b);
+        }
+    }
 #pragma unroll
     for (int s = 1; s < NSTATE; s++)
 #pragma unroll
@@ -102,12 +110,24 @@ template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeo
             a[i] = na[i];
             b[i] = nb[i];
         }
-        if (m < m1) {   // prefetch the next pair while this one is lifted
+        if constexpr (PFD == 2) {
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                na[i] = n2a[i];
+                nb[i] = n2b[i];
+            }
+            if (m + 1 < m1) {   // two pairs ahead
+                load(2 * m + 5, n2a);
+                load(2 * m + 6, n2b);
+            }
+        } else if (m < m1) {   // prefetch the next pair while this one is lifted
             load(2 * m + 3, na);
             load(2 * m + 4, nb);
         }
-        hfwd<WV, VPL>(a);
-        hfwd<WV, VPL>(b);
+        if (p.dbg != 2) {
+            hfwd<WV, VPL>(a);
+            hfwd<WV, VPL>(b);
+        }
 
         T oL[VPL], oH[VPL];   // column-lifted low / high outputs of this iteration
 #pragma unroll
@@ -132,7 +152,15 @@ template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeo
                 st[1][i] = d1n;
             }
         }
+        if (p.dbg == 2) {
+#pragma unroll
+            for (int i = 0; i < VPL; i++) {
+                oL[i] = a[i];
+                oH[i] = b[i];
+            }
+        }
         const int kk = m - DELAY;
+        if (p.dbg == 1 && oL[0] != T(123457)) continue;   // debug: no stores (the compare keeps the arithmetic alive)
         if (kk >= k0 && producer) {
             T o[HV];
 #pragma unroll
@@ -164,7 +192,7 @@ template <class WV, int VPL> __global__ void __launch_bounds__(128, (VPL * sizeo
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= p.ncg * p.nstrips) return;
-    const int cg = gw % p.ncg, strip = gw / p.ncg;
+    const int cg = gw % p.ncg, strip = gw / p.ncg + p.strip0;
     const int xl = cg * OUTW - VPL + lane * VPL;   // first OUTPUT column of this lane (even)
     const int cb = xl >> 1;                        // first subband column
     const int W = p.W, H = p.H;
@@ -298,7 +326,8 @@ template <class WV, int VPL> static void go_fwd(const LevelParams &p, int frames
 {
     const int warps = p.ncg * p.nstrips;
     const dim3 grid((warps + 3) / 4, frames);
-    launch_pdl(k_fwd_level<WV, VPL>, grid, dim3(128), 0, st, g_use_pdl, p);
+    if (p.pfd == 2 && VPL * sizeof(typename WV::T) >= 32) launch_pdl(k_fwd_level<WV, VPL, 2>, grid, dim3(128), 0, st, g_use_pdl, p);
+    else launch_pdl(k_fwd_level<WV, VPL>, grid, dim3(128), 0, st, g_use_pdl, p);
 }
 template <class WV, int VPL> static void go_inv(const LevelParams &p, int frames, cudaStream_t st)
 {
@@ -319,6 +348,9 @@ cudaError_t preload_stream()
     if (e == cudaSuccess) e = touch(k_inv_level<W97F, 8>);
     if (e == cudaSuccess) e = touch(k_inv_level<W97D, 4>);
     if (e == cudaSuccess) e = touch(k_inv_level<W53I, 8>);
+    if (e == cudaSuccess) e = touch(k_fwd_level<W97F, 8, 2>);
+    if (e == cudaSuccess) e = touch(k_fwd_level<W97D, 4, 2>);
+    if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 8, 2>);
     if (e == cudaSuccess) e = touch(k_fwd_level<W97F, 4>);
     if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 4>);
     if (e == cudaSuccess) e = touch(k_inv_level<W97F, 4>);
@@ -328,7 +360,7 @@ cudaError_t preload_stream()
 // two widths per type: 32 bytes per lane (16 warps per SM, fewest instructions per sample) and 16 bytes
 // per lane (half the registers -> 32 warps per SM, more latency hiding); p.narrow selects
 int stream_out_width(int kind, int narrow) { return kind == K_CDF97_F64 ? 30 * 4 : (30 * 8) >> (narrow ? 1 : 0); }
-int stream_warps_per_sm(int kind, int narrow) { return (narrow && kind != K_CDF97_F64) ? 32 : 16; }
+int stream_warps_per_sm(int kind, int narrow, int pfd) { return (narrow && kind != K_CDF97_F64) ? 32 : pfd == 2 ? 12 : 16; }
 
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {

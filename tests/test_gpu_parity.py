@@ -408,3 +408,24 @@ def test_wide_pattern_and_row_offset(dev, oracle):
         got = img.download()
         assert (bits(got, t) == bits(full[150:250], t)).all()
         img.close()
+
+
+# ---- the pipelined host path (large dense images): upload / level-0 strips / download overlapped, in place ----
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_pipelined_host_path(dev, oracle, kind):
+    w, t = kind
+    L = dev.lib()
+    es = np.dtype(DT[t]).itemsize
+    shapes = [(4096, 4096), (3001, 2999), (7919, 6007), (4100, 2050)] if t != "d" else [(3001, 2999), (2200, 2100)]
+    fails = []
+    for (ox, oy) in shapes:
+        for j in (-1, 2):
+            fails += both(dev, oracle, w, t, ox, oy, j, 0)
+            assert L.c.dwtb200_last_transform_ms() > 0
+    fails += both(dev, oracle, w, t, 3001, 2999, -1, 0, row_bytes=3001 * es + 13)   # unaligned row stride
+    L.check(L.c.dwtb200_set_tuning(5, 0))   # and the plain upload -> transform -> download path at the same size
+    try:
+        fails += ["pipeline off: " + f for f in both(dev, oracle, w, t, 3001, 2999, -1, 0)]
+    finally:
+        L.check(L.c.dwtb200_set_tuning(5, 1))
+    report(fails)
