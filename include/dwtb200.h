@@ -29,7 +29,12 @@ extern "C" {
 enum {
     DWTB200_CDF97_F32 = 0, /* dwt_cdf97_2f_s / dwt_cdf97_2i_s   src/libdwt.c:12776, 17040 */
     DWTB200_CDF97_F64 = 1, /* dwt_cdf97_2f_d / dwt_cdf97_2i_d   src/libdwt.c:12451, 16884 */
-    DWTB200_CDF53_I32 = 2  /* dwt_cdf53_2f_i / dwt_cdf53_2i_i   src/libdwt.c:16304, 18142 */
+    DWTB200_CDF53_I32 = 2, /* dwt_cdf53_2f_i / dwt_cdf53_2i_i   src/libdwt.c:16304, 18142 */
+    /* sibling drivers sharing the same kernels */
+    DWTB200_CDF53_F32 = 3, /* dwt_cdf53_2f_s / dwt_cdf53_2i_s   src/libdwt.c:16470, 18296 */
+    DWTB200_CDF53_F64 = 4, /* dwt_cdf53_2f_d / dwt_cdf53_2i_d   src/libdwt.c:12535, 16962 */
+    DWTB200_CDF97_I32 = 5, /* dwt_cdf97_2f_i / dwt_cdf97_2i_i   src/libdwt.c:16387, 18219 (9/7 with integer lifting) */
+    DWTB200_KIND_COUNT = 6
 };
 
 enum {

@@ -37,6 +37,22 @@ void dwt_cdf53_2f_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int
 void dwt_cdf53_2i_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                     int size_i_big_y, int j_max, int decompose_one, int zero_padding);
 
+/* sibling drivers sharing the same kernels.  CDF 5/3 float: src/libdwt.h:722-733, 1053-1064 (src/libdwt.c:16470, 18296) */
+void dwt_cdf53_2f_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf53_2i_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* CDF 5/3 double: src/libdwt.h:544-555, 849-860 (src/libdwt.c:12535, 16962) */
+void dwt_cdf53_2f_d(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf53_2i_d(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* CDF 9/7 with integer lifting: src/libdwt.h:704-715, 999-1010 (src/libdwt.c:16387, 18219) */
+void dwt_cdf97_2f_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2i_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                    int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+
 /* src/libdwt.h:1382-1409 (src/libdwt.c:1437, 1482): page-locked host memory instead of memalign(16, ...) */
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y);
 void dwt_util_free_image(void **pptr);

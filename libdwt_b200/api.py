@@ -14,9 +14,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libdwtb200.so")
 
-CDF97_F32, CDF97_F64, CDF53_I32 = 0, 1, 2
-_DT = {CDF97_F32: np.float32, CDF97_F64: np.float64, CDF53_I32: np.int32}
-_KIND = {("97", "s"): CDF97_F32, ("97", "d"): CDF97_F64, ("53", "i"): CDF53_I32}
+CDF97_F32, CDF97_F64, CDF53_I32, CDF53_F32, CDF53_F64, CDF97_I32 = 0, 1, 2, 3, 4, 5
+_DT = {CDF97_F32: np.float32, CDF97_F64: np.float64, CDF53_I32: np.int32,
+       CDF53_F32: np.float32, CDF53_F64: np.float64, CDF97_I32: np.int32}
+_KIND = {("97", "s"): CDF97_F32, ("97", "d"): CDF97_F64, ("53", "i"): CDF53_I32,
+         ("53", "s"): CDF53_F32, ("53", "d"): CDF53_F64, ("97", "i"): CDF97_I32}
 
 # every symbol include/dwtb200.h declares: (name, restype, argtypes)
 _i, _i64, _vp, _sz, _dbl = C.c_int, C.c_int64, C.c_void_p, C.c_size_t, C.c_double
@@ -124,6 +126,12 @@ def dwt_cdf97_2f_d(*a): _fwd(CDF97_F64, *a)
 def dwt_cdf97_2i_d(*a): _inv(CDF97_F64, *a)
 def dwt_cdf53_2f_i(*a): _fwd(CDF53_I32, *a)
 def dwt_cdf53_2i_i(*a): _inv(CDF53_I32, *a)
+def dwt_cdf53_2f_s(*a): _fwd(CDF53_F32, *a)
+def dwt_cdf53_2i_s(*a): _inv(CDF53_F32, *a)
+def dwt_cdf53_2f_d(*a): _fwd(CDF53_F64, *a)
+def dwt_cdf53_2i_d(*a): _inv(CDF53_F64, *a)
+def dwt_cdf97_2f_i(*a): _fwd(CDF97_I32, *a)
+def dwt_cdf97_2i_i(*a): _inv(CDF97_I32, *a)
 
 
 # ---- numpy conveniences with the calling shape of oracle/orc.py (images are [y, x] arrays) ----

@@ -32,6 +32,7 @@
 
 #include "../../include/dwtb200.h"
 #include "kernels.h"
+#include "lifting.cuh"
 
 using namespace dwtb200;
 
@@ -86,9 +87,10 @@ int fail(int code, const char *fmt, ...)
 
 inline int cdiv_pow2(int v, int j) { return (int)(((int64_t)v + ((int64_t)1 << j) - 1) >> j); }
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-inline size_t esize(int kind) { return kind == DWTB200_CDF97_F64 ? 8 : 4; }
-inline bool guard(int kind) { return kind == DWTB200_CDF97_F32; }            // src/libdwt.c:12837
-inline bool inv_cols_first(int kind) { return kind == DWTB200_CDF53_I32; }   // src/libdwt.c:18178
+inline size_t esize(int kind) { return (size_t)kind_elem_size(kind); }
+inline bool guard(int kind) { return kind == DWTB200_CDF97_F32; }            // src/libdwt.c:12837 (no other driver tests `lines > 1`)
+inline bool inv_cols_first(int kind) { return kind == DWTB200_CDF53_I32 || kind == DWTB200_CDF97_I32; }   // src/libdwt.c:18178, 18256
+inline bool kind_ok(int kind) { return kind >= 0 && kind < DWTB200_KIND_COUNT; }
 
 int ensure_stage(size_t bytes)
 {
@@ -255,7 +257,7 @@ int dwtb200_set_tuning(int key, long long value)
 dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
 {
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
-    if (kind < 0 || kind > 2 || ox < 1 || oy < 1 || frames < 1) {
+    if (!kind_ok(kind) || ox < 1 || oy < 1 || frames < 1) {
         fail(DWTB200_EINVAL, "image_create: bad arguments");
         return nullptr;
     }
@@ -836,7 +838,7 @@ int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
     if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
     cudaMemsetAsync(d, 0, 16, g.st);
     launch_compare((int)a->es, a->plane[a->cur], b->plane[b->cur], a->pitch, a->frame, a->ox, a->oy, a->frames,
-                   a->kind == DWTB200_CDF97_F64 ? 2 : a->kind == DWTB200_CDF97_F32 ? 1 : 0, d, g.st);
+                   kind_elem_class(a->kind), d, g.st);
     cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, g.st);
     const cudaError_t e = cudaStreamSynchronize(g.st);
     cudaFree(d);
@@ -857,7 +859,7 @@ double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
     if (cudaMalloc(&d, 16) != cudaSuccess) return -1.0;
     cudaMemsetAsync(d, 0, 16, g.st);
     launch_compare((int)a->es, a->plane[a->cur], b->plane[b->cur], a->pitch, a->frame, a->ox, a->oy, a->frames,
-                   a->kind == DWTB200_CDF97_F64 ? 2 : a->kind == DWTB200_CDF97_F32 ? 1 : 0, d, g.st);
+                   kind_elem_class(a->kind), d, g.st);
     cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, g.st);
     const cudaError_t e = cudaStreamSynchronize(g.st);
     cudaFree(d);
@@ -876,13 +878,13 @@ double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
 namespace {
 // device mirror of the caller's host image, cached per sample type between calls of the same shape (the
 // reference mallocs its temps per call, src/libdwt.c:12801; here the planes and the captured graphs persist)
-dwtb200_image *g_host_img[3] = {nullptr, nullptr, nullptr};
+dwtb200_image *g_host_img[DWTB200_KIND_COUNT] = {};
 cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 float g_last_ms = -1.f;
 
 dwtb200_image *host_image(int kind, int ox, int oy)
 {
-    if (kind < 0 || kind > 2) {
+    if (!kind_ok(kind)) {
         fail(DWTB200_EINVAL, "bad kind %d", kind);
         return nullptr;
     }
@@ -1072,7 +1074,7 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
 double dwtb200_last_transform_ms(void) { return (double)g_last_ms; }
 void dwtb200_release_host_cache(void)
 {
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < DWTB200_KIND_COUNT; k++) {
         if (g_host_img[k]) dwtb200_image_destroy(g_host_img[k]);
         g_host_img[k] = nullptr;
     }

@@ -102,12 +102,13 @@ template <class K> static cudaError_t touch(K kern)
 }
 cudaError_t preload_generic()
 {
-    cudaError_t e = touch(k_pass_fwd<W97F>);
-    if (e == cudaSuccess) e = touch(k_pass_fwd<W97D>);
-    if (e == cudaSuccess) e = touch(k_pass_fwd<W53I>);
-    if (e == cudaSuccess) e = touch(k_pass_inv<W97F>);
-    if (e == cudaSuccess) e = touch(k_pass_inv<W97D>);
-    if (e == cudaSuccess) e = touch(k_pass_inv<W53I>);
+    cudaError_t e = cudaSuccess;
+    for (int kind = 0; kind < K_COUNT; kind++)
+        dispatch_kind(kind, [&](auto wv) {
+            using WV = decltype(wv);
+            if (e == cudaSuccess) e = touch(k_pass_fwd<WV>);
+            if (e == cudaSuccess) e = touch(k_pass_inv<WV>);
+        });
     if (e == cudaSuccess) e = touch(k_zero<double>);
     if (e == cudaSuccess) e = touch(k_zero<int32_t>);
     return e;
@@ -118,23 +119,19 @@ void launch_pass_fwd(int kind, const PassParams &p, int frames, cudaStream_t st)
 {
     if (p.region_w <= 0 || p.region_h <= 0) return;
     const dim3 b(32, 8), g = grid2(p.region_w, p.region_h, frames, b);
-    if (kind == K_CDF97_F32) k_pass_fwd<W97F><<<g, b, 0, st>>>(p);
-    else if (kind == K_CDF97_F64) k_pass_fwd<W97D><<<g, b, 0, st>>>(p);
-    else k_pass_fwd<W53I><<<g, b, 0, st>>>(p);
+    dispatch_kind(kind, [&](auto wv) { k_pass_fwd<decltype(wv)><<<g, b, 0, st>>>(p); });
 }
 void launch_pass_inv(int kind, const PassParams &p, int frames, cudaStream_t st)
 {
     if (p.region_w <= 0 || p.region_h <= 0) return;
     const dim3 b(32, 8), g = grid2(p.region_w, p.region_h, frames, b);
-    if (kind == K_CDF97_F32) k_pass_inv<W97F><<<g, b, 0, st>>>(p);
-    else if (kind == K_CDF97_F64) k_pass_inv<W97D><<<g, b, 0, st>>>(p);
-    else k_pass_inv<W53I><<<g, b, 0, st>>>(p);
+    dispatch_kind(kind, [&](auto wv) { k_pass_inv<decltype(wv)><<<g, b, 0, st>>>(p); });
 }
 void launch_zero(int kind, const ZeroParams &p, int frames, cudaStream_t st)
 {
     if (p.region_w <= 0 || p.region_h <= 0) return;
     const dim3 b(32, 8), g = grid2(p.region_w, p.region_h, frames, b);
-    if (kind == K_CDF97_F64) k_zero<double><<<g, b, 0, st>>>(p);
+    if (kind_elem_size(kind) == 8) k_zero<double><<<g, b, 0, st>>>(p);
     else k_zero<int32_t><<<g, b, 0, st>>>(p);   // float 0.0f and int 0 share a bit pattern
 }
 

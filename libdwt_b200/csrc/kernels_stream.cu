@@ -342,49 +342,40 @@ template <class K> static cudaError_t touch(K kern)
 }
 cudaError_t preload_stream()
 {
-    cudaError_t e = touch(k_fwd_level<W97F, 8>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W97D, 4>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 8>);
-    if (e == cudaSuccess) e = touch(k_inv_level<W97F, 8>);
-    if (e == cudaSuccess) e = touch(k_inv_level<W97D, 4>);
-    if (e == cudaSuccess) e = touch(k_inv_level<W53I, 8>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W97F, 8, 2>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W97D, 4, 2>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 8, 2>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W97F, 4>);
-    if (e == cudaSuccess) e = touch(k_fwd_level<W53I, 4>);
-    if (e == cudaSuccess) e = touch(k_inv_level<W97F, 4>);
-    if (e == cudaSuccess) e = touch(k_inv_level<W53I, 4>);
+    cudaError_t e = cudaSuccess;
+    for (int kind = 0; kind < K_COUNT; kind++)
+        dispatch_kind(kind, [&](auto wv) {
+            using WV = decltype(wv);
+            constexpr int V = 32 / (int)sizeof(typename WV::T);
+            if (e == cudaSuccess) e = touch(k_fwd_level<WV, V>);
+            if (e == cudaSuccess) e = touch(k_inv_level<WV, V>);
+            if (e == cudaSuccess) e = touch(k_fwd_level<WV, V, 2>);
+            if (e == cudaSuccess) e = touch(k_fwd_level<WV, 4>);
+            if (e == cudaSuccess) e = touch(k_inv_level<WV, 4>);
+        });
     return e;
 }
 // two widths per type: 32 bytes per lane (16 warps per SM, fewest instructions per sample) and 16 bytes
-// per lane (half the registers -> 32 warps per SM, more latency hiding); p.narrow selects
-int stream_out_width(int kind, int narrow) { return kind == K_CDF97_F64 ? 30 * 4 : (30 * 8) >> (narrow ? 1 : 0); }
-int stream_warps_per_sm(int kind, int narrow, int pfd) { return (narrow && kind != K_CDF97_F64) ? 32 : pfd == 2 ? 12 : 16; }
+// per lane (half the registers -> 32 warps per SM, more latency hiding); p.narrow selects.  8-byte samples
+// always take 4 per lane (a lane must hold >= HALO samples).
+int stream_out_width(int kind, int narrow) { return kind_elem_size(kind) == 8 ? 30 * 4 : (30 * 8) >> (narrow ? 1 : 0); }
+int stream_warps_per_sm(int kind, int narrow, int pfd) { return (narrow && kind_elem_size(kind) != 8) ? 32 : pfd == 2 ? 12 : 16; }
 
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (p.narrow) {
-        if (kind == K_CDF97_F32) go_fwd<W97F, 4>(p, frames, st);
-        else if (kind == K_CDF97_F64) go_fwd<W97D, 4>(p, frames, st);   // a lane must hold >= HALO samples
-        else go_fwd<W53I, 4>(p, frames, st);
-    } else {
-        if (kind == K_CDF97_F32) go_fwd<W97F, 8>(p, frames, st);
-        else if (kind == K_CDF97_F64) go_fwd<W97D, 4>(p, frames, st);
-        else go_fwd<W53I, 8>(p, frames, st);
-    }
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        if (p.narrow) go_fwd<WV, 4>(p, frames, st);
+        else go_fwd<WV, 32 / (int)sizeof(typename WV::T)>(p, frames, st);
+    });
 }
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (p.narrow) {
-        if (kind == K_CDF97_F32) go_inv<W97F, 4>(p, frames, st);
-        else if (kind == K_CDF97_F64) go_inv<W97D, 4>(p, frames, st);
-        else go_inv<W53I, 4>(p, frames, st);
-    } else {
-        if (kind == K_CDF97_F32) go_inv<W97F, 8>(p, frames, st);
-        else if (kind == K_CDF97_F64) go_inv<W97D, 4>(p, frames, st);
-        else go_inv<W53I, 8>(p, frames, st);
-    }
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        if (p.narrow) go_inv<WV, 4>(p, frames, st);
+        else go_inv<WV, 32 / (int)sizeof(typename WV::T)>(p, frames, st);
+    });
 }
 
 }  // namespace dwtb200

@@ -30,7 +30,7 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(c
     inv_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
 }
 
-int tail_max_elems(int kind) { return TAIL_BUF_BYTES / (kind == K_CDF97_F64 ? 8 : 4); }
+int tail_max_elems(int kind) { return TAIL_BUF_BYTES / kind_elem_size(kind); }
 
 // Kernels are loaded lazily by the CUDA runtime; loading (and cudaFuncSetAttribute) is not allowed while
 // a stream is being captured, so dwtb200_init() calls this once before any graph is built.
@@ -43,27 +43,24 @@ template <class K> static cudaError_t prep(K kern)
 }
 cudaError_t preload_tail()
 {
-    cudaError_t e = prep(k_fwd_tail<W97F>);
-    if (e == cudaSuccess) e = prep(k_fwd_tail<W97D>);
-    if (e == cudaSuccess) e = prep(k_fwd_tail<W53I>);
-    if (e == cudaSuccess) e = prep(k_inv_tail<W97F>);
-    if (e == cudaSuccess) e = prep(k_inv_tail<W97D>);
-    if (e == cudaSuccess) e = prep(k_inv_tail<W53I>);
+    cudaError_t e = cudaSuccess;
+    for (int kind = 0; kind < K_COUNT; kind++)
+        dispatch_kind(kind, [&](auto wv) {
+            using WV = decltype(wv);
+            if (e == cudaSuccess) e = prep(k_fwd_tail<WV>);
+            if (e == cudaSuccess) e = prep(k_inv_tail<WV>);
+        });
     return e;
 }
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { launch_pdl(k_fwd_tail<W97F>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
-    else if (kind == K_CDF97_F64) { launch_pdl(k_fwd_tail<W97D>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
-    else { launch_pdl(k_fwd_tail<W53I>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_fwd_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); });
 }
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    if (kind == K_CDF97_F32) { launch_pdl(k_inv_tail<W97F>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
-    else if (kind == K_CDF97_F64) { launch_pdl(k_inv_tail<W97D>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
-    else { launch_pdl(k_inv_tail<W53I>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); }
+    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_inv_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); });
 }
 
 }  // namespace dwtb200

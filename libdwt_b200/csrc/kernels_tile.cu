@@ -292,25 +292,31 @@ template <class WV> static dim3 tile_grid(const LevelParams &p, int frames)
 }
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) launch_pdl(k_fwd_tile<W97F>, tile_grid<W97F>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
-    else if (kind == K_CDF97_F64) launch_pdl(k_fwd_tile<W97D>, tile_grid<W97D>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
-    else launch_pdl(k_fwd_tile<W53I>, tile_grid<W53I>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        launch_pdl(k_fwd_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    });
 }
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) launch_pdl(k_inv_tile<W97F>, tile_grid<W97F>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
-    else if (kind == K_CDF97_F64) launch_pdl(k_inv_tile<W97D>, tile_grid<W97D>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
-    else launch_pdl(k_inv_tile<W53I>, tile_grid<W53I>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        launch_pdl(k_inv_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+    });
 }
 
 int mid_tail_max_elems(int kind)
 {
     // the tail's two LL buffers alias the tile staging area of the persistent kernel
-    return kind == K_CDF97_F64 ? (int)(sizeof(TileSmem<W97D>) / 16) : kind == K_CDF97_F32 ? (int)(sizeof(TileSmem<W97F>) / 8)
-                                                                                          : (int)(sizeof(TileSmem<W53I>) / 8);
+    int n = 0;
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T)));
+    });
+    return n;
 }
 
-static int g_mid_ctas_per_sm[2][3];   // [inverse][kind], filled by preload_tile()
+static int g_mid_ctas_per_sm[2][K_COUNT];   // [inverse][kind], filled by preload_tile()
 static int g_sm_count = 0;
 
 template <class K> static cudaError_t launch_coop(K kern, const MidParams &mp, int ctas_per_sm, int work, cudaStream_t st)
@@ -333,15 +339,21 @@ template <class WV> static int mid_work(const MidParams &mp)
 }
 cudaError_t launch_fwd_mid(int kind, const MidParams &mp, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) return launch_coop(k_fwd_mid<W97F>, mp, g_mid_ctas_per_sm[0][0], mid_work<W97F>(mp), st);
-    if (kind == K_CDF97_F64) return launch_coop(k_fwd_mid<W97D>, mp, g_mid_ctas_per_sm[0][1], mid_work<W97D>(mp), st);
-    return launch_coop(k_fwd_mid<W53I>, mp, g_mid_ctas_per_sm[0][2], mid_work<W53I>(mp), st);
+    cudaError_t e = cudaSuccess;
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        e = launch_coop(k_fwd_mid<WV>, mp, g_mid_ctas_per_sm[0][kind], mid_work<WV>(mp), st);
+    });
+    return e;
 }
 cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st)
 {
-    if (kind == K_CDF97_F32) return launch_coop(k_inv_mid<W97F>, mp, g_mid_ctas_per_sm[1][0], mid_work<W97F>(mp), st);
-    if (kind == K_CDF97_F64) return launch_coop(k_inv_mid<W97D>, mp, g_mid_ctas_per_sm[1][1], mid_work<W97D>(mp), st);
-    return launch_coop(k_inv_mid<W53I>, mp, g_mid_ctas_per_sm[1][2], mid_work<W53I>(mp), st);
+    cudaError_t e = cudaSuccess;
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        e = launch_coop(k_inv_mid<WV>, mp, g_mid_ctas_per_sm[1][kind], mid_work<WV>(mp), st);
+    });
+    return e;
 }
 
 template <class K> static cudaError_t touch(K kern)
@@ -360,18 +372,15 @@ template <class K> static cudaError_t occupancy(K kern, int &out, int cap)
 cudaError_t preload_tile(int sm_count, int mid_ctas_per_sm)
 {
     g_sm_count = sm_count;
-    cudaError_t e = touch(k_fwd_tile<W97F>);
-    if (e == cudaSuccess) e = touch(k_fwd_tile<W97D>);
-    if (e == cudaSuccess) e = touch(k_fwd_tile<W53I>);
-    if (e == cudaSuccess) e = touch(k_inv_tile<W97F>);
-    if (e == cudaSuccess) e = touch(k_inv_tile<W97D>);
-    if (e == cudaSuccess) e = touch(k_inv_tile<W53I>);
-    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W97F>, g_mid_ctas_per_sm[0][0], mid_ctas_per_sm);
-    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W97D>, g_mid_ctas_per_sm[0][1], mid_ctas_per_sm);
-    if (e == cudaSuccess) e = occupancy(k_fwd_mid<W53I>, g_mid_ctas_per_sm[0][2], mid_ctas_per_sm);
-    if (e == cudaSuccess) e = occupancy(k_inv_mid<W97F>, g_mid_ctas_per_sm[1][0], mid_ctas_per_sm);
-    if (e == cudaSuccess) e = occupancy(k_inv_mid<W97D>, g_mid_ctas_per_sm[1][1], mid_ctas_per_sm);
-    if (e == cudaSuccess) e = occupancy(k_inv_mid<W53I>, g_mid_ctas_per_sm[1][2], mid_ctas_per_sm);
+    cudaError_t e = cudaSuccess;
+    for (int kind = 0; kind < K_COUNT; kind++)
+        dispatch_kind(kind, [&](auto wv) {
+            using WV = decltype(wv);
+            if (e == cudaSuccess) e = touch(k_fwd_tile<WV>);
+            if (e == cudaSuccess) e = touch(k_inv_tile<WV>);
+            if (e == cudaSuccess) e = occupancy(k_fwd_mid<WV>, g_mid_ctas_per_sm[0][kind], mid_ctas_per_sm);
+            if (e == cudaSuccess) e = occupancy(k_inv_mid<WV>, g_mid_ctas_per_sm[1][kind], mid_ctas_per_sm);
+        });
     return e;
 }
 

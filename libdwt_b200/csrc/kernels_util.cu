@@ -83,8 +83,9 @@ void launch_fill(int kind, void *buf, int64_t pitch, int64_t frame, int nx, int 
                  int frames, int y_offset, int wide, cudaStream_t st)
 {
     const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8, frames);
-    if (kind == K_CDF97_F32) k_fill<float><<<g, b, 0, st>>>((float *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
-    else if (kind == K_CDF97_F64) k_fill<double><<<g, b, 0, st>>>((double *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
+    const int cls = kind_elem_class(kind);
+    if (cls == 1) k_fill<float><<<g, b, 0, st>>>((float *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
+    else if (cls == 2) k_fill<double><<<g, b, 0, st>>>((double *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
     else k_fill<int32_t><<<g, b, 0, st>>>((int32_t *)buf, pitch, frame, nx, ny, rnd, type, mod, y_offset, wide);
 }
 

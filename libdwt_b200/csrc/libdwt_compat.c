@@ -38,6 +38,13 @@ FWD(dwt_cdf97_2f_d, DWTB200_CDF97_F64)
 INV(dwt_cdf97_2i_d, DWTB200_CDF97_F64)
 FWD(dwt_cdf53_2f_i, DWTB200_CDF53_I32)
 INV(dwt_cdf53_2i_i, DWTB200_CDF53_I32)
+/* sibling drivers on the same kernels */
+FWD(dwt_cdf53_2f_s, DWTB200_CDF53_F32)
+INV(dwt_cdf53_2i_s, DWTB200_CDF53_F32)
+FWD(dwt_cdf53_2f_d, DWTB200_CDF53_F64)
+INV(dwt_cdf53_2i_d, DWTB200_CDF53_F64)
+FWD(dwt_cdf97_2f_i, DWTB200_CDF97_I32)
+INV(dwt_cdf97_2i_i, DWTB200_CDF97_I32)
 
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y)
 {

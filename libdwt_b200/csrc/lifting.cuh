@@ -24,7 +24,7 @@
 
 namespace dwtb200 {
 
-enum Kind : int { K_CDF97_F32 = 0, K_CDF97_F64 = 1, K_CDF53_I32 = 2 };
+enum Kind : int { K_CDF97_F32 = 0, K_CDF97_F64 = 1, K_CDF53_I32 = 2, K_CDF53_F32 = 3, K_CDF53_F64 = 4, K_CDF97_I32 = 5, K_COUNT = 6 };
 
 struct W97F {
     using T = float;
@@ -100,6 +100,97 @@ struct W53I {
     static __device__ __forceinline__ T one_f(T x) { return x; }
     static __device__ __forceinline__ T one_i(T x) { return x; }
 };
+
+// ---- sibling transforms sharing the same kernels -------------------------
+//   W53F  dwt_cdf53_f_ex_stride_s / dwt_cdf53_i_ex_stride_s   src/libdwt.c:10986, 11785   (drivers :16470, 18296)
+//   W53D  dwt_cdf53_f_ex_stride_d / dwt_cdf53_i_ex_stride_d   src/libdwt.c:2085, 11484    (drivers :12535, 16962)
+//   W97I  dwt_cdf97_f_ex_stride_i / dwt_cdf97_i_ex_stride_i   src/libdwt.c:10901, 11699   (drivers :16387, 18219)
+// `x -= c*(l+r)` of the reference equals x + (-c)*(l+r) bit for bit (negation is exact).
+template <class FT> struct W53Float {
+    using T = FT;
+    static constexpr int NS = 2;
+    static constexpr int HALO = 2;
+    static constexpr bool HAS_ONE = true;    // libdwt.c:10997, 11797: a line of length 1 is scaled
+    static constexpr bool GUARD = false;     // libdwt.c:16508: no `lines > 1` test
+    static constexpr bool INV_COLS_FIRST = false;   // libdwt.c:18333 rows, then :18342 columns
+    static constexpr FT P1 = (FT)0.5, U1 = (FT)0.25;
+    static constexpr FT S1 = (FT)1.41421356237309504880, S2 = (FT)0.70710678118654752440;   // inline.h:333-341
+    static __device__ __forceinline__ T add(T a, T b)
+    {
+        if constexpr (sizeof(T) == 4) return __fadd_rn(a, b);
+        else return __dadd_rn(a, b);
+    }
+    static __device__ __forceinline__ T mul(T a, T b)
+    {
+        if constexpr (sizeof(T) == 4) return __fmul_rn(a, b);
+        else return __dmul_rn(a, b);
+    }
+    template <int S> static __device__ __forceinline__ T f(T x, T l, T r) { return add(x, mul(S == 0 ? -P1 : U1, add(l, r))); }
+    template <int S> static __device__ __forceinline__ T i(T x, T l, T r) { return add(x, mul(S == 0 ? -U1 : P1, add(l, r))); }
+    static __device__ __forceinline__ T fse(T x) { return mul(x, S1); }
+    static __device__ __forceinline__ T fso(T x) { return mul(x, S2); }
+    static __device__ __forceinline__ T ise(T x) { return mul(x, S2); }
+    static __device__ __forceinline__ T iso(T x) { return mul(x, S1); }
+    static __device__ __forceinline__ T one_f(T x) { return mul(x, S1); }
+    static __device__ __forceinline__ T one_i(T x) { return mul(x, S2); }
+};
+using W53F = W53Float<float>;
+using W53D = W53Float<double>;
+
+struct W97I {
+    using T = int32_t;
+    static constexpr int NS = 4;
+    static constexpr int HALO = 4;
+    static constexpr bool HAS_ONE = false;   // libdwt.c:10912: N < 2 leaves the line untouched
+    static constexpr bool GUARD = false;
+    static constexpr bool INV_COLS_FIRST = true;   // libdwt.c:18256 columns, then :18265 rows
+    // 32-bit two's-complement wrap-around like the compiled reference; >> is arithmetic
+    static __device__ __forceinline__ T q7(int c, T l, T r)    // ( c*(l+r) - (1<<6) ) >> 7
+    {
+        return (T)((uint32_t)c * ((uint32_t)l + (uint32_t)r) - 64u) >> 7;
+    }
+    static __device__ __forceinline__ T q12(int c, T l, T r)   // ( c*(l+r) + (1<<11) ) >> 12
+    {
+        return (T)((uint32_t)c * ((uint32_t)l + (uint32_t)r) + 2048u) >> 12;
+    }
+    static __device__ __forceinline__ T wadd(T a, T b) { return (T)((uint32_t)a + (uint32_t)b); }
+    static __device__ __forceinline__ T wsub(T a, T b) { return (T)((uint32_t)a - (uint32_t)b); }
+    template <int S> static __device__ __forceinline__ T f(T x, T l, T r)
+    {
+        if (S == 0) return wsub(x, q7(203, l, r));
+        if (S == 1) return wadd(x, q12(-217, l, r));
+        if (S == 2) return wsub(x, q7(-113, l, r));
+        return wadd(x, q12(1817, l, r));
+    }
+    template <int S> static __device__ __forceinline__ T i(T x, T l, T r)
+    {
+        if (S == 0) return wsub(x, q12(1817, l, r));
+        if (S == 1) return wadd(x, q7(-113, l, r));
+        if (S == 2) return wsub(x, q12(-217, l, r));
+        return wadd(x, q7(203, l, r));
+    }
+    static __device__ __forceinline__ T fse(T x) { return x; }
+    static __device__ __forceinline__ T fso(T x) { return x; }
+    static __device__ __forceinline__ T ise(T x) { return x; }
+    static __device__ __forceinline__ T iso(T x) { return x; }
+    static __device__ __forceinline__ T one_f(T x) { return x; }
+    static __device__ __forceinline__ T one_i(T x) { return x; }
+};
+
+// run f(WV{}) for the wavelet/type of `kind`
+template <class F> inline void dispatch_kind(int kind, F &&f)
+{
+    switch (kind) {
+    case K_CDF97_F32: f(W97F{}); break;
+    case K_CDF97_F64: f(W97D{}); break;
+    case K_CDF53_I32: f(W53I{}); break;
+    case K_CDF53_F32: f(W53F{}); break;
+    case K_CDF53_F64: f(W53D{}); break;
+    default: f(W97I{}); break;
+    }
+}
+inline int kind_elem_size(int kind) { return (kind == K_CDF97_F64 || kind == K_CDF53_F64) ? 8 : 4; }
+inline int kind_elem_class(int kind) { return (kind == K_CDF97_F32 || kind == K_CDF53_F32) ? 1 : kind_elem_size(kind) == 8 ? 2 : 0; }   // 0 int32, 1 float, 2 double
 
 // Programmatic dependent launch: every dense-path kernel lets its successor be scheduled at once
 // (launch_dependents) and waits for its predecessor's results before touching memory (wait).  A

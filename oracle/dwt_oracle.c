@@ -18,6 +18,8 @@
  *             16304 (53 2f_i) 18142 (53 2i_i)
  *   lines     src/libdwt.c:10744 11530 (float; cores 2264, 9510, 9844, 10199)
  *             2024 11424 (double)   10950 11749 (int 5/3)
+ *   siblings  drivers src/libdwt.c:16470 18296 (5/3 float) 12535 16962 (5/3 double) 16387 18219 (9/7 int);
+ *             lines 10986 11785, 2085 11484, 10901 11699; constants src/inline.h:333-341
  *   padding   src/libdwt.c:12080-12215
  *   constants src/inline.h:310-323, helpers 443-460, 590-607
  *   patterns  src/libdwt.c:1112-1244, fills 1247-1385, src/volume.c:41
@@ -146,6 +148,57 @@ static void inv53_i(void *v, int N)
     for (int i = 1; i < N - 2 + (N & 1); i += 2) t[i] = wadd(t[i], wadd(t[i - 1], t[i + 1]) >> 1);
 }
 
+/* ---- sibling transforms ----
+ * 5/3 float / double: libdwt.c:10986, 11785, 2085, 11484.  p1 = 0.5, u1 = 0.25, even *= sqrt2, odd *= 1/sqrt2
+ * (both written as decimal literals, src/inline.h:333-341); edges are (2c)*neighbour like 9/7. */
+static const float  P53s = 0.5, U53s = 0.25, S53_1s = 1.41421356237309504880, S53_2s = 0.70710678118654752440;
+static const double P53d = 0.5, U53d = 0.25, S53_1d = 1.41421356237309504880, S53_2d = 0.70710678118654752440;
+#define DEF_53F(T, SUF, P, U, S1, S2)                                  \
+    static void fwd53_##SUF(void *v, int N)                            \
+    {                                                                  \
+        T *t = (T *)v;                                                 \
+        lift_odd_##SUF(t, N, -P);                                      \
+        lift_even_##SUF(t, N, U);                                      \
+        for (int i = 0; i < N; i += 2) t[i] = t[i] * S1;               \
+        for (int i = 1; i < N; i += 2) t[i] = t[i] * S2;               \
+    }                                                                  \
+    static void inv53_##SUF(void *v, int N)                            \
+    {                                                                  \
+        T *t = (T *)v;                                                 \
+        for (int i = 0; i < N; i += 2) t[i] = t[i] * S2;               \
+        for (int i = 1; i < N; i += 2) t[i] = t[i] * S1;               \
+        lift_even_##SUF(t, N, -U);                                     \
+        lift_odd_##SUF(t, N, P);                                       \
+    }                                                                  \
+    static void one_fwd53_##SUF(void *v) { *(T *)v = *(T *)v * S1; }   \
+    static void one_inv53_##SUF(void *v) { *(T *)v = *(T *)v * S2; }
+DEF_53F(float, s, P53s, U53s, S53_1s, S53_2s)
+DEF_53F(double, d, P53d, U53d, S53_1d, S53_2d)
+
+/* 9/7 with integer lifting: libdwt.c:10901, 11699.  Steps ( c*(l+r) - 64 ) >> 7 subtracted from odd samples
+ * (c = 203, -113) and ( c*(l+r) + 2048 ) >> 12 added to even samples (c = -217, 1817); mirrored edges use
+ * (nb + nb); 32-bit wrap-around made explicit; no scaling; N < 2 untouched. */
+static int32_t q7(int32_t c, int32_t l, int32_t r) { return (int32_t)((uint32_t)c * ((uint32_t)l + (uint32_t)r) - 64u) >> 7; }
+static int32_t q12(int32_t c, int32_t l, int32_t r) { return (int32_t)((uint32_t)c * ((uint32_t)l + (uint32_t)r) + 2048u) >> 12; }
+static int32_t left_of(const int32_t *t, int i) { return t[i ? i - 1 : 1]; }
+static int32_t right_of(const int32_t *t, int i, int N) { return t[i + 1 < N ? i + 1 : N - 2]; }
+static void fwd97_i(void *v, int N)
+{
+    int32_t *t = (int32_t *)v;
+    for (int i = 1; i < N; i += 2) t[i] = wsub(t[i], q7(203, left_of(t, i), right_of(t, i, N)));
+    for (int i = 0; i < N; i += 2) t[i] = wadd(t[i], q12(-217, left_of(t, i), right_of(t, i, N)));
+    for (int i = 1; i < N; i += 2) t[i] = wsub(t[i], q7(-113, left_of(t, i), right_of(t, i, N)));
+    for (int i = 0; i < N; i += 2) t[i] = wadd(t[i], q12(1817, left_of(t, i), right_of(t, i, N)));
+}
+static void inv97_i(void *v, int N)
+{
+    int32_t *t = (int32_t *)v;
+    for (int i = 0; i < N; i += 2) t[i] = wsub(t[i], q12(1817, left_of(t, i), right_of(t, i, N)));
+    for (int i = 1; i < N; i += 2) t[i] = wadd(t[i], q7(-113, left_of(t, i), right_of(t, i, N)));
+    for (int i = 0; i < N; i += 2) t[i] = wsub(t[i], q12(-217, left_of(t, i), right_of(t, i, N)));
+    for (int i = 1; i < N; i += 2) t[i] = wadd(t[i], q7(203, left_of(t, i), right_of(t, i, N)));
+}
+
 /* =====================================================================================
  * Generic Mallat-layout level driver.
  * ===================================================================================== */
@@ -162,6 +215,9 @@ typedef struct {
 static const kind_t K97S = {4, fwd97_s, inv97_s, one_fwd97_s, one_inv97_s, 1, 0};
 static const kind_t K97D = {8, fwd97_d, inv97_d, one_fwd97_d, one_inv97_d, 0, 0};
 static const kind_t K53I = {4, fwd53_i, inv53_i, NULL, NULL, 0, 1};
+static const kind_t K53S = {4, fwd53_s, inv53_s, one_fwd53_s, one_inv53_s, 0, 0}; /* libdwt.c:16508, 18333: no guard, rows first */
+static const kind_t K53D = {8, fwd53_d, inv53_d, one_fwd53_d, one_inv53_d, 0, 0}; /* libdwt.c:12574, 16999 */
+static const kind_t K97I = {4, fwd97_i, inv97_i, NULL, NULL, 0, 1};               /* libdwt.c:18256: columns first */
 
 static void gather(void *dst, ptrdiff_t dstep, const void *src, ptrdiff_t sstep, int n, size_t esz)
 {
@@ -300,6 +356,9 @@ static void drive_inv(const kind_t *k, void *ptr, ptrdiff_t sx, ptrdiff_t sy, in
 EXPORT_2D(cdf97_s, K97S)
 EXPORT_2D(cdf97_d, K97D)
 EXPORT_2D(cdf53_i, K53I)
+EXPORT_2D(cdf53_s, K53S)
+EXPORT_2D(cdf53_d, K53D)
+EXPORT_2D(cdf97_i, K97I)
 
 /* =====================================================================================
  * Test patterns (src/libdwt.c:1112-1244).  wrap32 != 0 reproduces the reference's 32-bit

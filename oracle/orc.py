@@ -35,7 +35,7 @@ class Oracle:
             build()
         self.lib = L = C.CDLL(ORC_SO)
         i64, ci, vp = C.c_int64, C.c_int, C.c_void_p
-        for name in ("cdf97_s", "cdf97_d", "cdf53_i"):
+        for name in ("cdf97_s", "cdf97_d", "cdf53_i", "cdf53_s", "cdf53_d", "cdf97_i"):
             getattr(L, f"orc_{name}_2f").argtypes = [vp, i64, i64, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
             getattr(L, f"orc_{name}_2i").argtypes = [vp, i64, i64, ci, ci, ci, ci, ci, ci, ci]
         L.orc_fill_s.argtypes = [vp, i64, i64, ci, ci, ci, ci, ci]
@@ -52,7 +52,7 @@ class Oracle:
 
     @staticmethod
     def _fn(wavelet, t):
-        return {"97s": "cdf97_s", "97d": "cdf97_d", "53i": "cdf53_i"}[f"{wavelet}{t}"]
+        return {"97s": "cdf97_s", "97d": "cdf97_d", "53i": "cdf53_i", "53s": "cdf53_s", "53d": "cdf53_d", "97i": "cdf97_i"}[f"{wavelet}{t}"]
 
     def fwd2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         """In place on `img` ([oy, ox] outer array); returns achieved J."""
@@ -121,9 +121,9 @@ class Ref:
     def __init__(self):
         self.lib = L = C.CDLL(REF_SO)
         ci, vp = C.c_int, C.c_void_p
-        for n in ("dwt_cdf97_2f_s", "dwt_cdf97_2f_d", "dwt_cdf53_2f_i"):
+        for n in ("dwt_cdf97_2f_s", "dwt_cdf97_2f_d", "dwt_cdf53_2f_i", "dwt_cdf53_2f_s", "dwt_cdf53_2f_d", "dwt_cdf97_2f_i"):
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
-        for n in ("dwt_cdf97_2i_s", "dwt_cdf97_2i_d", "dwt_cdf53_2i_i"):
+        for n in ("dwt_cdf97_2i_s", "dwt_cdf97_2i_d", "dwt_cdf53_2i_i", "dwt_cdf53_2i_s", "dwt_cdf53_2i_d", "dwt_cdf97_2i_i"):
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         for n in ("dwt_util_test_image_fill_s", "dwt_util_test_image_fill_d", "dwt_util_test_image_fill_i"):
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci]
@@ -144,7 +144,8 @@ class Ref:
 
     @staticmethod
     def _fn(wavelet, t, d):
-        return {"97s": "dwt_cdf97_2%s_s", "97d": "dwt_cdf97_2%s_d", "53i": "dwt_cdf53_2%s_i"}[f"{wavelet}{t}"] % d
+        return {"97s": "dwt_cdf97_2%s_s", "97d": "dwt_cdf97_2%s_d", "53i": "dwt_cdf53_2%s_i",
+                "53s": "dwt_cdf53_2%s_s", "53d": "dwt_cdf53_2%s_d", "97i": "dwt_cdf97_2%s_i"}[f"{wavelet}{t}"] % d
 
     @staticmethod
     def _check(img):

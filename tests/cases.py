@@ -3,7 +3,8 @@ import hashlib
 
 import numpy as np
 
-KINDS = [("97", "s"), ("97", "d"), ("53", "i")]
+# the three north-star transforms, then the sibling drivers sharing their kernels
+KINDS = [("97", "s"), ("97", "d"), ("53", "i"), ("53", "s"), ("53", "d"), ("97", "i")]
 DT = {"s": np.float32, "d": np.float64, "i": np.int32}
 UT = {"s": np.uint32, "d": np.uint64, "i": np.uint32}
 

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import DT, bits, case_id, dense_cases, describe_mismatch, digest, sparse_cases
+from cases import DT, KINDS, bits, case_id, dense_cases, describe_mismatch, digest, sparse_cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
@@ -87,7 +87,7 @@ def test_int_roundtrip_is_exact_and_float_roundtrip_is_close(oracle):
 
 
 # ---- against the compiled reference itself (build container only) ---------------------------------
-@pytest.mark.parametrize("kind", [("97", "s"), ("97", "d"), ("53", "i")], ids=lambda k: k[0] + k[1])
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k[0] + k[1])
 def test_oracle_vs_reference_strided(oracle, ref, kind):
     from oracle.orc import strided_image
     w, t = kind
