@@ -59,7 +59,7 @@ struct Ctx {
     // tuning (dwtb200_set_tuning): a level with at most tile_max samples (all frames) takes the tile
     // kernels instead of the streaming ones; the tail kernel starts at the first level with at most
     // tail_max samples per frame
-    int64_t tile_max = (int64_t)2048 * 2048;
+    int64_t tile_max = (int64_t)1024 * 1024;
     int64_t mid_max = 0;   // levels this small (and <= tile_max) share ONE persistent cooperative launch; 0 = off
     int mid_ctas_per_sm = 4;
     int tail_max = 32 * 32;
@@ -67,6 +67,8 @@ struct Ctx {
     int dbg = 0;
     int pfd = 1;
     int pipeline = 1;   // pipelined host path for large dense images
+    int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
+    int ring_waves = 5, ring_pps_min = 0, ring_pps_max = 0;
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
 
@@ -160,6 +162,7 @@ int dwtb200_init(int device)
         return fail(DWTB200_ENODEV, "device %d is sm_%d%d; libdwtb200 is built for sm_100a only", device, prop.major, prop.minor);
     g.sm_count = prop.multiProcessorCount;
     CK(preload_stream());
+    CK(preload_ring());
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
@@ -237,6 +240,8 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
     case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
     case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
+    case DWTB200_TUNE_RING: g.ring = (int)value; break;
+    case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
     case 99: g.dbg = (int)value; break;   // measurement only, see kernels.h
     case DWTB200_TUNE_NARROW: g.narrow = value != 0; break;
@@ -499,6 +504,11 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.pfd = inverse ? 1 : g.pfd;
     const int outw = stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
+    {   // ring kernels: bands of at most ring_cta_warps() column groups, as equal as possible
+        const int cw = ring_cta_warps((g.ring >> 4) & 3), nb = (p.ncg + cw - 1) / cw;
+        p.bw = (p.ncg + nb - 1) / nb;
+        p.nbands = (p.ncg + p.bw - 1) / p.bw;
+    }
     const int units = inverse ? (H >> 1) + 1 : p.nLy;   // row pairs to emit
     int pps;
     if (g.strip_rows > 0) {
@@ -506,12 +516,24 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     } else {
         // enough warps for ~16 per SM, but strips of at least 8 and at most 64 pairs (warm-up rows are
         // re-read per strip: 3 pairs for 9/7 forward, 4 for inverse)
-        const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow, p.pfd);
-        int64_t per_col = want / ((int64_t)p.ncg * im->frames);   // strips per column group: never more warps than fit at once
-        if (per_col < 1) per_col = 1;
-        pps = (int)((units + per_col - 1) / per_col);
-        if (pps < 8) pps = 8;
-        if (pps > 64) pps = 64;
+        const bool ring = !p.narrow && (inverse ? (g.ring & 2) : (g.ring & 1));
+        if (ring) {
+            // Measured (profiles/ring_pps_r1.txt): CTAs run at visibly different speeds, so many short CTAs handed out
+            // dynamically beat one long CTA per slot in spite of the warm-up rows every strip re-reads:
+            // aim at >= ring_waves waves of CTAs, strips of 16 .. 32 row pairs (8 .. 16 for the two-step wavelets)
+            const int cfg = (g.ring >> 4) & 3;
+            const int64_t slots = (int64_t)g.sm_count * ring_ctas_per_sm(cfg);
+            const int lo = g.ring_pps_min > 0 ? g.ring_pps_min : 16, hi = g.ring_pps_max > 0 ? g.ring_pps_max : 32;
+            int64_t v = (int64_t)units * p.nbands * im->frames / (g.ring_waves * slots);
+            pps = (int)(v < lo ? lo : v > hi ? hi : v);
+        } else {
+            const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow, p.pfd);
+            int64_t per_col = want / ((int64_t)p.ncg * im->frames);   // strips per column group: never more warps than fit at once
+            if (per_col < 1) per_col = 1;
+            pps = (int)((units + per_col - 1) / per_col);
+            if (pps < 8) pps = 8;
+            if (pps > 64) pps = 64;
+        }
     }
     p.pps = pps;
     p.nstrips = (units + pps - 1) / pps;
@@ -556,9 +578,22 @@ void inv_level_params(const dwtb200_image *im, int j, int J, char *src_plane, ch
     p.hh = src_plane + ((size_t)ody * im->pitch + odx) * im->es;
     p.sub_pitch = im->pitch;
     p.sub_frame = im->frame;
+    p.h_room = (int)(im->pitch - odx);
     p.dst = out.p;
     p.dst_pitch = out.pitch;
     p.dst_frame = out.frame;
+}
+
+void stream_fwd(int kind, const LevelParams &p, int frames, cudaStream_t st)
+{
+    if ((g.ring & 1) && !p.narrow) launch_fwd_ring(kind, p, frames, (g.ring >> 4) & 3, st);
+    else launch_fwd_level(kind, p, frames, st);
+}
+
+void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
+{
+    if ((g.ring & 2) && !p.narrow && p.sub_aligned) launch_inv_ring(kind, p, frames, (g.ring >> 4) & 3, st);
+    else launch_inv_level(kind, p, frames, st);
 }
 
 int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
@@ -604,7 +639,7 @@ int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
         LevelParams p;
         in = fwd_level_params(im, j, J, in, dst_plane, p);
         if (pl.type[j] == PLAN_TILE) launch_fwd_tile(im->kind, p, im->frames, g.st);
-        else launch_fwd_level(im->kind, p, im->frames, g.st);
+        else stream_fwd(im->kind, p, im->frames, g.st);
         g.launches++;
     }
     return 0;
@@ -652,7 +687,7 @@ int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop = 0)
         LevelParams p;
         inv_level_params(im, j, J, src_plane, dst_plane, p);
         if (pl.type[j] == PLAN_TILE) launch_inv_tile(im->kind, p, im->frames, g.st);
-        else launch_inv_level(im->kind, p, im->frames, g.st);
+        else stream_inv(im->kind, p, im->frames, g.st);
         g.launches++;
     }
     return 0;
@@ -977,7 +1012,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             LevelParams q = lp;
             q.strip0 = s_lo[c];
             q.nstrips = s_lo[c + 1] - s_lo[c];
-            launch_fwd_level(im->kind, q, 1, g.st);
+            stream_fwd(im->kind, q, 1, g.st);
             CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
             CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
             CK(d2h(k0, k1, nLx, W, dst_plane));   // HL rows: these host rows were uploaded before the kernel ran
@@ -1018,7 +1053,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             LevelParams q = lp;
             q.strip0 = s_lo[c];
             q.nstrips = s_lo[c + 1] - s_lo[c];
-            launch_inv_level(im->kind, q, 1, g.st);
+            stream_inv(im->kind, q, 1, g.st);
             CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
             CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
             const int r0 = std::max(0, 2 * q0 - 1), r1 = std::min(H, 2 * q1 - 1);   // rows this range reconstructs

@@ -31,12 +31,21 @@ struct LevelParams {
     int strip0;           // ... starting with this one (the host path pipelines level 0 strip range by strip range)
     int pps;              // output row pairs (fwd) / iterations (inv) per strip
     int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
+    int h_room;           // elements from the hl / hh column origin to the end of the pitched plane row
+    int bw, nbands;       // ring kernels: column groups per CTA (band), bands per row of CTAs
     int pfd;              // row pairs prefetched ahead in registers: 1 (4 CTAs/SM) or 2 (3 CTAs/SM)
     int dbg;              // measurement only: 1 = no stores, 2 = no lifting arithmetic (forward streaming kernel)
     int narrow;           // 1: 16 bytes per lane instead of 32 (half the registers, twice the warps per SM)
 };
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
+// the same level with its input staged through a shared-memory ring by the bulk-copy engine (kernels_ring.cu)
+cudaError_t preload_ring();
+void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
+void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
+int ring_warps_per_sm(int cfg);
+int ring_cta_warps(int cfg);
+int ring_ctas_per_sm(int cfg);
 int stream_out_width(int kind, int narrow);   // output columns per warp
 int stream_warps_per_sm(int kind, int narrow, int pfd);
 // tile kernels (kernels_tile.cu): same LevelParams (ncg/nstrips/pps/sub_aligned unused), low latency

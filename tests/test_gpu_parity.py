@@ -96,16 +96,20 @@ def test_dense_parity(dev, oracle, kind, shape):
     report(fails)
 
 
-# kernel selection per level: (DWTB200_TUNE_TILE_MAX, DWTB200_TUNE_TAIL_MAX, DWTB200_TUNE_MID_MAX)
+# kernel selection per level: (DWTB200_TUNE_TILE_MAX, DWTB200_TUNE_TAIL_MAX, DWTB200_TUNE_MID_MAX[, DWTB200_TUNE_RING]);
+# "stream" levels take the bulk-copy ring kernels (ring = 3, default) or the register double-buffer kernels (ring = 0)
 BIG = 1 << 40
 FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-only": (BIG, 0, 0), "stream-only": (0, 0, 0),
             "tile+tinytail": (BIG, 16, 0), "persistent+tail": (BIG, 1024, BIG), "persistent-notail": (BIG, 0, BIG),
-            "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256)}
-DEFAULT_TUNING = (2048 * 2048, 1024, 0)
+            "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256),
+            "regstream-only": (0, 0, 0, 0), "regstream+bigtail": (0, 16384, 0, 0), "ringfwd-reginv": (0, 1024, 0, 1),
+            "ring15x1": (0, 1024, 0, 3 | 16)}
+DEFAULT_TUNING = (1024 * 1024, 1024, 0, 3)
 
 
 def set_tuning(L, t):
-    for key, v in zip((0, 1, 2), t):
+    t = tuple(t) + (3,) * (4 - len(t))
+    for key, v in zip((0, 1, 2, 6), t):
         L.check(L.c.dwtb200_set_tuning(key, v))
 
 
