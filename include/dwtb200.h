@@ -131,9 +131,11 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_NARROW    1: streaming kernels hold 16 instead of 32 bytes per lane: twice the warps per SM (0)
  *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips and download for large dense images (1)
  *   DWTB200_TUNE_RING      bit 0 / bit 1: forward / inverse streaming levels stage their input through a shared-memory
- *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer */
+ *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer
+ *   DWTB200_TUNE_CHAIN     1: the kernels of a pyramid are launched with programmatic stream serialization and wait for
+ *                          their input row block by row block on completion counters, so consecutive levels overlap (1) */
 enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2, DWTB200_TUNE_PDL = 3, DWTB200_TUNE_NARROW = 4,
-       DWTB200_TUNE_PIPELINE = 5, DWTB200_TUNE_RING = 6 };
+       DWTB200_TUNE_PIPELINE = 5, DWTB200_TUNE_RING = 6, DWTB200_TUNE_CHAIN = 7 };
 int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t

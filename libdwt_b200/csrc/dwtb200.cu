@@ -12,7 +12,8 @@
 //   plane[0], plane[1]   two full planes, pitch = width rounded up to 32 elements (128 B / 256 B rows);
 //                        a transform reads plane[cur] and writes plane[cur^1] (Mallat layout forbids
 //                        in-place tiling: level-j H subbands land where other tiles still read), then cur flips
-//   ll[0], ll[1]         LL ping-pong scratch: level j writes its LL band to ll[j&1] (S/4 and S/16 samples)
+//   llpool               LL scratch, one band per level (S/3 in total): level j writes LL_j, level j+1 reads it; separate
+//                        bands because the kernels of a pyramid overlap (struct Chain, kernels.h)
 // Each level of the dense path is ONE kernel launch (kernels_stream.cu) reading its LL input once and
 // writing its four subbands once; the coarse levels whose LL band fits one CTA's shared memory are ONE
 // launch in total (kernels_tail.cu).  The launch sequence of a call is captured into a CUDA graph and
@@ -69,6 +70,7 @@ struct Ctx {
     int pipeline = 1;   // pipelined host path for large dense images
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
     int ring_waves = 5, ring_pps_min = 0, ring_pps_max = 0;
+    int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
 
@@ -112,12 +114,16 @@ struct dwtb200_image {
     int64_t pitch = 0, frame = 0;   // elements
     void *plane[2] = {nullptr, nullptr};
     int cur = 0;
-    void *ll[2] = {nullptr, nullptr};
+    void *llpool = nullptr;           // LL_j bands of the levels j = 0 .. (one buffer per level: the kernels of a pyramid overlap)
+    int64_t ll_off[40] = {0};         // element offset of LL_j inside llpool
+    uint32_t *sync = nullptr;         // chain counters of un-captured launch sequences (captured graphs own theirs)
+    size_t sync_words = 0;
     int last_launches = 0, last_path = 0;
     typedef std::tuple<int, int, int, int, int, int, int, int, int> Key;
     struct Entry {
         cudaGraphExec_t exec;
         int launches, path, flips;
+        uint32_t *sync;   // generation word + completion counters of this graph's kernel chain
     };
     std::map<Key, Entry> graphs;
 };
@@ -241,6 +247,7 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
     case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
+    case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
     case 99: g.dbg = (int)value; break;   // measurement only, see kernels.h
@@ -275,10 +282,17 @@ dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
     im->pitch = align_up(ox, 32);
     im->frame = im->pitch * oy;
     const size_t plane_bytes = (size_t)im->frame * frames * im->es;
-    const size_t ll0 = (size_t)align_up(cdiv_pow2(ox, 1), 32) * cdiv_pow2(oy, 1) * frames * im->es;
-    const size_t ll1 = (size_t)align_up(cdiv_pow2(ox, 2), 32) * cdiv_pow2(oy, 2) * frames * im->es;
+    int64_t pool = 0;
+    for (int j = 0; j < 40; j++) {   // LL_j = (w_{j+1} x h_{j+1}) per frame, 128-byte aligned
+        im->ll_off[j] = pool;
+        const int w = cdiv_pow2(ox, j + 1), h = cdiv_pow2(oy, j + 1);
+        if (w * (int64_t)h > 1 || j == 0) pool += align_up(align_up(w, 32) * (int64_t)h * frames, 32);
+    }
+    // chain counters: at most one per 8 output rows of every level, per frame
+    im->sync_words = 2 + (size_t)frames * ((size_t)oy / 4 + 4 * 40 + 64);
     bool ok = cudaMalloc(&im->plane[0], plane_bytes) == cudaSuccess && cudaMalloc(&im->plane[1], plane_bytes) == cudaSuccess &&
-              cudaMalloc(&im->ll[0], ll0) == cudaSuccess && cudaMalloc(&im->ll[1], ll1) == cudaSuccess;
+              cudaMalloc(&im->llpool, (size_t)pool * im->es) == cudaSuccess &&
+              cudaMalloc((void **)&im->sync, im->sync_words * sizeof(uint32_t)) == cudaSuccess;
     if (ok) ok = cudaMemsetAsync(im->plane[0], 0, plane_bytes, g.st) == cudaSuccess &&
                  cudaMemsetAsync(im->plane[1], 0, plane_bytes, g.st) == cudaSuccess;
     if (!ok) {
@@ -293,11 +307,14 @@ void dwtb200_image_destroy(dwtb200_image *im)
 {
     if (!im) return;
     if (g.st) cudaStreamSynchronize(g.st);
-    for (auto &kv : im->graphs) cudaGraphExecDestroy(kv.second.exec);
-    for (int i = 0; i < 2; i++) {
-        if (im->plane[i]) cudaFree(im->plane[i]);
-        if (im->ll[i]) cudaFree(im->ll[i]);
+    for (auto &kv : im->graphs) {
+        cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.sync) cudaFree(kv.second.sync);
     }
+    for (int i = 0; i < 2; i++)
+        if (im->plane[i]) cudaFree(im->plane[i]);
+    if (im->llpool) cudaFree(im->llpool);
+    if (im->sync) cudaFree(im->sync);
     delete im;
 }
 
@@ -484,7 +501,7 @@ Band ll_band(const dwtb200_image *im, int j)   // LL_j = output of level j, (w_{
 {
     const int w = cdiv_pow2(im->ox, j + 1), h = cdiv_pow2(im->oy, j + 1);
     Band b;
-    b.p = im->ll[j & 1];
+    b.p = (char *)im->llpool + (size_t)im->ll_off[j] * im->es;
     b.pitch = align_up(w, 32);
     b.frame = b.pitch * h;
     return b;
@@ -589,20 +606,125 @@ void stream_fwd(int kind, const LevelParams &p, int frames, cudaStream_t st)
     if ((g.ring & 1) && !p.narrow) launch_fwd_ring(kind, p, frames, (g.ring >> 4) & 3, st);
     else launch_fwd_level(kind, p, frames, st);
 }
-
 void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
     if ((g.ring & 2) && !p.narrow && p.sub_aligned) launch_inv_ring(kind, p, frames, (g.ring >> 4) & 3, st);
     else launch_inv_level(kind, p, frames, st);
 }
 
-int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
+// ---- the dense path as a list of launches, linked into a chain (struct Chain, kernels.h) ----------------
+struct Launch {
+    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
+    LevelParams lp;
+    TailParams tp;
+    MidParams mp;
+    bool chainable = false;
+    // how consumers find the row block of an LL row this launch produces
+    int out_nblocks = 0, out_div = 1, out_bias = 0, out_need = 0;
+    unsigned total = 0;
+    Chain *chain() { return (type == TAIL_F || type == TAIL_I) ? &tp.chain : &lp.chain; }
+};
+
+void plan_level(dwtb200_image *im, Launch &L, bool inverse, int plan_type)
+{
+    const LevelParams &p = L.lp;
+    if (plan_type == PLAN_TILE) {
+        L.type = inverse ? Launch::TILE_I : Launch::TILE_F;
+        const dim3 gr = tile_grid_of(im->kind, p, im->frames);
+        L.chainable = (g.chain & 2) != 0;
+        L.out_nblocks = (int)gr.y;
+        L.out_div = inverse ? tile_rows() : tile_rows() / 2;
+        L.out_need = (int)gr.x;
+        L.total = gr.x * gr.y * gr.z;
+        return;
+    }
+    const bool ring = !p.narrow && (inverse ? ((g.ring & 2) && p.sub_aligned) : (g.ring & 1));
+    L.type = inverse ? (ring ? Launch::RING_I : Launch::REG_I) : (ring ? Launch::RING_F : Launch::REG_F);
+    L.chainable = ring && (g.chain & 1);
+    if (ring) {
+        L.out_nblocks = p.nstrips;
+        L.out_div = inverse ? 2 * p.pps : p.pps;
+        L.out_bias = inverse ? 1 : 0;
+        L.out_need = p.nbands;
+        L.total = (unsigned)p.nbands * p.nstrips * im->frames;
+    }
+}
+
+size_t chain_words(const std::vector<Launch> &ls, int frames)
+{
+    size_t w = 2;
+    for (const Launch &l : ls) w += (size_t)l.out_nblocks * frames;
+    return w;
+}
+
+// link consecutive chainable launches; `sync` = generation word, done counter, then the launches' counters
+void link_chain(std::vector<Launch> &ls, uint32_t *sync, int frames)
+{
+    const int n = (int)ls.size();
+    size_t off = 2;
+    int last = -1;
+    std::vector<uint32_t *> flags(n, nullptr);
+    for (int i = 0; i < n; i++) {
+        flags[i] = sync + off;
+        off += (size_t)ls[i].out_nblocks * frames;
+    }
+    for (int i = 0; i < n; i++) {
+        Chain &c = *ls[i].chain();
+        memset(&c, 0, sizeof c);
+        if (!g.chain || !sync) continue;
+        const bool in = i > 0 && ls[i - 1].chainable && ls[i].chainable;
+        const bool out = i + 1 < n && ls[i].chainable && ls[i + 1].chainable;
+        if (!in && !out) continue;
+        c.gen = sync;
+        c.total = ls[i].total;
+        if (in) {
+            c.in = flags[i - 1];
+            c.in_nblocks = ls[i - 1].out_nblocks;
+            c.in_div = ls[i - 1].out_div;
+            c.in_bias = ls[i - 1].out_bias;
+            c.in_need = ls[i - 1].out_need;
+            c.pdl = 1;
+        }
+        if (out) {
+            c.out = flags[i];
+            c.out_nblocks = ls[i].out_nblocks;
+        }
+        last = i;
+    }
+    if (last >= 0) ls[last].chain()->done = sync + 1;
+}
+
+int issue(dwtb200_image *im, std::vector<Launch> &ls)
+{
+    for (Launch &l : ls) {
+        cudaError_t e = cudaSuccess;
+        switch (l.type) {
+        case Launch::RING_F: launch_fwd_ring(im->kind, l.lp, im->frames, (g.ring >> 4) & 3, g.st); break;
+        case Launch::REG_F: launch_fwd_level(im->kind, l.lp, im->frames, g.st); break;
+        case Launch::TILE_F: launch_fwd_tile(im->kind, l.lp, im->frames, g.st); break;
+        case Launch::TAIL_F: launch_fwd_tail(im->kind, l.tp, im->frames, g.st); break;
+        case Launch::MID_F: e = launch_fwd_mid(im->kind, l.mp, g.st); break;
+        case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, (g.ring >> 4) & 3, g.st); break;
+        case Launch::REG_I: launch_inv_level(im->kind, l.lp, im->frames, g.st); break;
+        case Launch::TILE_I: launch_inv_tile(im->kind, l.lp, im->frames, g.st); break;
+        case Launch::TAIL_I: launch_inv_tail(im->kind, l.tp, im->frames, g.st); break;
+        case Launch::MID_I: e = launch_inv_mid(im->kind, l.mp, g.st); break;
+        }
+        if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch: %s", cudaGetErrorString(e));
+        g.launches++;
+    }
+    return 0;
+}
+
+// levels jstart .. J-1 of the forward transform (jstart > 0: the caller ran the levels below it itself)
+void plan_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart, std::vector<Launch> &ls)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     Band in = {src_plane, im->pitch, im->frame};
-    if (jstart > 0) in = ll_band(im, jstart - 1);   // levels below jstart were run by the caller (pipelined host path)
+    if (jstart > 0) in = ll_band(im, jstart - 1);
     auto tail_params = [&](int j, const Band &from) {
         TailParams t;
+        memset(&t, 0, sizeof t);
         t.src = from.p;
         t.src_pitch = from.pitch;
         t.src_frame = from.frame;
@@ -616,13 +738,18 @@ int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
         return t;
     };
     for (int j = jstart; j < J; j++) {
+        ls.emplace_back();
+        Launch &L = ls.back();
         if (j == pl.jt) {   // stand-alone tail
-            launch_fwd_tail(im->kind, tail_params(j, in), im->frames, g.st);
-            g.launches++;
-            return 0;
+            L.type = Launch::TAIL_F;
+            L.tp = tail_params(j, in);
+            L.chainable = (g.chain & 2) != 0;
+            L.total = im->frames;
+            return;
         }
         if (pl.type[j] == PLAN_MID) {   // levels j .. jt-1 and the tail in one cooperative launch
-            MidParams mp;
+            L.type = Launch::MID_F;
+            MidParams &mp = L.mp;
             memset(&mp, 0, sizeof mp);
             mp.frames = im->frames;
             mp.tail_elems = mid_tail_max_elems(im->kind);
@@ -631,27 +758,22 @@ int run_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart = 0)
                 mp.has_tail = 1;
                 mp.tail = tail_params(pl.jt, in);
             }
-            const cudaError_t e = launch_fwd_mid(im->kind, mp, g.st);
-            if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch (forward): %s", cudaGetErrorString(e));
-            g.launches++;
-            return 0;
+            return;
         }
-        LevelParams p;
-        in = fwd_level_params(im, j, J, in, dst_plane, p);
-        if (pl.type[j] == PLAN_TILE) launch_fwd_tile(im->kind, p, im->frames, g.st);
-        else stream_fwd(im->kind, p, im->frames, g.st);
-        g.launches++;
+        in = fwd_level_params(im, j, J, in, dst_plane, L.lp);
+        plan_level(im, L, false, pl.type[j]);
     }
-    return 0;
 }
 
-int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop = 0)
+// the tail (if any) and the levels jtop-1 .. jstop of the inverse transform
+void plan_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop, std::vector<Launch> &ls)
 {
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     const int jt = pl.jt;
     auto tail_params = [&]() {
         const Band out = (jt == 0) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, jt - 1);
         TailParams t;
+        memset(&t, 0, sizeof t);
         t.src = src_plane;
         t.src_pitch = im->pitch;
         t.src_frame = im->frame;
@@ -666,7 +788,10 @@ int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop = 0)
     };
     int jtop = jt < J ? jt : J;   // levels jtop-1 .. 0 remain after the tail
     if (pl.jm < jt) {             // tail (if any) and levels jt-1 .. jm in one cooperative launch
-        MidParams mp;
+        ls.emplace_back();
+        Launch &L = ls.back();
+        L.type = Launch::MID_I;
+        MidParams &mp = L.mp;
         memset(&mp, 0, sizeof mp);
         mp.frames = im->frames;
         mp.tail_elems = mid_tail_max_elems(im->kind);
@@ -675,22 +800,39 @@ int run_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop = 0)
             mp.tail = tail_params();
         }
         for (int j = jt - 1; j >= pl.jm; j--) inv_level_params(im, j, J, src_plane, dst_plane, mp.lv[mp.nlev++]);
-        const cudaError_t e = launch_inv_mid(im->kind, mp, g.st);
-        if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch (inverse): %s", cudaGetErrorString(e));
-        g.launches++;
         jtop = pl.jm;
     } else if (jt < J) {
-        launch_inv_tail(im->kind, tail_params(), im->frames, g.st);
-        g.launches++;
+        ls.emplace_back();
+        Launch &L = ls.back();
+        L.type = Launch::TAIL_I;
+        L.tp = tail_params();
+        L.chainable = (g.chain & 2) != 0;
+        L.out_nblocks = 1;
+        L.out_div = 1 << 30;
+        L.out_need = 1;
+        L.total = im->frames;
     }
     for (int j = jtop - 1; j >= jstop; j--) {   // jstop > 0: the caller runs the levels below it (pipelined host path)
-        LevelParams p;
-        inv_level_params(im, j, J, src_plane, dst_plane, p);
-        if (pl.type[j] == PLAN_TILE) launch_inv_tile(im->kind, p, im->frames, g.st);
-        else stream_inv(im->kind, p, im->frames, g.st);
-        g.launches++;
+        ls.emplace_back();
+        Launch &L = ls.back();
+        inv_level_params(im, j, J, src_plane, dst_plane, L.lp);
+        plan_level(im, L, true, pl.type[j]);
     }
-    return 0;
+}
+
+// un-captured launch sequences (no-graph mode, pipelined host path) share the image's own counters, zeroed per call
+int run_dense_uncaptured(dwtb200_image *im, bool inverse, int J, const DensePlan &pl, int jlimit)
+{
+    std::vector<Launch> ls;
+    if (inverse) plan_inv_dense(im, J, pl, jlimit, ls);
+    else plan_fwd_dense(im, J, pl, jlimit, ls);
+    uint32_t *sync = nullptr;
+    if (g.chain && chain_words(ls, im->frames) <= im->sync_words) {
+        sync = im->sync;
+        CK(cudaMemsetAsync(sync, 0, chain_words(ls, im->frames) * sizeof(uint32_t), g.st));
+    }
+    link_chain(ls, sync, im->frames);
+    return issue(im, ls);
 }
 
 // one generic pass A -> B over the level's outer region, then the second pass B -> A; a pass the
@@ -803,10 +945,23 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
     if (it == im->graphs.end()) {
         g.launches = 0;
         cudaGraph_t graph = nullptr;
+        std::vector<Launch> ls;
+        uint32_t *sync = nullptr;
+        if (dense && g.use_graph) {   // a captured chain owns its counters: zeroed once, generations thereafter
+            if (inverse) plan_inv_dense(im, J, pl, 0, ls);
+            else plan_fwd_dense(im, J, pl, 0, ls);
+            if (g.chain) {
+                const size_t bytes = chain_words(ls, im->frames) * sizeof(uint32_t);
+                CK(cudaMalloc((void **)&sync, bytes));
+                CK(cudaMemsetAsync(sync, 0, bytes, g.st));
+                CK(cudaStreamSynchronize(g.st));
+            }
+            link_chain(ls, sync, im->frames);
+        }
         if (g.use_graph) CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
         int rr = 0;
         if (dense) {
-            rr = inverse ? run_inv_dense(im, J, pl) : run_fwd_dense(im, J, pl);
+            rr = g.use_graph ? issue(im, ls) : run_dense_uncaptured(im, inverse, J, pl, 0);
         } else {
             if (inverse) run_inv_generic(im, ix, iy, J, zero_padding);
             else run_fwd_generic(im, ix, iy, J, zero_padding);
@@ -816,18 +971,22 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
             const cudaError_t ce = cudaStreamEndCapture(g.st, &graph);
             if (rr) {
                 if (graph) cudaGraphDestroy(graph);
+                if (sync) cudaFree(sync);
                 return rr;
             }
             if (le != cudaSuccess || ce != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
+                if (sync) cudaFree(sync);
                 return fail(DWTB200_ECUDA, "launch/capture failed: %s / %s", cudaGetErrorString(le), cudaGetErrorString(ce));
             }
             dwtb200_image::Entry e;
             e.launches = g.launches;
             e.path = dense ? 0 : 1;
             e.flips = dense ? 1 : 0;
+            e.sync = sync;
             const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
             cudaGraphDestroy(graph);
+            if (ie != cudaSuccess && sync) cudaFree(sync);
             if (ie != cudaSuccess) return fail(DWTB200_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
             it = im->graphs.emplace(key, e).first;
         } else {
@@ -1021,7 +1180,10 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(cu), 0));
             CK(d2h(nLy + k0, nLy + kh, 0, W, dst_plane));
         }
-        run_fwd_dense(im, J, pl, 1);   // levels 1 .. J-1 on the LL band (stream order after the last range)
+        {   // levels 1 .. J-1 on the LL band (stream order after the last range)
+            const int rr = run_dense_uncaptured(im, false, J, pl, 1);
+            if (rr) return rr;
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(g_t1, g.st));
         CK(cudaStreamWaitEvent(g_pipe.dn, g_t1, 0));
@@ -1031,7 +1193,10 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
         CK(h2d(0, nLy, 0, nLx, src_plane));
         CK(cudaEventRecord(g_pipe.get(2 * nch + 1), g_pipe.up));
         CK(cudaStreamWaitEvent(g.st, g_pipe.get(2 * nch + 1), 0));
-        run_inv_dense(im, J, pl, 1);
+        {
+            const int rr = run_dense_uncaptured(im, true, J, pl, 1);
+            if (rr) return rr;
+        }
         CK(cudaGetLastError());
         const int units = (H >> 1) + 1;
         std::vector<int> hl_hi(nch), hh_hi(nch);   // HL rows < hl_hi[c] / LH|HH rows < hh_hi[c] uploaded after chunk c

@@ -15,6 +15,24 @@ cudaError_t preload_generic();
 cudaError_t preload_util();
 cudaError_t preload_tile(int sm_count, int mid_ctas_per_sm);
 
+// ---- dataflow links between the kernels of one transform (chain.cuh) ---------------------------------
+// The kernels of a pyramid are launched back to back with programmatic stream serialization: a kernel may
+// start as soon as every CTA of its predecessor has STARTED, and waits for its input row block by row block
+// on completion counters its predecessor bumps, instead of waiting for the predecessor to finish.  The tail
+// of level j then overlaps the head of level j+1 and the small levels cost a flag round trip, not a launch.
+// Counters are never reset: a block is complete when its counter reaches (gen + 1) * need, and the
+// transform's last chained kernel increments the generation word when its last CTA retires.
+struct Chain {
+    const uint32_t *gen;   // generation word (nullptr: this launch is not chained at all)
+    const uint32_t *in;    // counters of the kernel producing this kernel's LL input (nullptr: input complete at launch)
+    uint32_t *out;         // counters this kernel's CTAs bump once their LL output rows are written (nullptr: nobody waits)
+    uint32_t *done;        // != nullptr: last chained kernel of the transform, its last CTA bumps *gen
+    int in_nblocks, in_bias, in_div, in_need;   // input row r lives in block (r + in_bias) / in_div, complete after in_need arrivals
+    int out_nblocks;       // counters per frame of `out`
+    int pdl;               // launch attribute: programmatic stream serialization
+    unsigned total;        // CTAs of this launch
+};
+
 // ---- streaming level kernels (dense planes): one launch = one decomposition level ---------------
 // Forward: reads the level's LL input (W x H) once, writes LL' (to `ll`) and HL/LH/HH (Mallat
 // positions inside the output plane) once.  Inverse is the mirror image.
@@ -33,6 +51,7 @@ struct LevelParams {
     int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
     int h_room;           // elements from the hl / hh column origin to the end of the pitched plane row
     int bw, nbands;       // ring kernels: column groups per CTA (band), bands per row of CTAs
+    Chain chain;
     int pfd;              // row pairs prefetched ahead in registers: 1 (4 CTAs/SM) or 2 (3 CTAs/SM)
     int dbg;              // measurement only: 1 = no stores, 2 = no lifting arithmetic (forward streaming kernel)
     int narrow;           // 1: 16 bytes per lane instead of 32 (half the registers, twice the warps per SM)
@@ -49,6 +68,8 @@ int ring_ctas_per_sm(int cfg);
 int stream_out_width(int kind, int narrow);   // output columns per warp
 int stream_warps_per_sm(int kind, int narrow, int pfd);
 // tile kernels (kernels_tile.cu): same LevelParams (ncg/nstrips/pps/sub_aligned unused), low latency
+int tile_rows();   // output rows of the full-resolution side per tile (forward tiles emit tile_rows()/2 LL rows)
+dim3 tile_grid_of(int kind, const LevelParams &p, int frames);
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 
@@ -62,6 +83,7 @@ struct TailParams {
     int64_t src_pitch, dst_pitch, src_frame, dst_frame;
     int W0, H0;        // full image size (level 0) -> Mallat offsets
     int j0, j1;        // levels j0 .. j1-1 are transformed (fwd ascending, inv descending)
+    Chain chain;
 };
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st);
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st);

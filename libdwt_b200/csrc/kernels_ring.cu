@@ -21,6 +21,7 @@
 //
 // Same reference semantics and bit-identical results as kernels_stream.cu (see there for the
 // /root/reference/src/libdwt.c lines each pass replaces).
+#include "chain.cuh"
 #include "stream_common.cuh"
 
 namespace dwtb200 {
@@ -148,7 +149,7 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    pdl_begin();
+    const uint32_t gen = chain_begin(p.chain);
 
     constexpr int WARM = WV::NS / 2 + (WV::NS == 4 ? 1 : 0);   // warm-up iterations: 3 (9/7) or 1 (5/3)
     constexpr int DELAY = WV::NS / 2 - 1;                      // iteration m emits pair m - DELAY
@@ -167,17 +168,26 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         const uint32_t dst0 = ring0 + (c0 - xs0) * ES;
         const int nitems = m1 - m0 + 2;   // one single row, then one row pair per iteration
         RingState rs;
+        ChainWindow win;
+        const bool dep = p.chain.in != nullptr;
         for (int q = 0; q < nitems; q++) {
             if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
             const uint32_t d = dst0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
             if (q == 0) {
+                const int r = reflect(2 * m0, H);
+                if (dep) win.need_row(p.chain, gen, blockIdx.y, r);
                 mbar_expect_tx(fb, bytes);
-                bulk_g2s(d + CFG::ROWB, src + (int64_t)reflect(2 * m0, H) * p.src_pitch, bytes, fb);
+                bulk_g2s(d + CFG::ROWB, src + (int64_t)r * p.src_pitch, bytes, fb);
             } else {
                 const int m = m0 + q - 1;
+                const int ra = reflect(2 * m + 1, H), rb = reflect(2 * m + 2, H);
+                if (dep) {
+                    win.need_row(p.chain, gen, blockIdx.y, ra);
+                    win.need_row(p.chain, gen, blockIdx.y, rb);
+                }
                 mbar_expect_tx(fb, 2 * bytes);
-                bulk_g2s(d, src + (int64_t)reflect(2 * m + 1, H) * p.src_pitch, bytes, fb);
-                bulk_g2s(d + CFG::ROWB, src + (int64_t)reflect(2 * m + 2, H) * p.src_pitch, bytes, fb);
+                bulk_g2s(d, src + (int64_t)ra * p.src_pitch, bytes, fb);
+                bulk_g2s(d + CFG::ROWB, src + (int64_t)rb * p.src_pitch, bytes, fb);
             }
             rs.next();
         }
@@ -271,6 +281,10 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
             }
         }
     }
+    if (p.chain.gen) {   // the strip's LL rows are written: tell the next level (consumer warps only: named barrier)
+        asm volatile("bar.sync 1, %0;" ::"r"(nact * 32) : "memory");
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.y, strip);
+    }
 }
 
 // =====================================================================================================
@@ -298,7 +312,7 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    pdl_begin();
+    const uint32_t gen = chain_begin(p.chain);
 
     constexpr int DELAY = WV::NS / 2 - 1;   // iteration k emits rows 2(k-DELAY)-1 and 2(k-DELAY)
     constexpr int WARM = WV::NS;            // warm-up iterations
@@ -322,11 +336,14 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         const uint32_t dst0 = ring0 + (c0 - cs0) * ES;
         const int nitems = kb - ka + 1;
         RingState rs;
+        ChainWindow win;
+        const bool dep = p.chain.in != nullptr;
         for (int q = 0; q < nitems; q++) {
             if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
             const uint32_t d = dst0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
             const int k = ka + q;
             const int ra = reflect(2 * k, H) >> 1, rb = reflect(2 * k + 1, H) >> 1;
+            if (dep) win.need_row(p.chain, gen, blockIdx.y, ra);   // only the LL band is produced inside this transform
             mbar_expect_tx(fb, nll + nh + nlh + nh);
             bulk_g2s(d, ll + (int64_t)ra * p.ll_pitch, nll, fb);
             bulk_g2s(d + SEGB, hl + (int64_t)ra * p.sub_pitch, nh, fb);
@@ -419,6 +436,10 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
             put(2 * q, oE);
         }
     }
+    if (p.chain.gen) {
+        asm volatile("bar.sync 1, %0;" ::"r"(nact * 32) : "memory");
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.y, strip);
+    }
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -462,7 +483,7 @@ void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         dispatch_cfg(cfg, [&](auto c) {
             using CFG = decltype(c);
             const dim3 grid(p.nbands * p.nstrips, frames);
-            launch_pdl(k_fwd_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, g_use_pdl, p);
+            launch_pdl(k_fwd_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
         });
     });
 }
@@ -475,7 +496,7 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         dispatch_cfg(cfg, [&](auto c) {
             using CFG = decltype(c);
             const dim3 grid(p.nbands * p.nstrips, frames);
-            launch_pdl(k_inv_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, g_use_pdl, p);
+            launch_pdl(k_inv_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
         });
     });
 }

@@ -8,6 +8,7 @@
 // when the line count is <= 1; :2036, :11437: double scales a length-1 line; :10961: int leaves it).
 // Lines are evaluated pair-wise with the mirrored window of lifting.cuh, so results are
 // bit-identical to the streaming kernels and to the reference.
+#include "chain.cuh"
 #include "tail_body.cuh"
 
 namespace dwtb200 {
@@ -19,15 +20,30 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_fwd_tail(c
 {
     using T = typename WV::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pdl_begin();
-    fwd_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
+    const uint32_t gen = chain_begin(p.chain);
+    T *bufA = reinterpret_cast<T *>(smem_raw), *bufB = reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES);
+    if (p.chain.in) {   // chained: wait for every row block of the LL band, read it through L2
+        for (int b = threadIdx.x; b < p.chain.in_nblocks; b += TAIL_THREADS) chain_wait(p.chain, gen, blockIdx.x, b);
+        __syncthreads();
+        fwd_tail_body<WV>(p, blockIdx.x, bufA, bufB, LdCg());
+    } else {
+        fwd_tail_body<WV>(p, blockIdx.x, bufA, bufB, LdNc());
+    }
+    if (p.chain.gen) {
+        __syncthreads();
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.x, 0);
+    }
 }
 template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(const TailParams p)
 {
     using T = typename WV::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    pdl_begin();
+    chain_begin(p.chain);   // first kernel of an inverse chain: its input is complete at launch
     inv_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
+    if (p.chain.gen) {
+        __syncthreads();
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.x, 0);
+    }
 }
 
 int tail_max_elems(int kind) { return TAIL_BUF_BYTES / kind_elem_size(kind); }
@@ -55,12 +71,12 @@ cudaError_t preload_tail()
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_fwd_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); });
+    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_fwd_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, p.chain.pdl, p); });
 }
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
     const size_t sm = 2 * TAIL_BUF_BYTES;
-    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_inv_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, g_use_pdl, p); });
+    dispatch_kind(kind, [&](auto wv) { launch_pdl(k_inv_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, p.chain.pdl, p); });
 }
 
 }  // namespace dwtb200

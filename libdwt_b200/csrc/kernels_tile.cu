@@ -15,6 +15,7 @@
 // bit-identical to the reference whichever kernel family handles a level.
 #include <cooperative_groups.h>
 
+#include "chain.cuh"
 #include "tail_body.cuh"
 
 namespace dwtb200 {
@@ -210,17 +211,48 @@ __device__ __forceinline__ void inv_tile_body(const LevelParams &p, int bx, int 
 }
 
 // ---- stand-alone kernels: one tile per CTA ---------------------------------------------------------
+// Chained (struct Chain): the tile waits for the row blocks of its input the producing kernel has not
+// finished yet, reads them through L2 (they were written while this kernel was already running), and bumps
+// its own row block's counter when its LL rows (forward) / output rows (inverse) are written.
+template <class WV> __device__ __forceinline__ void tile_wait(const LevelParams &p, uint32_t gen, int row_lo, int row_hi)
+{
+    const int b0 = chain_block(p.chain, row_lo), b1 = chain_block(p.chain, row_hi);
+    for (int b = b0 + (int)threadIdx.x; b <= b1; b += TILE_THREADS) chain_wait(p.chain, gen, blockIdx.z, b);
+    __syncthreads();
+}
 template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_tile(const LevelParams p)
 {
+    using C = TileCfg<WV>;
     __shared__ __align__(16) TileSmem<WV> sm;
-    pdl_begin();
-    fwd_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+    const uint32_t gen = chain_begin(p.chain);
+    if (p.chain.in) {
+        const int y0 = blockIdx.y * C::TH;
+        tile_wait<WV>(p, gen, max(y0 - WV::HALO, 0), min(y0 + C::TH + WV::HALO, p.H) - 1);
+        fwd_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdCg());
+    } else {
+        fwd_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+    }
+    if (p.chain.gen) {
+        __syncthreads();
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.z, blockIdx.y);
+    }
 }
 template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(const LevelParams p)
 {
+    using C = TileCfg<WV>;
     __shared__ __align__(16) TileSmem<WV> sm;
-    pdl_begin();
-    inv_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+    const uint32_t gen = chain_begin(p.chain);
+    if (p.chain.in) {   // the LL band comes from the previous kernel of the chain, the other subbands from the source plane
+        const int y0 = blockIdx.y * C::TH;
+        tile_wait<WV>(p, gen, max(y0 - WV::HALO, 0) >> 1, (min(y0 + C::TH + WV::HALO, p.H) - 1) >> 1);
+        inv_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdCg());
+    } else {
+        inv_tile_body<WV>(p, blockIdx.x, blockIdx.y, blockIdx.z, sm, LdNc());
+    }
+    if (p.chain.gen) {
+        __syncthreads();
+        if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.z, blockIdx.y);
+    }
 }
 
 // ---- persistent kernels: every level from the first L2-resident one to the end of the pyramid in ONE
@@ -290,18 +322,25 @@ template <class WV> static dim3 tile_grid(const LevelParams &p, int frames)
     using C = TileCfg<WV>;
     return dim3((p.W + C::TW - 1) / C::TW, (p.H + C::TH - 1) / C::TH, frames);
 }
+int tile_rows() { return TileCfg<W97F>::TH; }
+dim3 tile_grid_of(int kind, const LevelParams &p, int frames)
+{
+    dim3 g;
+    dispatch_kind(kind, [&](auto wv) { g = tile_grid<decltype(wv)>(p, frames); });
+    return g;
+}
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
-        launch_pdl(k_fwd_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+        launch_pdl(k_fwd_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, p.chain.pdl, p);
     });
 }
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
-        launch_pdl(k_inv_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, g_use_pdl, p);
+        launch_pdl(k_inv_tile<WV>, tile_grid<WV>(p, frames), dim3(TILE_THREADS), 0, st, p.chain.pdl, p);
     });
 }
 
