@@ -70,6 +70,19 @@ int dwtb200_fwd2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, i
 int dwtb200_inv2_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
                       int size_i_big_x, int size_i_big_y, int j_max, int decompose_one, int zero_padding);
 
+/* out-of-place variants, dwt_cdf97_2f_s2 / dwt_cdf97_2i_s2 (src/libdwt.h:667-679, 962-974; src/libdwt.c:12619, 17985):
+ * `src` is read, `dst` (same strides) receives the result; what the reference leaves of dst's old content in a sparse
+ * layout is left here too */
+int dwtb200_fwd2_host2(int kind, const void *src, void *dst, int64_t stride_x, int64_t stride_y, int size_o_big_x,
+                       int size_o_big_y, int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+int dwtb200_inv2_host2(int kind, const void *src, void *dst, int64_t stride_x, int64_t stride_y, int size_o_big_x,
+                       int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* the reference's performance protocol on the device, dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i
+ * (src/libdwt.h:2498-2513, src/libdwt.c:21391, 21262): M device-resident test images, N loops of M forward then M
+ * inverse transforms, minimum over the loops of the mean seconds per transform (CUDA events, no host copies) */
+int dwtb200_perf2(int kind, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max,
+                  int decompose_one, int zero_padding, int M, int N, float *fwd_secs, float *inv_secs);
+
 /* device time (CUDA events on the library stream) of the transform inside the last *_host call, in
  * milliseconds, host<->device copies excluded; replaces dwt_util_get_clock() brackets (src/libdwt.c:18701) */
 double dwtb200_last_transform_ms(void);

@@ -53,6 +53,20 @@ void dwt_cdf97_2f_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int
 void dwt_cdf97_2i_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                     int size_i_big_y, int j_max, int decompose_one, int zero_padding);
 
+/* out-of-place 9/7 float: src/libdwt.h:667-679, 962-974 (src/libdwt.c:12619, 17985) */
+void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                     int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2i_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                     int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* the performance harness re-pointed at the device: src/libdwt.h:2498-2513 (src/libdwt.c:21391, 21262); M images, N loops,
+ * minimum of the mean seconds per transform, measured with CUDA events on HBM-resident images */
+void dwt_util_perf_cdf97_2_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                             int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                             float *inv_secs);
+void dwt_util_perf_cdf53_2_i(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                             int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                             float *inv_secs);
+
 /* src/libdwt.h:1382-1409 (src/libdwt.c:1437, 1482): page-locked host memory instead of memalign(16, ...) */
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y);
 void dwt_util_free_image(void **pptr);

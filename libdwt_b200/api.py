@@ -30,6 +30,9 @@ SYMBOLS = [
     ("dwtb200_ceil_log2", _i, [_i]), ("dwtb200_clamp_j", _i, [_i, _i, _i, _i]),
     ("dwtb200_fwd2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
     ("dwtb200_inv2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_fwd2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
+    ("dwtb200_inv2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_perf2", _i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
     ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
     ("dwtb200_image_upload", _i, [_vp, _i, _vp, _i64, _i64]), ("dwtb200_image_download", _i, [_vp, _i, _vp, _i64, _i64]),
@@ -132,6 +135,34 @@ def dwt_cdf53_2f_d(*a): _fwd(CDF53_F64, *a)
 def dwt_cdf53_2i_d(*a): _inv(CDF53_F64, *a)
 def dwt_cdf97_2f_i(*a): _fwd(CDF97_I32, *a)
 def dwt_cdf97_2i_i(*a): _inv(CDF97_I32, *a)
+
+
+def dwt_cdf97_2f_s2(src, dst, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max_ptr, decompose_one,
+                    zero_padding):
+    j = C.c_int(j_max_ptr[0] if isinstance(j_max_ptr, list) else j_max_ptr.value)
+    L = lib()
+    L.check(L.c.dwtb200_fwd2_host2(CDF97_F32, _addr(src), _addr(dst), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                   size_i_big_y, C.byref(j), decompose_one, zero_padding))
+    if isinstance(j_max_ptr, list):
+        j_max_ptr[0] = j.value
+    else:
+        j_max_ptr.value = j.value
+
+
+def dwt_cdf97_2i_s2(src, dst, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max, decompose_one,
+                    zero_padding):
+    L = lib()
+    L.check(L.c.dwtb200_inv2_host2(CDF97_F32, _addr(src), _addr(dst), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                   size_i_big_y, j_max, decompose_one, zero_padding))
+
+
+def perf2(kind, size_x, size_y, j_max=-1, M=1, N=1, inner=None, decompose_one=0, zero_padding=0):
+    """dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i on the device: (fwd_secs, inv_secs) per transform."""
+    iy, ix = inner if inner is not None else (size_y, size_x)
+    f, i = C.c_float(), C.c_float()
+    L = lib()
+    L.check(L.c.dwtb200_perf2(kind, size_x, size_y, ix, iy, j_max, decompose_one, zero_padding, M, N, C.byref(f), C.byref(i)))
+    return f.value, i.value
 
 
 # ---- numpy conveniences with the calling shape of oracle/orc.py (images are [y, x] arrays) ----

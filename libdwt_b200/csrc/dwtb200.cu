@@ -69,7 +69,7 @@ struct Ctx {
     int pfd = 1;
     int pipeline = 1;   // pipelined host path for large dense images
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
-    int ring_waves = 5, ring_pps_min = 0, ring_pps_max = 0;
+    int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // profiles/geo_r1.txt
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
@@ -329,22 +329,29 @@ static inline size_t host_span(int ox, int oy, int64_t sx, int64_t sy, size_t es
     return (size_t)((int64_t)(oy - 1) * sx + (int64_t)(ox - 1) * sy) + es;
 }
 
+// the top-left w x h samples of a host image -> the current plane of `frame`
+static int upload_region(dwtb200_image *im, int frame, const void *host, int64_t sx, int64_t sy, int w, int h)
+{
+    if (w <= 0 || h <= 0) return DWTB200_OK;
+    char *d = frame_ptr(im, im->cur, frame);
+    if (sy == (int64_t)im->es && sx >= (int64_t)(w * im->es)) {
+        CK(cudaMemcpy2DAsync(d, im->pitch * im->es, host, (size_t)sx, w * im->es, h, cudaMemcpyDefault, g.st));
+    } else {
+        const size_t span = host_span(w, h, sx, sy, im->es);
+        int r = ensure_stage(span);
+        if (r) return r;
+        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
+        launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, w, h, 1, g.st);
+        CK(cudaGetLastError());
+    }
+    return DWTB200_OK;
+}
+
 int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t sx, int64_t sy)
 {
     NEED_DEV();
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_upload: bad arguments");
-    char *d = frame_ptr(im, im->cur, frame);
-    if (sy == (int64_t)im->es && sx >= (int64_t)(im->ox * im->es)) {
-        CK(cudaMemcpy2DAsync(d, im->pitch * im->es, host, (size_t)sx, im->ox * im->es, im->oy, cudaMemcpyDefault, g.st));
-    } else {
-        const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
-        int r = ensure_stage(span);
-        if (r) return r;
-        CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
-        launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 1, g.st);
-        CK(cudaGetLastError());
-    }
-    return DWTB200_OK;
+    return upload_region(im, frame, host, sx, sy, im->ox, im->oy);
 }
 
 int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx, int64_t sy)
@@ -843,6 +850,7 @@ void generic_level(dwtb200_image *im, bool inverse, bool first_along_x, bool do_
     char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];
     auto pass = [&](char *s, char *d, bool along_x) {
         PassParams p;
+        memset(&p, 0, sizeof p);
         p.src = s;
         p.dst = d;
         p.src_pitch = p.dst_pitch = im->pitch;
@@ -872,32 +880,76 @@ void generic_level(dwtb200_image *im, bool inverse, bool first_along_x, bool do_
     }
 }
 
-void run_fwd_generic(dwtb200_image *im, int ix, int iy, int J, int zero_padding)
+// level 0 of the out-of-place forward transform on a sparse layout (dwt_cdf97_2f_s2, src/libdwt.c:12678-12745): plane A
+// (current) holds dst's old content, plane B the source samples; the first pass that runs reads B and writes only its L / H
+// outputs into A, the rest of A keeps dst's content; the second pass runs in place on A
+void s2_level0(dwtb200_image *im, int ix, int iy)
+{
+    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];
+    const bool gd = guard(im->kind);
+    const bool rows = !gd || im->ox > 1, cols = !gd || im->oy > 1;
+    const int odx = cdiv_pow2(im->ox, 1), ody = cdiv_pow2(im->oy, 1);
+    auto pass = [&](char *s, char *d, bool along_x, int keep) {
+        PassParams p;
+        memset(&p, 0, sizeof p);
+        p.src = s;
+        p.dst = d;
+        p.src_pitch = p.dst_pitch = im->pitch;
+        p.src_frame = p.dst_frame = im->frame;
+        p.region_w = im->ox;
+        p.region_h = im->oy;
+        p.along_x = along_x ? 1 : 0;
+        p.N = along_x ? ix : iy;
+        p.off_h = along_x ? odx : ody;
+        p.keep_dst = keep;
+        launch_pass_fwd(im->kind, p, im->frames, g.st);
+        g.launches++;
+    };
+    if (rows) {
+        pass(B, A, true, 1);
+        if (cols) {
+            pass(A, B, false, 0);
+            launch_copy2d((int)im->es, A, im->pitch, B, im->pitch, im->ox, im->oy, im->frame, im->frame, im->frames, g.st);
+            g.launches++;
+        }
+    } else if (cols) {
+        pass(B, A, false, 1);
+    }
+}
+
+// src/libdwt.c:12896-12916: after level j, zero what lies between the inner subbands and the outer ones
+void fwd_zero_padding(dwtb200_image *im, int ix, int iy, int j)
+{
+    const int osx = cdiv_pow2(im->ox, j), osy = cdiv_pow2(im->oy, j);
+    const int odx = cdiv_pow2(im->ox, j + 1), ody = cdiv_pow2(im->oy, j + 1);
+    const int isx = cdiv_pow2(ix, j), isy = cdiv_pow2(iy, j);
+    ZeroParams z;
+    z.buf = im->plane[im->cur];
+    z.pitch = im->pitch;
+    z.frame = im->frame;
+    z.region_w = osx;
+    z.region_h = osy;
+    z.x0a = (isx + 1) >> 1;
+    z.x0b = odx;
+    z.x1a = odx + (isx >> 1);
+    z.x1b = osx;
+    z.y0a = (isy + 1) >> 1;
+    z.y0b = ody;
+    z.y1a = ody + (isy >> 1);
+    z.y1b = osy;
+    launch_zero(im->kind, z, im->frames, g.st);
+    g.launches++;
+}
+
+void run_fwd_generic(dwtb200_image *im, int ix, int iy, int J, int zero_padding, int jstart = 0)
 {
     const bool gd = guard(im->kind);
-    for (int j = 0; j < J; j++) {
+    for (int j = jstart; j < J; j++) {
         const int osx = cdiv_pow2(im->ox, j), osy = cdiv_pow2(im->oy, j);
         const int odx = cdiv_pow2(im->ox, j + 1), ody = cdiv_pow2(im->oy, j + 1);
         const int isx = cdiv_pow2(ix, j), isy = cdiv_pow2(iy, j);
         generic_level(im, false, true, !gd || osx > 1, !gd || osy > 1, osx, osy, isx, isy, odx, ody);
-        if (zero_padding) {   // src/libdwt.c:12896-12916
-            ZeroParams z;
-            z.buf = im->plane[im->cur];
-            z.pitch = im->pitch;
-            z.frame = im->frame;
-            z.region_w = osx;
-            z.region_h = osy;
-            z.x0a = (isx + 1) >> 1;
-            z.x0b = odx;
-            z.x1a = odx + (isx >> 1);
-            z.x1b = osx;
-            z.y0a = (isy + 1) >> 1;
-            z.y0b = ody;
-            z.y1a = ody + (isy >> 1);
-            z.y1b = osy;
-            launch_zero(im->kind, z, im->frames, g.st);
-            g.launches++;
-        }
+        if (zero_padding) fwd_zero_padding(im, ix, iy, j);
     }
 }
 
@@ -1294,6 +1346,110 @@ int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int o
     NEED_DEV();
     if (!ptr) return fail(DWTB200_EINVAL, "inv2_host: null argument");
     return host_transform(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
+}
+
+// Out of place (dwt_cdf97_2f_s2 / 2i_s2, src/libdwt.c:12619, 17985): the first pass of the first level reads `src`
+// and writes `dst`, everything after that runs in place on `dst` (src/libdwt.c:12700 "src = dst"); the inverse copies
+// the inner region of `src` into `dst` first (:18000).  Both are therefore the in-place transform of `dst` with the
+// region that first pass reads replaced by `src` -- which is what is done here, on the device copy of `dst`.
+static int host_transform2(bool inverse, int kind, const void *src, void *dst, int64_t sx, int64_t sy, int ox, int oy, int ix,
+                           int iy, int *j_io, int decompose_one, int zero_padding)
+{
+    if (ix < 1 || iy < 1 || ix > ox || iy > oy) return fail(DWTB200_EINVAL, "inner size %d x %d outside outer %d x %d", ix, iy, ox, oy);
+    const int J = dwtb200_clamp_j(*j_io, ox, oy, decompose_one);
+    if (!inverse) *j_io = J;
+    int rw = ix, rh = iy;   // region of `src` that reaches `dst`
+    if (!inverse) {
+        if (J == 0) return DWTB200_OK;                  // no level: dst is not touched at all
+        if (!guard(kind) || ox > 1) rh = oy;            // row pass first: every outer row, inner columns (:12680)
+        else rw = ox;                                   // row pass skipped: the column pass reads src (:12713)
+    }
+    dwtb200_image *im = host_image(kind, ox, oy);
+    if (!im) return DWTB200_ENOMEM;
+    int r = DWTB200_OK;
+    const bool covers = rw == ox && rh == oy;
+    if (inverse || covers) {   // the region replaces dst's content before anything is computed: overlay, then in place
+        if (!covers) r = dwtb200_image_upload(im, 0, dst, sx, sy);
+        if (!r) r = upload_region(im, 0, src, sx, sy, rw, rh);
+        if (!r) r = inverse ? dwtb200_image_inv2(im, ix, iy, J, decompose_one, zero_padding)
+                            : dwtb200_image_fwd2(im, ix, iy, j_io, decompose_one, zero_padding);
+    } else {
+        // sparse forward: the first pass writes only its L / H outputs into dst, whose other samples keep their content
+        r = dwtb200_image_upload(im, 0, dst, sx, sy);
+        if (!r) {
+            im->cur ^= 1;
+            r = upload_region(im, 0, src, sx, sy, rw, rh);   // the source samples go to the other plane
+            im->cur ^= 1;
+        }
+        if (!r) {
+            s2_level0(im, ix, iy);
+            if (zero_padding) fwd_zero_padding(im, ix, iy, 0);
+            run_fwd_generic(im, ix, iy, J, zero_padding, 1);
+            im->last_path = 1;
+            CK(cudaGetLastError());
+        }
+    }
+    if (!r) r = dwtb200_image_download(im, 0, dst, sx, sy);
+    return r;
+}
+int dwtb200_fwd2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
+                       int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!src || !dst || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_host2: null argument");
+    return host_transform2(false, kind, src, dst, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one, zero_padding);
+}
+int dwtb200_inv2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
+                       int decompose_one, int zero_padding)
+{
+    NEED_DEV();
+    if (!src || !dst) return fail(DWTB200_EINVAL, "inv2_host2: null argument");
+    return host_transform2(true, kind, src, dst, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
+}
+
+// The reference's performance protocol (dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i, src/libdwt.c:21391, 21262)
+// on the device: M images filled with the test pattern, N loops of "M forward transforms, then M inverse transforms",
+// the minimum over the loops of the mean time per transform -- timed with CUDA events on the library stream instead
+// of dwt_util_get_clock, the images resident in HBM (M of them cycled, like the reference's cache flush).
+int dwtb200_perf2(int kind, int ox, int oy, int ix, int iy, int j_max, int decompose_one, int zero_padding, int M, int N,
+                  float *fwd_secs, float *inv_secs)
+{
+    NEED_DEV();
+    if (M < 1 || N < 1 || !fwd_secs || !inv_secs) return fail(DWTB200_EINVAL, "perf2: bad arguments");
+    std::vector<dwtb200_image *> imgs;
+    int r = DWTB200_OK;
+    for (int m = 0; m < M && !r; m++) {
+        dwtb200_image *im = dwtb200_image_create(kind, ox, oy, 1);
+        if (!im) r = DWTB200_ENOMEM;
+        else {
+            imgs.push_back(im);
+            r = dwtb200_image_fill(im, 0, 0, 0);
+        }
+    }
+    float best_f = 1e30f, best_i = 1e30f;
+    std::vector<int> j(M, j_max);
+    for (int n = -1; n < N && !r; n++) {   // loop -1 warms up (graph capture)
+        float ms = 0;
+        if (!r) r = dwtb200_timer_start();
+        for (int m = 0; m < M && !r; m++) {
+            j[m] = j_max;
+            r = dwtb200_image_fwd2(imgs[m], ix, iy, &j[m], decompose_one, zero_padding);
+        }
+        if (!r) {
+            ms = (float)dwtb200_timer_stop_ms();
+            if (n >= 0 && ms / M < best_f) best_f = ms / M;
+        }
+        if (!r) r = dwtb200_timer_start();
+        for (int m = 0; m < M && !r; m++) r = dwtb200_image_inv2(imgs[m], ix, iy, j[m], decompose_one, zero_padding);
+        if (!r) {
+            ms = (float)dwtb200_timer_stop_ms();
+            if (n >= 0 && ms / M < best_i) best_i = ms / M;
+        }
+    }
+    for (dwtb200_image *im : imgs) dwtb200_image_destroy(im);
+    *fwd_secs = best_f * 1e-3f;
+    *inv_secs = best_i * 1e-3f;
+    return r;
 }
 
 // =====================================================================================================

@@ -108,6 +108,7 @@ struct PassParams {
     int along_x;              // 1: lines are rows, 0: lines are columns
     int N;                    // inner line length
     int off_h;                // position of the H half along the line
+    int keep_dst;             // 1: samples the line function does not write keep dst's content instead of being copied from src
 };
 void launch_pass_fwd(int kind, const PassParams &p, int frames, cudaStream_t st);
 void launch_pass_inv(int kind, const PassParams &p, int frames, cudaStream_t st);

@@ -39,11 +39,13 @@ template <class WV> __global__ void __launch_bounds__(256) k_pass_fwd(PassParams
             if (q < nh) d[(p.off_h + q) * de] = H;
         }
         const bool in_l = q < nl, in_h = q >= p.off_h && q < p.off_h + nh;
-        if (!in_l && !in_h) d[q * de] = s[q * se];
-    } else {
+        if (!in_l && !in_h && !p.keep_dst) d[q * de] = s[q * se];
+    } else if (!p.keep_dst) {
         T v = s[q * se];
         if (N == 1 && q == 0 && WV::HAS_ONE) v = WV::one_f(v);
         d[q * de] = v;
+    } else if (N == 1 && q == 0 && WV::HAS_ONE) {
+        d[0] = WV::one_f(s[0]);
     }
 }
 

@@ -46,6 +46,41 @@ INV(dwt_cdf53_2i_d, DWTB200_CDF53_F64)
 FWD(dwt_cdf97_2f_i, DWTB200_CDF97_I32)
 INV(dwt_cdf97_2i_i, DWTB200_CDF97_I32)
 
+void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                     int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)
+{
+    const int rc = dwtb200_fwd2_host2(DWTB200_CDF97_F32, src, dst, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                      size_i_big_y, j_max_ptr, decompose_one, zero_padding);
+    if (rc) die("dwt_cdf97_2f_s2", rc);
+}
+void dwt_cdf97_2i_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                     int size_i_big_y, int j_max, int decompose_one, int zero_padding)
+{
+    const int rc = dwtb200_inv2_host2(DWTB200_CDF97_F32, src, dst, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                      size_i_big_y, j_max, decompose_one, zero_padding);
+    if (rc) die("dwt_cdf97_2i_s2", rc);
+}
+
+/* the reference's perf harness, timed on the device (strides and clock type have no meaning for HBM-resident images) */
+void dwt_util_perf_cdf97_2_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                             int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                             float *inv_secs)
+{
+    (void)stride_x; (void)stride_y; (void)clock_type;
+    const int rc = dwtb200_perf2(DWTB200_CDF97_F32, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max, decompose_one,
+                                 zero_padding, M, N, fwd_secs, inv_secs);
+    if (rc) die("dwt_util_perf_cdf97_2_s", rc);
+}
+void dwt_util_perf_cdf53_2_i(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                             int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                             float *inv_secs)
+{
+    (void)stride_x; (void)stride_y; (void)clock_type;
+    const int rc = dwtb200_perf2(DWTB200_CDF53_I32, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max, decompose_one,
+                                 zero_padding, M, N, fwd_secs, inv_secs);
+    if (rc) die("dwt_util_perf_cdf53_2_i", rc);
+}
+
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y)
 {
     (void)stride_y;

@@ -69,6 +69,70 @@ class Oracle:
         getattr(self.lib, f"orc_{self._fn(wavelet, t)}_2i")(
             _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
 
+    def fwd2_s2(self, src, dst, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        """dwt_cdf97_2f_s2 (src/libdwt.c:12619): the first pass of level 0 that runs reads its lines from src and writes
+        only their L / H halves into dst (:12680-12745, then `src = dst`); everything after that is in place on dst.
+        Restated with the in-place oracle: run level 0 on a scratch copy whose inner lines are src, take from it exactly
+        the samples that pass wrote, then continue in place."""
+        oy, ox = dst.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        lim = self.ceil_log2(max(ox, oy) if decompose_one else min(ox, oy))
+        J = lim if (j_max < 0 or j_max > lim) else j_max
+        if J == 0:
+            return 0
+        if (ix, iy) == (ox, oy):   # dense: every sample of dst is written by the first pass
+            dst[...] = src
+            return self.fwd2(dst, "97", "s", j_max=j_max, decompose_one=decompose_one, zero_padding=zero_padding, inner=inner)
+        import numpy as np
+        nl, nh = (ix + 1) // 2, ix // 2
+        odx, ody = (ox + 1) // 2, (oy + 1) // 2
+        if ox > 1:   # row pass: rows of length ix from src, as a 1-level transform of an (oy x ix)-inner, 1-row-high problem
+            for y in range(oy):
+                line = np.ascontiguousarray(src[y:y + 1, :ix]).copy()
+                if ix >= 2:
+                    tmp = np.zeros((1, ix), np.float32)
+                    tmp[...] = line
+                    self.fwd2(tmp, "97", "s", j_max=1, decompose_one=1)   # one level along x only (height 1: the column pass is skipped)
+                    dst[y, :nl] = tmp[0, :nl]
+                    dst[y, odx:odx + nh] = tmp[0, nl:nl + nh]
+                else:
+                    dst[y, 0] = np.float32(line[0, 0]) * np.float32(1.1496043988602)
+            # column pass of level 0 in place on dst, zero padding, then the remaining levels: emulate with a 1-level
+            # transform restricted to columns, i.e. transpose trick: a (ox x oy) image whose rows are dst's columns
+            t = np.ascontiguousarray(dst.T).copy()
+            if oy > 1:
+                for x in range(ox):
+                    col = np.zeros((1, iy), np.float32)
+                    col[...] = t[x:x + 1, :iy]
+                    if iy >= 2:
+                        self.fwd2(col, "97", "s", j_max=1, decompose_one=1)
+                        nly, nhy = (iy + 1) // 2, iy // 2
+                        t[x, :nly] = col[0, :nly]
+                        t[x, ody:ody + nhy] = col[0, nly:nly + nhy]
+                    else:
+                        t[x, 0] = np.float32(col[0, 0]) * np.float32(1.1496043988602)
+            dst[...] = t.T
+        else:
+            raise NotImplementedError("width-1 sparse out-of-place case")
+        if zero_padding:
+            nly, nhy = (iy + 1) // 2, iy // 2
+            dst[:, nl:odx] = 0
+            dst[:, odx + nh:ox] = 0
+            dst[nly:ody, :] = 0
+            dst[ody + nhy:oy, :] = 0
+        if J > 1:   # levels 1 .. J-1: the in-place transform of the LL quadrant region, i.e. of an image half the size
+            sub = dst[:ody, :odx]
+            self.fwd2(sub, "97", "s", j_max=J - 1, decompose_one=decompose_one, zero_padding=zero_padding,
+                      inner=((iy + 1) // 2, (ix + 1) // 2))
+        return J
+
+    def inv2_s2(self, src, dst, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        """dwt_cdf97_2i_s2 (src/libdwt.c:17985): copies the inner region of src into dst (:18000), then in place."""
+        oy, ox = dst.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        dst[:iy, :ix] = src[:iy, :ix]
+        self.inv2(dst, "97", "s", j_max=j_max, decompose_one=decompose_one, zero_padding=zero_padding, inner=inner)
+
     def fill(self, img, t, rand=0, type_=0, wrap32=1):
         ny, nx = img.shape
         if t == "s":
@@ -129,6 +193,8 @@ class Ref:
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci]
         for n in ("dwt_util_test_image_fill2_s", "dwt_util_test_image_fill2_i"):
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci]
+        L.dwt_cdf97_2f_s2.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
+        L.dwt_cdf97_2i_s2.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         L.dwt_util_set_num_threads.argtypes = [ci]
         L.dwt_util_get_num_threads.restype = ci
         L.dwt_util_set_accel.argtypes = [ci]
@@ -167,6 +233,20 @@ class Ref:
         iy, ix = inner if inner is not None else (oy, ox)
         getattr(self.lib, self._fn(wavelet, t, "i"))(
             _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
+
+    def fwd2_s2(self, src, dst, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        assert src.strides == dst.strides
+        oy, ox = dst.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        j = C.c_int(j_max)
+        self.lib.dwt_cdf97_2f_s2(_ptr(src), _ptr(dst), dst.strides[0], dst.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one, zero_padding)
+        return j.value
+
+    def inv2_s2(self, src, dst, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
+        assert src.strides == dst.strides
+        oy, ox = dst.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        self.lib.dwt_cdf97_2i_s2(_ptr(src), _ptr(dst), dst.strides[0], dst.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
 
     def fill(self, img, t, rand=0, type_=0, wrap32=1):
         self._check(img)

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["simple", "simple-int", "simple-double"])
+@pytest.mark.parametrize("name", ["simple", "simple-int", "simple-double", "simple-perf", "simple-perf-int"])
 def test_unmodified_example_runs_on_the_gpu(name, tmp_path):
     exe = os.path.join(ROOT, "build", "examples", name)
     assert os.path.exists(exe), f"{exe} missing: run `make examples` in the build container (it travels via gpurun)"
@@ -19,3 +19,7 @@ def test_unmodified_example_runs_on_the_gpu(name, tmp_path):
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-2000:]
     assert "success" in out and "images differs" not in out, out[-2000:]
+    if "perf" in name:   # dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i timed on the device
+        import re
+        m = re.search(r"performance test: fwd=([0-9.eE+-]+) secs", out)
+        assert m and 0 < float(m.group(1)) < 0.01, out[-2000:]   # 1920x1080, one level: well under 10 ms on a B200

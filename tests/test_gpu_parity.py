@@ -436,3 +436,35 @@ def test_pipelined_host_path(dev, oracle, kind):
     finally:
         L.check(L.c.dwtb200_set_tuning(5, 1))
     report(fails)
+
+
+# ---- out-of-place transforms and the perf harness -----------------------------
+def test_out_of_place_transforms(dev, oracle):
+    from test_oracle import S2_CASES
+    fails = []
+    for (ox, oy, ix, iy, j, d1, zp) in S2_CASES + [(3001, 2999, 3001, 2999, -1, 0, 0)]:
+        src = oracle.fill(np.zeros((oy, ox), np.float32), "s")
+        da = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=2) + 3
+        db = da.copy()
+        Ja = oracle.fwd2_s2(src, da, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        jj = [j]
+        dev.dwt_cdf97_2f_s2(src, db, db.strides[0], db.strides[1], ox, oy, ix, iy, jj, d1, zp)
+        if jj[0] != Ja or not (bits(da, "s") == bits(db, "s")).all():
+            fails.append(f"s2 forward {(ox, oy, ix, iy, j, d1, zp)}: " + describe_mismatch(db, da, "s"))
+            db[...] = da
+        ea = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=1) - 2
+        eb = ea.copy()
+        oracle.inv2_s2(da, ea, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        dev.dwt_cdf97_2i_s2(db, eb, eb.strides[0], eb.strides[1], ox, oy, ix, iy, Ja, d1, zp)
+        if not (bits(ea, "s") == bits(eb, "s")).all():
+            fails.append(f"s2 inverse {(ox, oy, ix, iy, j, d1, zp)}: " + describe_mismatch(eb, ea, "s"))
+    report(fails)
+
+
+def test_perf_harness_on_device(dev):
+    """dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i re-pointed at the device: plausible device times."""
+    for kind in (dev.CDF97_F32, dev.CDF53_I32):
+        f, i = dev.perf2(kind, 1920, 1080, j_max=1, M=4, N=4)
+        assert 0 < f < 5e-3 and 0 < i < 5e-3, (f, i)
+        f13, i13 = dev.perf2(kind, 2048, 2048, j_max=-1, M=2, N=3)
+        assert 0 < f13 < 5e-3 and 0 < i13 < 5e-3

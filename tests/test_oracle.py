@@ -122,3 +122,24 @@ def test_oracle_vs_reference_config_sizes(oracle, ref):
         ref.inv2(a, w, t, j_max=Ja)
         oracle.inv2(b, w, t, j_max=Jb)
         assert (bits(a, t) == bits(b, t)).all()
+
+
+S2_CASES = [(64, 64, 64, 64, -1, 0, 0), (517, 301, 517, 301, -1, 0, 0), (64, 64, 50, 37, -1, 0, 1), (128, 96, 128, 50, 2, 0, 0),
+            (100, 80, 33, 80, -1, 1, 0), (1, 9, 1, 9, -1, 1, 0), (9, 1, 9, 1, -1, 1, 0), (33, 70, 17, 5, -1, 0, 1), (16, 16, 16, 16, 0, 0, 0)]
+
+
+def test_out_of_place_semantics_match_reference(oracle, ref):
+    """dwt_cdf97_2f_s2 / 2i_s2: the oracle's restatement (overlay + in place) against the compiled reference, including
+    what is left of dst's previous content in sparse layouts."""
+    for (ox, oy, ix, iy, j, d1, zp) in S2_CASES:
+        src = oracle.fill(np.zeros((oy, ox), np.float32), "s")
+        da = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=2) + 3
+        db = da.copy()
+        Ja = ref.fwd2_s2(src, da, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        Jb = oracle.fwd2_s2(src, db, j_max=j, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        assert Ja == Jb and (bits(da, "s") == bits(db, "s")).all(), (ox, oy, ix, iy, j, d1, zp, describe_mismatch(db, da, "s"))
+        ea = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=1) - 2
+        eb = ea.copy()
+        ref.inv2_s2(da, ea, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        oracle.inv2_s2(db, eb, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
+        assert (bits(ea, "s") == bits(eb, "s")).all(), (ox, oy, ix, iy, j, d1, zp, describe_mismatch(eb, ea, "s"))
