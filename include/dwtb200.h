@@ -145,10 +145,12 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips and download for large dense images (1)
  *   DWTB200_TUNE_RING      bit 0 / bit 1: forward / inverse streaming levels stage their input through a shared-memory
  *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer
+ *   DWTB200_TUNE_PYR       T > 0: runs of tile levels are fused: one launch carries T x T tiles of the last level's LL band
+ *                          through up to three levels in shared memory (0 = one tile launch per level)
  *   DWTB200_TUNE_CHAIN     1: the kernels of a pyramid are launched with programmatic stream serialization and wait for
  *                          their input row block by row block on completion counters, so consecutive levels overlap (1) */
 enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2, DWTB200_TUNE_PDL = 3, DWTB200_TUNE_NARROW = 4,
-       DWTB200_TUNE_PIPELINE = 5, DWTB200_TUNE_RING = 6, DWTB200_TUNE_CHAIN = 7 };
+       DWTB200_TUNE_PIPELINE = 5, DWTB200_TUNE_RING = 6, DWTB200_TUNE_CHAIN = 7, DWTB200_TUNE_PYR = 8 };
 int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t

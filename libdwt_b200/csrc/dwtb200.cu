@@ -70,6 +70,8 @@ struct Ctx {
     int pipeline = 1;   // pipelined host path for large dense images
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
     int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // profiles/geo_r1.txt
+    int64_t pyr_max_in = (int64_t)512 * 512;   // only levels with at most this many input samples per frame are fused
+    int pyr = 0;        // > 0: runs of tile levels are fused, tiles of this edge carried through up to 3 levels (kernels_pyr.cu)
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
@@ -169,6 +171,7 @@ int dwtb200_init(int device)
     g.sm_count = prop.multiProcessorCount;
     CK(preload_stream());
     CK(preload_ring());
+    CK(preload_pyr());
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
@@ -248,6 +251,8 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
+    case DWTB200_TUNE_PYR: g.pyr = (int)value; break;
+    case 96: g.pyr_max_in = value; break;
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
     case 99: g.dbg = (int)value; break;   // measurement only, see kernels.h
@@ -464,12 +469,13 @@ struct Band {   // where an LL band lives
 //   TILE    kernels_tile.cu     one launch per level, small tiles (only when the persistent kernel is off)
 //   MID     kernels_tile.cu     L2-resident levels: ALL of them plus the tail in ONE cooperative launch
 //   TAIL    kernels_tail.cu     every remaining level once the LL band fits one CTA's shared memory
-enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2 };
+enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2, PLAN_PYR = 3 };   // PLAN_PYR: first level of a fused group (pyr_len levels)
 struct DensePlan {
     int jt;                 // first level of the tail (== J: no tail); -1: the dense kernels cannot take this pyramid
     int jm;                 // first level of the persistent launch (== jt when it holds no tile level)
     bool tail_in_mid;       // the tail runs inside the persistent launch
     int type[40];
+    int pyr_len[40];
 };
 
 DensePlan dense_plan(const dwtb200_image *im, int J)
@@ -501,6 +507,20 @@ DensePlan dense_plan(const dwtb200_image *im, int J)
         }
     }
     pl.tail_in_mid = mid_on && pl.jt < J && pl.jm < pl.jt;
+    // runs of tile levels become fused groups (forward only so far; the inverse keeps one tile launch per level)
+    for (int j = 0; j < 40; j++) pl.pyr_len[j] = 0;
+    if (g.pyr > 0) {
+        const int maxf = pyr_max_levels(im->kind);
+        for (int j = 0; j < pl.jt;) {
+            int f = 0;
+            while (j + f < pl.jt && f < maxf && pl.type[j + f] == PLAN_TILE &&
+                   (int64_t)cdiv_pow2(im->ox, j + f) * cdiv_pow2(im->oy, j + f) <= g.pyr_max_in &&
+                   std::min(cdiv_pow2(im->ox, j + f), cdiv_pow2(im->oy, j + f)) >= pyr_min_side())
+                f++;
+            if (f >= 2) pl.pyr_len[j] = f;
+            j += f > 0 ? f : 1;
+        }
+    }
     return pl;
 }
 
@@ -621,7 +641,9 @@ void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
 
 // ---- the dense path as a list of launches, linked into a chain (struct Chain, kernels.h) ----------------
 struct Launch {
-    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
+    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, PYR_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
+    Band pin, pout;   // PYR_*: input / output band of the group
+    int pj0 = 0, pF = 0;
     LevelParams lp;
     TailParams tp;
     MidParams mp;
@@ -711,6 +733,10 @@ int issue(dwtb200_image *im, std::vector<Launch> &ls)
         case Launch::TILE_F: launch_fwd_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_F: launch_fwd_tail(im->kind, l.tp, im->frames, g.st); break;
         case Launch::MID_F: e = launch_fwd_mid(im->kind, l.mp, g.st); break;
+        case Launch::PYR_F:
+            launch_fwd_pyr(im->kind, l.pin.p, l.pin.pitch, l.pin.frame, l.pout.p, l.pout.pitch, l.pout.frame, im->plane[im->cur ^ 1],
+                           im->pitch, im->frame, im->ox, im->oy, l.pj0, l.pF, im->frames, g.pyr, g.st);
+            break;
         case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, (g.ring >> 4) & 3, g.st); break;
         case Launch::REG_I: launch_inv_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_I: launch_inv_tile(im->kind, l.lp, im->frames, g.st); break;
@@ -766,6 +792,18 @@ void plan_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart, s
                 mp.tail = tail_params(pl.jt, in);
             }
             return;
+        }
+        if (pl.pyr_len[j] >= 2) {   // levels j .. j+F-1 in one launch
+            const int F = pl.pyr_len[j];
+            L.type = Launch::PYR_F;
+            memset(&L.lp, 0, sizeof L.lp);
+            L.pin = in;
+            L.pout = (j + F == J) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j + F - 1);
+            L.pj0 = j;
+            L.pF = F;
+            in = L.pout;
+            j += F - 1;
+            continue;
         }
         in = fwd_level_params(im, j, J, in, dst_plane, L.lp);
         plan_level(im, L, false, pl.type[j]);

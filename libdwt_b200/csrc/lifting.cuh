@@ -275,4 +275,56 @@ template <class WV> __device__ __forceinline__ void window_inv(typename WV::T (&
     }
 }
 
+// ---- P output pairs from one window of 2P + 2*HALO samples (kernels_pyr.cu) -------------------------------
+// The same lifting steps as window_fwd / window_inv, evaluated on a longer window so that the redundant work at the
+// window edges is shared by P pairs: forward step S updates the samples of its parity in [S+1, n-2-S], inverse step S
+// those in [2+S, n-2-S]; outputs are w[HALO + 2i] (even) and w[HALO + 1 + 2i] (odd), i < P.
+template <class WV, int S, int N> __device__ __forceinline__ void lift_range_fwd(typename WV::T (&w)[N])
+{
+#pragma unroll
+    for (int q = S + 1; q <= N - 2 - S; q += 2) w[q] = WV::template f<S>(w[q], w[q - 1], w[q + 1]);
+}
+template <class WV, int S, int N> __device__ __forceinline__ void lift_range_inv(typename WV::T (&w)[N])
+{
+#pragma unroll
+    for (int q = 2 + S; q <= N - 2 - S; q += 2) w[q] = WV::template i<S>(w[q], w[q - 1], w[q + 1]);
+}
+template <class WV, int P>
+__device__ __forceinline__ void window_fwd_p(typename WV::T (&w)[2 * P + 2 * WV::HALO], typename WV::T (&L)[P], typename WV::T (&H)[P])
+{
+    constexpr int N = 2 * P + 2 * WV::HALO;
+    lift_range_fwd<WV, 0, N>(w);
+    lift_range_fwd<WV, 1, N>(w);
+    if constexpr (WV::NS == 4) {
+        lift_range_fwd<WV, 2, N>(w);
+        lift_range_fwd<WV, 3, N>(w);
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        L[i] = WV::fse(w[WV::HALO + 2 * i]);
+        H[i] = WV::fso(w[WV::HALO + 1 + 2 * i]);
+    }
+}
+template <class WV, int P>
+__device__ __forceinline__ void window_inv_p(typename WV::T (&w)[2 * P + 2 * WV::HALO], typename WV::T (&E)[P], typename WV::T (&O)[P])
+{
+    constexpr int N = 2 * P + 2 * WV::HALO;
+#pragma unroll
+    for (int q = 0; q < N; q += 2) {
+        w[q] = WV::ise(w[q]);
+        w[q + 1] = WV::iso(w[q + 1]);
+    }
+    lift_range_inv<WV, 0, N>(w);
+    lift_range_inv<WV, 1, N>(w);
+    if constexpr (WV::NS == 4) {
+        lift_range_inv<WV, 2, N>(w);
+        lift_range_inv<WV, 3, N>(w);
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        E[i] = w[WV::HALO + 2 * i];
+        O[i] = w[WV::HALO + 1 + 2 * i];
+    }
+}
+
 }  // namespace dwtb200

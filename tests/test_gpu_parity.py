@@ -106,13 +106,16 @@ FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-
             "ring15x1": (0, 1024, 0, 3 | 16),
             # the same mixes without the dataflow chain between the kernels of a pyramid (DWTB200_TUNE_CHAIN = 0)
             "nochain-default": (1024 * 1024, 1024, 0, 3, 0), "nochain-stream": (0, 0, 0, 3, 0), "nochain-tile": (BIG, 16, 0, 3, 0),
-            "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1)}
-DEFAULT_TUNING = (1024 * 1024, 1024, 0, 3, 1)
+            "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1),
+            # runs of tile levels fused into one launch (DWTB200_TUNE_PYR = tile edge), with and without a tail / ring levels
+            "pyr8": (BIG, 1024, 0, 3, 1, 8), "pyr8-tinytail": (BIG, 16, 0, 3, 1, 8), "pyr4-notail": (BIG, 0, 0, 3, 1, 4),
+            "pyr16+ring": (128 * 128, 256, 0, 3, 1, 16), "pyr8-default": (1024 * 1024, 1024, 0, 3, 1, 8)}
+DEFAULT_TUNING = (1024 * 1024, 1024, 0, 3, 1, 0)
 
 
 def set_tuning(L, t):
-    t = tuple(t) + (3, 1)[len(t) - 3:] if len(t) < 5 else tuple(t)
-    for key, v in zip((0, 1, 2, 6, 7), t):
+    t = tuple(t) + (3, 1, 0)[len(t) - 3:] if len(t) < 6 else tuple(t)
+    for key, v in zip((0, 1, 2, 6, 7, 8), t):
         L.check(L.c.dwtb200_set_tuning(key, v))
 
 
