@@ -69,7 +69,7 @@ struct Ctx {
     int pfd = 1;
     int pipeline = 1;   // pipelined host path for large dense images
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
-    int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // profiles/geo_r1.txt
+    int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // strip-length search range of the ring kernels (0: defaults)
     int64_t pyr_max_in = (int64_t)512 * 512;   // only levels with at most this many input samples per frame are fused
     int pyr = 0;        // > 0: runs of tile levels are fused, tiles of this edge carried through up to 3 levels (kernels_pyr.cu)
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
@@ -562,14 +562,26 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
         // re-read per strip: 3 pairs for 9/7 forward, 4 for inverse)
         const bool ring = !p.narrow && (inverse ? (g.ring & 2) : (g.ring & 1));
         if (ring) {
-            // Measured (profiles/ring_pps_r1.txt): CTAs run at visibly different speeds, so many short CTAs handed out
-            // dynamically beat one long CTA per slot in spite of the warm-up rows every strip re-reads:
-            // aim at >= ring_waves waves of CTAs, strips of 16 .. 32 row pairs (8 .. 16 for the two-step wavelets)
+            // Measured (profiles/ring_pps_r1.txt, pps_single_r1.txt): CTAs run at visibly different speeds, so many short
+            // CTAs handed out dynamically beat one long CTA per slot in spite of the warm-up rows every strip re-reads;
+            // and the last wave matters: 3.85 or 2.9 waves of CTAs run 5-10 % faster than 4.3 or 2.2.  Pick the strip
+            // length with the lowest modelled time: (re-read overhead) / (occupancy of the last wave) + imbalance.
             const int cfg = (g.ring >> 4) & 3;
             const int64_t slots = (int64_t)g.sm_count * ring_ctas_per_sm(cfg);
-            const int lo = g.ring_pps_min > 0 ? g.ring_pps_min : 16, hi = g.ring_pps_max > 0 ? g.ring_pps_max : 32;
-            int64_t v = (int64_t)units * p.nbands * im->frames / (g.ring_waves * slots);
-            pps = (int)(v < lo ? lo : v > hi ? hi : v);
+            const int ns = kind_lifting_steps(im->kind), warm = inverse ? ns : ns / 2 + (ns == 4 ? 1 : 0);
+            const int lo = g.ring_pps_min > 0 ? g.ring_pps_min : (ns == 4 ? 12 : 8), hi = g.ring_pps_max > 0 ? g.ring_pps_max : 40;
+            double best = 1e30;
+            pps = lo;
+            for (int c = lo; c <= hi; c++) {
+                const int64_t n = (int64_t)p.nbands * ((units + c - 1) / c) * im->frames;
+                const int64_t waves = (n + slots - 1) / slots;
+                const double eff = (double)n / (double)(waves * slots);
+                const double cost = (1.0 + 0.5 * warm / c) / eff + 0.002 * c;
+                if (cost < best - 1e-9) {
+                    best = cost;
+                    pps = c;
+                }
+            }
         } else {
             const int64_t want = (int64_t)g.sm_count * stream_warps_per_sm(im->kind, p.narrow, p.pfd);
             int64_t per_col = want / ((int64_t)p.ncg * im->frames);   // strips per column group: never more warps than fit at once

@@ -189,6 +189,7 @@ template <class F> inline void dispatch_kind(int kind, F &&f)
     default: f(W97I{}); break;
     }
 }
+inline int kind_lifting_steps(int kind) { return (kind == K_CDF97_F32 || kind == K_CDF97_F64 || kind == K_CDF97_I32) ? 4 : 2; }
 inline int kind_elem_size(int kind) { return (kind == K_CDF97_F64 || kind == K_CDF53_F64) ? 8 : 4; }
 inline int kind_elem_class(int kind) { return (kind == K_CDF97_F32 || kind == K_CDF53_F32) ? 1 : kind_elem_size(kind) == 8 ? 2 : 0; }   // 0 int32, 1 float, 2 double
 
