@@ -136,7 +136,7 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_TILE_MAX  a level with <= value samples over all frames takes the tile kernels, larger
  *                          levels the streaming kernels (2048*2048)
  *   DWTB200_TUNE_TAIL_MAX  the single-launch tail starts at the first level with <= value samples per
- *                          frame (32*32; 0 disables the tail)
+ *                          frame (64*64; 0 disables the tail)
  *   DWTB200_TUNE_MID_MAX   levels with <= value samples over all frames (and <= TILE_MAX) are fused, together
  *                          with the tail, into ONE persistent cooperative launch (0 = off: a grid-wide
  *                          barrier measured ~5 us on B200, no better than a dependent launch)

@@ -63,7 +63,7 @@ struct Ctx {
     int64_t tile_max = (int64_t)1024 * 1024;
     int64_t mid_max = 0;   // levels this small (and <= tile_max) share ONE persistent cooperative launch; 0 = off
     int mid_ctas_per_sm = 4;
-    int tail_max = 32 * 32;
+    int tail_max = 64 * 64;
     int narrow = 0;
     int dbg = 0;
     int pfd = 1;
@@ -797,7 +797,7 @@ void plan_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart, s
             MidParams &mp = L.mp;
             memset(&mp, 0, sizeof mp);
             mp.frames = im->frames;
-            mp.tail_elems = mid_tail_max_elems(im->kind);
+            mp.tail_elems = mid_tail_buf_elems(im->kind);
             for (; j < pl.jt; j++) in = fwd_level_params(im, j, J, in, dst_plane, mp.lv[mp.nlev++]);
             if (pl.jt < J) {
                 mp.has_tail = 1;
@@ -851,7 +851,7 @@ void plan_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop, st
         MidParams &mp = L.mp;
         memset(&mp, 0, sizeof mp);
         mp.frames = im->frames;
-        mp.tail_elems = mid_tail_max_elems(im->kind);
+        mp.tail_elems = mid_tail_buf_elems(im->kind);
         if (jt < J) {
             mp.has_tail = 1;
             mp.tail = tail_params();

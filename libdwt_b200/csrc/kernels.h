@@ -106,6 +106,7 @@ struct MidParams {
 cudaError_t launch_fwd_mid(int kind, const MidParams &mp, cudaStream_t st);
 cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st);
 int mid_tail_max_elems(int kind);
+int mid_tail_buf_elems(int kind);
 
 // ---- generic pass kernels: exact reference semantics for sparse (outer != inner) layouts ------
 struct PassParams {

@@ -13,8 +13,9 @@
 
 namespace dwtb200 {
 
-constexpr int TAIL_THREADS = 512;
-constexpr int TAIL_BUF_BYTES = 64 * 1024;   // per buffer, two buffers
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_CAP_BYTES = 64 * 1024;                        // largest LL band a tail takes (samples x size)
+constexpr int TAIL_BUF_BYTES = TAIL_CAP_BYTES / 16 * 17;         // per buffer, two buffers: room for the odd row pitch (tail_pitch)
 
 template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_fwd_tail(const TailParams p)
 {
@@ -46,7 +47,7 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(c
     }
 }
 
-int tail_max_elems(int kind) { return TAIL_BUF_BYTES / kind_elem_size(kind); }
+int tail_max_elems(int kind) { return TAIL_CAP_BYTES / kind_elem_size(kind); }
 
 // Kernels are loaded lazily by the CUDA runtime; loading (and cudaFuncSetAttribute) is not allowed while
 // a stream is being captured, so dwtb200_init() calls this once before any graph is built.

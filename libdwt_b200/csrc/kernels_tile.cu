@@ -344,13 +344,22 @@ void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st
     });
 }
 
+int mid_tail_buf_elems(int kind)   // stride between the tail's two shared-memory buffers inside the tile staging area
+{
+    int n = 0;
+    dispatch_kind(kind, [&](auto wv) {
+        using WV = decltype(wv);
+        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T)));
+    });
+    return n;
+}
 int mid_tail_max_elems(int kind)
 {
     // the tail's two LL buffers alias the tile staging area of the persistent kernel
     int n = 0;
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
-        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T)));
+        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T))) / 17 * 16;   // room for the odd row pitch (tail_pitch)
     });
     return n;
 }

@@ -14,6 +14,12 @@ struct LdCg {   // written earlier in the same launch by other SMs: L2 only, nev
     template <class T> __device__ __forceinline__ T operator()(const T *p) const { return __ldcg(p); }
 };
 
+constexpr int TAIL_P = 4;            // output pairs per window evaluation on the fast paths
+constexpr int TAIL_FAST_MIN = 16;    // lines at least this long take them (>= 2 * TAIL_P, so a shifted last group exists)
+// row pitch of a w-wide band in shared memory: odd for the bands the fast paths walk, so that neither a walk down a
+// column nor one thread per row hits a single bank (costs at most 1/16 more room: see tail_max_elems)
+__host__ __device__ inline int tail_pitch(int w) { return w >= TAIL_FAST_MIN ? (w | 1) : w; }
+
 __host__ __device__ inline int cdiv_pow2(int v, int j) { return (int)(((int64_t)v + ((int64_t)1 << j) - 1) >> j); }
 
 // length-1 line: only the unguarded double driver scales it
@@ -38,53 +44,104 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
     const int TAIL_THREADS = blockDim.x;
 
     int w = cdiv_pow2(p.W0, p.j0), h = cdiv_pow2(p.H0, p.j0);
-    for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[t] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
+    for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[(t / w) * tail_pitch(w) + (t % w)] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
     T *in = bufA, *other = bufB;
     __syncthreads();
 
     for (int j = p.j0; j < p.j1; j++) {
         const int nlx = (w + 1) >> 1, nhx = w >> 1, nly = (h + 1) >> 1, nhy = h >> 1;
+        const int pw = tail_pitch(w), pn = tail_pitch(nlx);   // pitches of this level's band and of the next one
         // ---- rows: in -> other, row y = [L (nlx) | H (nhx)] ----
         T *rows = in;
         if (!(WV::GUARD && w <= 1)) {
             rows = other;
-            if (w >= 2) {
+            if (w >= TAIL_FAST_MIN) {
+                // P pairs per window evaluation (lifting.cuh), one integer division per task; the last group of a line
+                // is shifted back so that it ends with the line (recomputes a few pairs, same values)
+                constexpr int P = TAIL_P, NT = 2 * P + 2 * WV::HALO;
+                const int ng = (nlx + P - 1) / P;
+                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
+                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                    int k = g * P;
+                    if (k + P > nlx) k = nlx - P;
+                    const T *line = in + y * pw;
+                    T win[NT], L[P], H[P];
+                    const int t0 = 2 * k - WV::HALO;
+                    if (t0 >= 0 && t0 + NT <= w) {
+#pragma unroll
+                        for (int i = 0; i < NT; i++) win[i] = line[t0 + i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NT; i++) win[i] = line[reflect(t0 + i, w)];
+                    }
+                    window_fwd_p<WV, P>(win, L, H);
+#pragma unroll
+                    for (int i = 0; i < P; i++) {
+                        rows[y * pw + k + i] = L[i];
+                        if (k + i < nhx) rows[y * pw + nlx + k + i] = H[i];
+                    }
+                }
+            } else if (w >= 2) {
                 for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
                     const int y = t / nlx, k = t % nlx;
-                    const T *line = in + y * w;
+                    const T *line = in + y * pw;
                     T win[2 * WV::HALO + 2];
 #pragma unroll
                     for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = line[reflect(2 * k - WV::HALO + i, w)];
                     T L, H;
                     window_fwd<WV>(win, L, H);
-                    rows[y * w + k] = L;
-                    if (k < nhx) rows[y * w + nlx + k] = H;
+                    rows[y * pw + k] = L;
+                    if (k < nhx) rows[y * pw + nlx + k] = H;
                 }
             } else {
-                for (int t = tid; t < h; t += TAIL_THREADS) rows[t] = one_fwd<WV>(in[t]);
+                for (int t = tid; t < h; t += TAIL_THREADS) rows[t * pw] = one_fwd<WV>(in[t * pw]);
             }
             __syncthreads();
         }
         // ---- columns: rows -> LL' (smem) + HL/LH/HH (global, Mallat positions) ----
         T *next = (rows == in) ? other : in;
-        if (!(WV::GUARD && h <= 1) && h >= 2) {
+        if (!(WV::GUARD && h <= 1) && h >= TAIL_FAST_MIN) {
+            constexpr int P = TAIL_P, NT = 2 * P + 2 * WV::HALO;
+            const int ng = (nly + P - 1) / P;
+            for (int t = tid; t < ng * w; t += TAIL_THREADS) {
+                const int g = t / w, x = t - g * w;
+                int k = g * P;
+                if (k + P > nly) k = nly - P;
+                T win[NT], L[P], H[P];
+                const int t0 = 2 * k - WV::HALO;
+                if (t0 >= 0 && t0 + NT <= h) {
+#pragma unroll
+                    for (int i = 0; i < NT; i++) win[i] = rows[(t0 + i) * pw + x];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NT; i++) win[i] = rows[reflect(t0 + i, h) * pw + x];
+                }
+                window_fwd_p<WV, P>(win, L, H);
+#pragma unroll
+                for (int i = 0; i < P; i++) {
+                    if (x < nlx) next[(k + i) * pn + x] = L[i];
+                    else dst[(int64_t)(k + i) * p.dst_pitch + x] = L[i];
+                    if (k + i < nhy) dst[(int64_t)(nly + k + i) * p.dst_pitch + x] = H[i];
+                }
+            }
+        } else if (!(WV::GUARD && h <= 1) && h >= 2) {
             for (int t = tid; t < nly * w; t += TAIL_THREADS) {
                 const int k = t / w, x = t % w;
                 T win[2 * WV::HALO + 2];
 #pragma unroll
-                for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = rows[reflect(2 * k - WV::HALO + i, h) * w + x];
+                for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = rows[reflect(2 * k - WV::HALO + i, h) * pw + x];
                 T L, H;
                 window_fwd<WV>(win, L, H);
-                if (x < nlx) next[k * nlx + x] = L;
+                if (x < nlx) next[k * pn + x] = L;
                 else dst[(int64_t)k * p.dst_pitch + x] = L;
                 if (k < nhy) dst[(int64_t)(nly + k) * p.dst_pitch + x] = H;
             }
         } else {   // h == 1 (or guarded): the single row passes through
             for (int t = tid; t < h * w; t += TAIL_THREADS) {
                 const int y = t / w, x = t % w;
-                T v = rows[t];
+                T v = rows[y * pw + x];
                 if (!(WV::GUARD && h <= 1)) v = one_fwd<WV>(v);
-                if (x < nlx) next[y * nlx + x] = v;
+                if (x < nlx) next[y * pn + x] = v;
                 else dst[(int64_t)y * p.dst_pitch + x] = v;
             }
         }
@@ -94,7 +151,27 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
         w = nlx;
         h = nly;
     }
-    for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[t];
+    for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[(t / w) * tail_pitch(w) + (t % w)];
+}
+
+// P output pairs k .. k+P-1 of one inverse line of n samples: tap(c) returns interleaved coefficient c, emit(q, E, O)
+// receives samples 2q and 2q+1
+template <class WV, int P, class TAP, class EMIT> __device__ __forceinline__ void inv_group(int k, int n, TAP tap, EMIT emit)
+{
+    using T = typename WV::T;
+    constexpr int NT = 2 * P + 2 * WV::HALO;
+    T win[NT], E[P], O[P];
+    const int t0 = 2 * k - WV::HALO;
+    if (t0 >= 0 && t0 + NT <= n) {
+#pragma unroll
+        for (int i = 0; i < NT; i++) win[i] = tap(t0 + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NT; i++) win[i] = tap(reflect(t0 + i, n));
+    }
+    window_inv_p<WV, P>(win, E, O);
+#pragma unroll
+    for (int i = 0; i < P; i++) emit(k + i, E[i], O[i]);
 }
 
 template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, typename WV::T *bufA, typename WV::T *bufB, LD ld)
@@ -107,7 +184,7 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
 
     {   // coarsest LL band
         const int w = cdiv_pow2(p.W0, p.j1), h = cdiv_pow2(p.H0, p.j1);
-        for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[t] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
+        for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[(t / w) * tail_pitch(w) + (t % w)] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
     }
     T *in = bufA, *tmp = bufB;
     __syncthreads();
@@ -115,14 +192,27 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
     for (int j = p.j1; j > p.j0; j--) {
         const int w = cdiv_pow2(p.W0, j - 1), h = cdiv_pow2(p.H0, j - 1);   // size being reconstructed
         const int nlx = (w + 1) >> 1, nly = (h + 1) >> 1;
+        const int pw = tail_pitch(w), pl = tail_pitch(nlx);   // pitches of the band being reconstructed and of the LL band
         // Mallat-arranged input of this level: LL from shared memory, the rest from the plane
         auto M = [&](int y, int x) -> T {
-            return (y < nly && x < nlx) ? in[y * nlx + x] : ld(src + (int64_t)y * p.src_pitch + x);
+            return (y < nly && x < nlx) ? in[y * pl + x] : ld(src + (int64_t)y * p.src_pitch + x);
         };
         const bool do_rows = !(WV::GUARD && w <= 1), do_cols = !(WV::GUARD && h <= 1);
         if constexpr (!WV::INV_COLS_FIRST) {
             // rows: M -> tmp (h x w, rows still in Mallat order)
-            if (do_rows && w >= 2) {
+            if (do_rows && w >= TAIL_FAST_MIN) {
+                const int ng = (nlx + TAIL_P - 1) / TAIL_P;
+                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
+                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                    const int k = (g + 1) * TAIL_P > nlx ? nlx - TAIL_P : g * TAIL_P;
+                    inv_group<WV, TAIL_P>(
+                        k, w, [&](int c) { return M(y, (c & 1) ? nlx + (c >> 1) : (c >> 1)); },
+                        [&](int q, T E, T O) {
+                            tmp[y * pw + 2 * q] = E;
+                            if (2 * q + 1 < w) tmp[y * pw + 2 * q + 1] = O;
+                        });
+                }
+            } else if (do_rows && w >= 2) {
                 for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
                     const int y = t / nlx, k = t % nlx;
                     T win[2 * WV::HALO + 2];
@@ -133,19 +223,37 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
                     }
                     T E, O;
                     window_inv<WV>(win, E, O);
-                    tmp[y * w + 2 * k] = E;
-                    if (2 * k + 1 < w) tmp[y * w + 2 * k + 1] = O;
+                    tmp[y * pw + 2 * k] = E;
+                    if (2 * k + 1 < w) tmp[y * pw + 2 * k + 1] = O;
                 }
             } else {
                 for (int t = tid; t < h * w; t += TAIL_THREADS) {
                     const T v = M(t / w, t % w);
-                    tmp[t] = do_rows ? one_inv<WV>(v) : v;
+                    tmp[(t / w) * pw + (t % w)] = do_rows ? one_inv<WV>(v) : v;
                 }
             }
             __syncthreads();
             // columns: tmp -> out (next LL in shared memory, or the destination plane at the end)
             T *out = in;   // `in` is dead once the row pass has finished
             const bool last = (j - 1 == p.j0);
+            if (do_cols && h >= TAIL_FAST_MIN) {
+                const int ng = (nly + TAIL_P - 1) / TAIL_P;
+                for (int t = tid; t < ng * w; t += TAIL_THREADS) {
+                    const int g = t / w, x = t - g * w;
+                    const int k = (g + 1) * TAIL_P > nly ? nly - TAIL_P : g * TAIL_P;
+                    inv_group<WV, TAIL_P>(
+                        k, h, [&](int c) { return tmp[((c & 1) ? nly + (c >> 1) : (c >> 1)) * pw + x]; },
+                        [&](int q, T E, T O) {
+                            if (last) {
+                                dst[(int64_t)(2 * q) * p.dst_pitch + x] = E;
+                                if (2 * q + 1 < h) dst[(int64_t)(2 * q + 1) * p.dst_pitch + x] = O;
+                            } else {
+                                out[(2 * q) * pw + x] = E;
+                                if (2 * q + 1 < h) out[(2 * q + 1) * pw + x] = O;
+                            }
+                        });
+                }
+            } else
             for (int t = tid; t < nly * w; t += TAIL_THREADS) {
                 const int k = t / w, x = t % w;
                 T E, O = T(0);
@@ -154,7 +262,7 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
 #pragma unroll
                     for (int i = 0; i < 2 * WV::HALO + 2; i++) {
                         const int c = reflect(2 * k - WV::HALO + i, h);
-                        win[i] = tmp[((c & 1) ? nly + (c >> 1) : (c >> 1)) * w + x];
+                        win[i] = tmp[((c & 1) ? nly + (c >> 1) : (c >> 1)) * pw + x];
                     }
                     window_inv<WV>(win, E, O);
                 } else {
@@ -164,13 +272,26 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
                     dst[(int64_t)(2 * k) * p.dst_pitch + x] = E;
                     if (2 * k + 1 < h) dst[(int64_t)(2 * k + 1) * p.dst_pitch + x] = O;
                 } else {
-                    out[(2 * k) * w + x] = E;
-                    if (2 * k + 1 < h) out[(2 * k + 1) * w + x] = O;
+                    out[(2 * k) * pw + x] = E;
+                    if (2 * k + 1 < h) out[(2 * k + 1) * pw + x] = O;
                 }
             }
             __syncthreads();
         } else {
             // columns first (int 5/3): M -> tmp (rows de-interleaved, columns still in Mallat order)
+            if (h >= TAIL_FAST_MIN) {
+                const int ng = (nly + TAIL_P - 1) / TAIL_P;
+                for (int t = tid; t < ng * w; t += TAIL_THREADS) {
+                    const int g = t / w, x = t - g * w;
+                    const int k = (g + 1) * TAIL_P > nly ? nly - TAIL_P : g * TAIL_P;
+                    inv_group<WV, TAIL_P>(
+                        k, h, [&](int c) { return M((c & 1) ? nly + (c >> 1) : (c >> 1), x); },
+                        [&](int q, T E, T O) {
+                            tmp[(2 * q) * pw + x] = E;
+                            if (2 * q + 1 < h) tmp[(2 * q + 1) * pw + x] = O;
+                        });
+                }
+            } else
             for (int t = tid; t < nly * w; t += TAIL_THREADS) {
                 const int k = t / w, x = t % w;
                 if (h >= 2) {
@@ -182,15 +303,33 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
                     }
                     T E, O;
                     window_inv<WV>(win, E, O);
-                    tmp[(2 * k) * w + x] = E;
-                    if (2 * k + 1 < h) tmp[(2 * k + 1) * w + x] = O;
+                    tmp[(2 * k) * pw + x] = E;
+                    if (2 * k + 1 < h) tmp[(2 * k + 1) * pw + x] = O;
                 } else {
-                    tmp[x] = one_inv<WV>(M(0, x));
+                    tmp[x] = one_inv<WV>(M(0, x));   // h == 1: row 0
                 }
             }
             __syncthreads();
             T *out = in;
             const bool last = (j - 1 == p.j0);
+            if (w >= TAIL_FAST_MIN) {
+                const int ng = (nlx + TAIL_P - 1) / TAIL_P;
+                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
+                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                    const int k = (g + 1) * TAIL_P > nlx ? nlx - TAIL_P : g * TAIL_P;
+                    inv_group<WV, TAIL_P>(
+                        k, w, [&](int c) { return tmp[y * pw + ((c & 1) ? nlx + (c >> 1) : (c >> 1))]; },
+                        [&](int q, T E, T O) {
+                            if (last) {
+                                dst[(int64_t)y * p.dst_pitch + 2 * q] = E;
+                                if (2 * q + 1 < w) dst[(int64_t)y * p.dst_pitch + 2 * q + 1] = O;
+                            } else {
+                                out[y * pw + 2 * q] = E;
+                                if (2 * q + 1 < w) out[y * pw + 2 * q + 1] = O;
+                            }
+                        });
+                }
+            } else
             for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
                 const int y = t / nlx, k = t % nlx;
                 T E, O = T(0);
@@ -199,18 +338,18 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
 #pragma unroll
                     for (int i = 0; i < 2 * WV::HALO + 2; i++) {
                         const int c = reflect(2 * k - WV::HALO + i, w);
-                        win[i] = tmp[y * w + ((c & 1) ? nlx + (c >> 1) : (c >> 1))];
+                        win[i] = tmp[y * pw + ((c & 1) ? nlx + (c >> 1) : (c >> 1))];
                     }
                     window_inv<WV>(win, E, O);
                 } else {
-                    E = one_inv<WV>(tmp[y]);
+                    E = one_inv<WV>(tmp[y * pw]);
                 }
                 if (last) {
                     dst[(int64_t)y * p.dst_pitch + 2 * k] = E;
                     if (2 * k + 1 < w) dst[(int64_t)y * p.dst_pitch + 2 * k + 1] = O;
                 } else {
-                    out[y * w + 2 * k] = E;
-                    if (2 * k + 1 < w) out[y * w + 2 * k + 1] = O;
+                    out[y * pw + 2 * k] = E;
+                    if (2 * k + 1 < w) out[y * pw + 2 * k + 1] = O;
                 }
             }
             __syncthreads();
@@ -218,7 +357,7 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
     }
     if (p.j1 == p.j0) {   // nothing to do: pass the band through
         const int w = cdiv_pow2(p.W0, p.j0), h = cdiv_pow2(p.H0, p.j0);
-        for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[t];
+        for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[(t / w) * tail_pitch(w) + (t % w)];
     }
 }
 

@@ -110,7 +110,7 @@ FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-
             # runs of tile levels fused into one launch (DWTB200_TUNE_PYR = tile edge), with and without a tail / ring levels
             "pyr8": (BIG, 1024, 0, 3, 1, 8), "pyr8-tinytail": (BIG, 16, 0, 3, 1, 8), "pyr4-notail": (BIG, 0, 0, 3, 1, 4),
             "pyr16+ring": (128 * 128, 256, 0, 3, 1, 16), "pyr8-default": (1024 * 1024, 1024, 0, 3, 1, 8)}
-DEFAULT_TUNING = (1024 * 1024, 1024, 0, 3, 1, 0)
+DEFAULT_TUNING = (1024 * 1024, 4096, 0, 3, 1, 0)
 
 
 def set_tuning(L, t):
