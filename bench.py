@@ -271,6 +271,31 @@ def run_ours(args):
         for im in singles:
             im.close()
 
+    # ---- one image far larger than L2 and than the launch overheads: BASELINE config 5a on a single GPU ----
+    large = None
+    if rank == 0 and world == 1 and not args.no_large:
+        try:
+            n = 32768   # 4 GiB per float plane, 9.3 GiB per image object
+            for k, name, es in kinds:
+                big = d.DeviceImage(k, n, n, 1)
+                big.fill(0, 0, 0)
+                jb = big.fwd2()
+                big.inv2(jb)
+                L.check(L.c.dwtb200_sync())
+                L.check(L.c.dwtb200_timer_start())
+                big.fwd2()
+                tf = L.c.dwtb200_timer_stop_ms() * 1e-3
+                L.check(L.c.dwtb200_timer_start())
+                big.inv2(jb)
+                ti = L.c.dwtb200_timer_stop_ms() * 1e-3
+                big.close()
+                b = algorithmic_bytes(n, n, jb, 4)
+                large = large or {"workload": f"one {n}x{n} image, J={jb}, forward / inverse, device-resident"}
+                large[name] = {"fwd_ms": tf * 1e3, "inv_ms": ti * 1e3, "fwd_gpixel_s": n * n / tf / 1e9, "inv_gpixel_s": n * n / ti / 1e9,
+                               "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
+        except Exception as e:   # not enough memory on a shared GPU: the headline numbers do not depend on this leg
+            large = {"skipped": str(e)}
+
     # ---- roofline of the dominant kernel: level 0 of the forward 9/7 float transform ----
     # one launch = one j_max=1 transform of the batch: reads M 8192^2 planes once, writes their four subbands once
     im = imgs["97s"]
@@ -359,7 +384,7 @@ def run_ours(args):
                        "l2": "each batch is M x 256 MiB per plane (>> 126 MB L2): inputs larger than L2",
                        "sharding": "independent frames per GPU, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
-            "breakdown": breakdown,
+            "breakdown": breakdown, "large_image": large,
         }
         print(json.dumps(line))
     if world > 1:
@@ -374,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=4, help="independent 8192^2 images per sample type per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the 32768^2 single-image leg")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.impl == "reference" else 100
