@@ -119,6 +119,14 @@ int dwtb200_image_inv2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, i
                        int zero_padding);
 /* current plane of frame 0 (device pointer) and its pitch in bytes; frames are frame_bytes apart */
 void *dwtb200_image_devptr(dwtb200_image *img, size_t *pitch_bytes, size_t *frame_bytes);
+/* dwt_util_subband_{s,d,i} (src/libdwt.h:2286-2340, src/libdwt.c:20731) for a device-resident image: device pointer, pitch and
+ * inner size of subband `band` (0 LL, 1 HL, 2 LH, 3 HH: enum dwt_subbands) of level j inside the current Mallat plane */
+int dwtb200_image_subband(dwtb200_image *img, int frame, int size_i_big_x, int size_i_big_y, int j, int band, void **dev_ptr,
+                          size_t *pitch_bytes, int *size_x, int *size_y);
+/* sum, sum of squares and max |x| of that subband, accumulated in double on the device: the inputs of the per-subband
+ * feature reductions (dwt_util_wps_s, _var_s, _norm_s ..., src/libdwt.c:23086-23786) without a device-to-host copy */
+int dwtb200_image_subband_moments(dwtb200_image *img, int frame, int size_i_big_x, int size_i_big_y, int j, int band, double *sum,
+                                  double *sum_sq, double *max_abs);
 /* bit-exact comparison of the current planes of two images on the device: number of differing samples */
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b);
 /* max |a-b| over the current planes (float/double kinds), cf. dwt_util_compare_s (src/libdwt.c:1593) */
@@ -167,6 +175,10 @@ int dwtb200_volume_download(dwtb200_volume *v, void *host, size_t stride_x, size
 int dwtb200_volume_fill(dwtb200_volume *v);   /* volume_fill_s, src/volume.c:41 */
 int dwtb200_volume_fwd3(dwtb200_volume *v);   /* cdf97_3f_ip_sep_horizontal_s */
 int dwtb200_volume_inv3(dwtb200_volume *v);   /* cdf97_3i_ip_sep_horizontal_s */
+
+/* volume_perftest_fwd97op_s (src/volume-dwt.h:234, src/volume-dwt.c:2810) on the device: N runs of fill / forward (timed) /
+ * inverse / compare; minimum forward seconds per voxel, number of failed round trips */
+int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors);
 
 /* ---- device-event timing: replaces dwt_util_get_clock around transforms (src/libdwt.c:18701) ---- */
 int dwtb200_sync(void);                 /* wait for the library stream */

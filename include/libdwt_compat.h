@@ -82,6 +82,10 @@ void cdf97_3f_op_sep_horizontal_s(struct volume_t *src, struct volume_t *dst);
 void cdf97_3f_ip_sep_horizontal_s(struct volume_t *volume);
 void cdf97_3i_ip_sep_horizontal_s(struct volume_t *volume);
 
+/* src/volume-dwt.h:234 (src/volume-dwt.c:2810): `approach` is enum volume_approach there (an int here: every approach is a
+ * CPU schedule of the same transform); seconds per voxel of the forward transform on a device-resident volume */
+int volume_perftest_fwd97op_s(int size, int opt_stride, int approach, int N, double *secs, long unsigned *faults);
+
 /* device-event timing around the transforms (replaces dwt_util_get_clock in benchmarks, src/libdwt.c:18701):
  * milliseconds the device spent in the last transform call, excluding host<->device copies */
 double dwt_b200_last_transform_ms(void);

@@ -33,6 +33,7 @@ SYMBOLS = [
     ("dwtb200_fwd2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
     ("dwtb200_inv2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
     ("dwtb200_perf2", _i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("dwtb200_perf3", _i, [_i, _i, C.POINTER(_dbl), _ip]),
     ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
     ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
     ("dwtb200_image_upload", _i, [_vp, _i, _vp, _i64, _i64]), ("dwtb200_image_download", _i, [_vp, _i, _vp, _i64, _i64]),
@@ -41,6 +42,8 @@ SYMBOLS = [
     ("dwtb200_image_ipc_export", _i, [_vp, _vp]), ("dwtb200_ipc_open", _vp, [_vp]), ("dwtb200_ipc_close", _i, [_vp]),
     ("dwtb200_image_fwd2", _i, [_vp, _i, _i, _ip, _i, _i]), ("dwtb200_image_inv2", _i, [_vp, _i, _i, _i, _i, _i]),
     ("dwtb200_image_devptr", _vp, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    ("dwtb200_image_subband", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_sz), _ip, _ip]),
+    ("dwtb200_image_subband_moments", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
     ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
     ("dwtb200_image_copy", _i, [_vp, _vp]),
     ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
@@ -165,6 +168,14 @@ def perf2(kind, size_x, size_y, j_max=-1, M=1, N=1, inner=None, decompose_one=0,
     return f.value, i.value
 
 
+def perf3(size, N=1):
+    """volume_perftest_fwd97op_s on the device: (seconds per voxel of the forward transform, failed round trips)."""
+    s, e = C.c_double(), C.c_int()
+    L = lib()
+    L.check(L.c.dwtb200_perf3(size, N, C.byref(s), C.byref(e)))
+    return s.value, e.value
+
+
 # ---- numpy conveniences with the calling shape of oracle/orc.py (images are [y, x] arrays) ----
 def fwd2(img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
     oy, ox = img.shape
@@ -256,6 +267,20 @@ class DeviceImage:
     def inv2(self, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         iy, ix = inner if inner is not None else (self.size_y, self.size_x)
         self.L.check(self.L.c.dwtb200_image_inv2(self.h, ix, iy, j_max, decompose_one, zero_padding))
+
+    def subband(self, j, band, frame=0, inner=None):
+        """dwt_util_subband: (device pointer, pitch in bytes, size_x, size_y) of LL/HL/LH/HH (0..3) of level j."""
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        p, pitch, sx, sy = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_int()
+        self.L.check(self.L.c.dwtb200_image_subband(self.h, frame, ix, iy, j, band, C.byref(p), C.byref(pitch), C.byref(sx), C.byref(sy)))
+        return p.value, pitch.value, sx.value, sy.value
+
+    def subband_moments(self, j, band, frame=0, inner=None):
+        """(sum, sum of squares, max |x|) of a subband, accumulated in double on the device."""
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.L.check(self.L.c.dwtb200_image_subband_moments(self.h, frame, ix, iy, j, band, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def diff(self, other):
         r = self.L.c.dwtb200_image_diff(self.h, other.h)

@@ -1124,6 +1124,52 @@ int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompo
     return transform(im, true, ix, iy, J, zero_padding);
 }
 
+// dwt_util_subband (src/libdwt.c:20731): where subband `band` of level j lives inside the Mallat plane, and its inner size
+int dwtb200_image_subband(dwtb200_image *im, int frame, int ix, int iy, int j, int band, void **dev_ptr, size_t *pitch_bytes,
+                          int *size_x, int *size_y)
+{
+    if (!im || frame < 0 || frame >= im->frames || j < 0 || band < 0 || band > 3 || ix < 0 || iy < 0 || ix > im->ox || iy > im->oy)
+        return fail(DWTB200_EINVAL, "image_subband: bad arguments");
+    int hx = 0, hy = 0, lx = ix, ly = iy, ox = im->ox, oy = im->oy;
+    for (int l = 1; l <= j; l++) {
+        hx = lx >> 1;
+        hy = ly >> 1;
+        lx = (lx + 1) >> 1;
+        ly = (ly + 1) >> 1;
+        ox = (ox + 1) >> 1;
+        oy = (oy + 1) >> 1;
+    }
+    const int col = (band == 1 || band == 3) ? ox : 0, row = (band == 2 || band == 3) ? oy : 0;   // LL, HL, LH, HH (enum dwt_subbands)
+    if (dev_ptr) *dev_ptr = frame_ptr(im, im->cur, frame) + ((size_t)row * im->pitch + col) * im->es;
+    if (pitch_bytes) *pitch_bytes = (size_t)im->pitch * im->es;
+    if (size_x) *size_x = (band == 1 || band == 3) ? hx : lx;
+    if (size_y) *size_y = (band == 2 || band == 3) ? hy : ly;
+    return DWTB200_OK;
+}
+
+// sum, sum of squares and max |x| of a subband, accumulated in double on the device
+int dwtb200_image_subband_moments(dwtb200_image *im, int frame, int ix, int iy, int j, int band, double *sum, double *sum_sq,
+                                  double *max_abs)
+{
+    NEED_DEV();
+    void *p = nullptr;
+    int sx = 0, sy = 0;
+    int r = dwtb200_image_subband(im, frame, ix, iy, j, band, &p, nullptr, &sx, &sy);
+    if (r) return r;
+    double *d = nullptr, h[3] = {0, 0, 0};
+    CK(cudaMalloc((void **)&d, sizeof h));
+    CK(cudaMemsetAsync(d, 0, sizeof h, g.st));
+    launch_moments(kind_elem_class(im->kind), p, im->pitch, sx, sy, d, g.st);
+    cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, g.st);
+    const cudaError_t e = cudaStreamSynchronize(g.st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(DWTB200_ECUDA, "subband_moments: %s", cudaGetErrorString(e));
+    if (sum) *sum = h[0];
+    if (sum_sq) *sum_sq = h[1];
+    if (max_abs) *max_abs = h[2];
+    return DWTB200_OK;
+}
+
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
 {
     if (g.dev < 0 || !a || !b || a->kind != b->kind || a->ox != b->ox || a->oy != b->oy || a->frames != b->frames) {
@@ -1664,6 +1710,48 @@ int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny
     if (!r) r = dwtb200_volume_inv3(v);
     if (!r) r = dwtb200_volume_download(v, vol, sx, sy, sz);
     dwtb200_volume_destroy(v);
+    return r;
+}
+
+// volume_perftest_fwd97op_s (src/volume-dwt.c:2810) on the device: N runs of "fill, forward (timed with CUDA events),
+// inverse, compare with the pattern"; *secs_per_voxel = minimum forward time / voxels; returns the number of runs whose
+// round trip missed the reference's tolerance (dwt_util_compare2_s, 1e-3) in *errors
+int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors)
+{
+    NEED_DEV();
+    if (size < 5 || N < 1 || !secs_per_voxel) return fail(DWTB200_EINVAL, "perf3: bad arguments");
+    dwtb200_volume *v = dwtb200_volume_create(size, size, size), *ref = dwtb200_volume_create(size, size, size);
+    int r = (v && ref) ? DWTB200_OK : DWTB200_ENOMEM;
+    double best = 1e30;
+    int bad = 0;
+    unsigned long long *d = nullptr;
+    if (!r && cudaMalloc(&d, 16) != cudaSuccess) r = fail(DWTB200_ENOMEM, "perf3: cudaMalloc");
+    if (!r) r = dwtb200_volume_fill(ref);
+    for (int n = -1; n < N && !r; n++) {   // run -1 warms up
+        r = dwtb200_volume_fill(v);
+        if (!r) r = dwtb200_timer_start();
+        if (!r) r = dwtb200_volume_fwd3(v);
+        if (!r) {
+            const double ms = dwtb200_timer_stop_ms();
+            if (n >= 0 && ms >= 0 && ms * 1e-3 < best) best = ms * 1e-3;
+        }
+        if (!r) r = dwtb200_volume_inv3(v);
+        if (!r) {
+            unsigned long long h[2] = {0, 0};
+            cudaMemsetAsync(d, 0, 16, g.st);
+            launch_compare(4, v->buf[v->cur], ref->buf[ref->cur], v->pitch, v->slice, v->nx, v->ny, v->nz, 1, d, g.st);
+            cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, g.st);
+            if (cudaStreamSynchronize(g.st) != cudaSuccess) r = fail(DWTB200_ECUDA, "perf3: compare failed");
+            double e;
+            memcpy(&e, &h[1], 8);
+            if (n >= 0 && !(e < 1e-3)) bad++;
+        }
+    }
+    if (d) cudaFree(d);
+    dwtb200_volume_destroy(v);
+    dwtb200_volume_destroy(ref);
+    *secs_per_voxel = best / ((double)size * size * size);
+    if (errors) *errors = bad;
     return r;
 }
 

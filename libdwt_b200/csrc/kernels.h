@@ -144,6 +144,7 @@ void launch_copy2d(int elem_size, void *dst, int64_t dpitch, const void *src, in
 
 void launch_compare(int elem_size, const void *a, const void *b, int64_t pitch, int64_t frame, int nx, int ny, int frames,
                     int mode, unsigned long long *out, cudaStream_t st);
+void launch_moments(int elem_class, const void *a, int64_t pitch_elems, int nx, int ny, double *out3, cudaStream_t st);
 void launch_volume_fill(float *buf, int64_t pitch, int64_t slice, int nx, int ny, int nz, cudaStream_t st);
 
 // ---- 3-D (one level, interleaved, in place): lifting along one axis --------------------------

@@ -174,6 +174,37 @@ void launch_compare(int es, const void *a, const void *b, int64_t pitch, int64_t
     else k_compare<int32_t><<<g, blk, 0, st>>>((const int32_t *)a, (const int32_t *)b, pitch, frame, nx, ny, out);
 }
 
+// ---- moments of a rectangle (a subband of the Mallat plane): sum, sum of squares, max |x|, in double ----
+// what dwt_util_band_wps_s / _var_s / _norm_s style feature reductions need (src/libdwt.c:23086-23786) without bringing the
+// coefficients back to the host
+template <class T> __global__ void __launch_bounds__(256) k_moments(const T *a, int64_t pitch, int nx, int ny, double *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.0;
+    if (x < nx && y < ny) v = (double)a[(int64_t)y * pitch + x];
+    double s = v, q = v * v, m = fabs(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        q += __shfl_down_sync(0xffffffffu, q, o);
+        m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, s);
+        atomicAdd(out + 1, q);
+        atomicMax((unsigned long long *)(out + 2), (unsigned long long)__double_as_longlong(m));   // m >= 0: bit order = value order
+    }
+}
+void launch_moments(int elem_class, const void *a, int64_t pitch, int nx, int ny, double *out, cudaStream_t st)
+{
+    if (nx <= 0 || ny <= 0) return;
+    const dim3 blk(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
+    if (elem_class == 2) k_moments<double><<<g, blk, 0, st>>>((const double *)a, pitch, nx, ny, out);
+    else if (elem_class == 1) k_moments<float><<<g, blk, 0, st>>>((const float *)a, pitch, nx, ny, out);
+    else k_moments<int32_t><<<g, blk, 0, st>>>((const int32_t *)a, pitch, nx, ny, out);
+}
+
 // ---- volume_fill_s (src/volume.c:41): slice z = 2-D type-0 float pattern with rand = fold(z & 11) ----
 __global__ void __launch_bounds__(256) k_volume_fill(float *buf, int64_t pitch, int64_t slice, int nx, int ny)
 {

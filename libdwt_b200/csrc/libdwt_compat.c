@@ -112,4 +112,16 @@ void cdf97_3i_ip_sep_horizontal_s(struct volume_t *v)
     if (rc) die("cdf97_3i_ip_sep_horizontal_s", rc);
 }
 
+/* src/volume-dwt.c:2810: every `approach` is a CPU schedule of the same transform; the device has one */
+int volume_perftest_fwd97op_s(int size, int opt_stride, int approach, int N, double *secs, long unsigned *faults)
+{
+    (void)opt_stride;
+    (void)approach;
+    int errors = 0;
+    const int rc = dwtb200_perf3(size, N, secs, &errors);
+    if (rc) die("volume_perftest_fwd97op_s", rc);
+    if (faults) *faults = 0;
+    return errors;
+}
+
 double dwt_b200_last_transform_ms(void) { return dwtb200_last_transform_ms(); }

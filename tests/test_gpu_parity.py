@@ -471,3 +471,32 @@ def test_perf_harness_on_device(dev):
         assert 0 < f < 5e-3 and 0 < i < 5e-3, (f, i)
         f13, i13 = dev.perf2(kind, 2048, 2048, j_max=-1, M=2, N=3)
         assert 0 < f13 < 5e-3 and 0 < i13 < 5e-3
+    s, bad = dev.perf3(256, N=2)   # volume_perftest_fwd97op_s: seconds per voxel, failed round trips
+    assert bad == 0 and 0 < s * 256 ** 3 < 5e-3, (s, bad)
+
+
+def test_device_resident_subband_views_and_moments(dev, oracle):
+    """dwt_util_subband on the device: subband rectangles of the Mallat plane and their moments,
+    against numpy on the oracle's coefficients (double accumulation: tolerance 1e-12 relative)."""
+    for (w, t, ox, oy) in (("97", "s", 517, 301), ("53", "i", 300, 200), ("97", "d", 130, 257)):
+        a = oracle.fill(np.zeros((oy, ox), DT[t]), t)
+        J = oracle.fwd2(a, w, t)
+        img = dev.DeviceImage(dev.kind_of(w, t), ox, oy, 2)
+        img.fill(0, 0, 0)
+        assert img.fwd2() == J
+        base, pitch, _ = img.devptr()
+        for j in (1, 2, J):
+            lx, ly, hx, hy, cx, cy = ox, oy, 0, 0, ox, oy
+            for _ in range(j):
+                hx, hy, lx, ly, cx, cy = lx // 2, ly // 2, (lx + 1) // 2, (ly + 1) // 2, (cx + 1) // 2, (cy + 1) // 2
+            for band, (r0, c0, sy, sx) in enumerate(((0, 0, ly, lx), (0, cx, ly, hx), (cy, 0, hy, lx), (cy, cx, hy, hx))):
+                p, pb, gx, gy = img.subband(j, band, frame=1)
+                frame_bytes = img.devptr()[2]
+                assert (gx, gy) == (sx, sy) and pb == pitch
+                assert p == base + frame_bytes + r0 * pitch + c0 * a.itemsize
+                s, q, m = img.subband_moments(j, band, frame=1)
+                ref = a[r0:r0 + sy, c0:c0 + sx].astype(np.float64)
+                want = (ref.sum(), (ref * ref).sum(), np.abs(ref).max() if ref.size else 0.0)
+                for got, exp in zip((s, q, m), want):
+                    assert abs(got - exp) <= 1e-12 * max(1.0, abs(exp)) * max(1, ref.size) ** 0.5, (w, t, j, band, got, exp)
+        img.close()
