@@ -254,15 +254,15 @@ def run_ours(args):
         L.check(L.c.dwtb200_sync())
         tf = ti = 0.0
         reps = 5
-        for _ in range(reps):
-            L.check(L.c.dwtb200_timer_start())
+        for _ in range(reps):   # one image at a time (independent images would overlap on their own streams)
             for im in singles:
+                L.check(L.c.dwtb200_timer_start())
                 im.fwd2()
-            tf += L.c.dwtb200_timer_stop_ms()
-            L.check(L.c.dwtb200_timer_start())
+                tf += L.c.dwtb200_timer_stop_ms()
             for im in singles:
+                L.check(L.c.dwtb200_timer_start())
                 im.inv2(J)
-            ti += L.c.dwtb200_timer_stop_ms()
+                ti += L.c.dwtb200_timer_stop_ms()
         for direction, t in (("fwd", tf), ("inv", ti)):
             t = t / (reps * 3) * 1e-3
             b = algorithmic_bytes(W, H, J, 4)

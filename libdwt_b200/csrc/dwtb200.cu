@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <tuple>
 #include <algorithm>
 #include <vector>
@@ -45,7 +46,10 @@ int g_use_pdl = 0;
 namespace {
 struct Ctx {
     int dev = -1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;    // the stream the current call issues on: the image's own stream inside an image call (ImageScope)
+    cudaStream_t st0 = nullptr;   // the library stream: volumes, timing events, everything that is not one image's work
+    std::set<dwtb200_image *> live;   // images alive: dwtb200_sync / the timer join their streams
+    cudaEvent_t stage_ev = nullptr;   // last use of the shared staging buffer
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     char err[512] = "";
     int force_generic = 0;
@@ -101,6 +105,7 @@ inline bool kind_ok(int kind) { return kind >= 0 && kind < DWTB200_KIND_COUNT; }
 int ensure_stage(size_t bytes)
 {
     if (bytes <= g.stage_bytes) return 0;
+    if (g.stage_ev) cudaEventSynchronize(g.stage_ev);   // the old buffer may still be in use on another image's stream
     if (g.stage) cudaFree(g.stage);
     g.stage = nullptr;
     g.stage_bytes = 0;
@@ -111,6 +116,8 @@ int ensure_stage(size_t bytes)
 }  // namespace
 
 struct dwtb200_image {
+    cudaStream_t st = nullptr;   // independent images overlap: the small levels of one run in the shadow of another's big ones
+    cudaEvent_t ev = nullptr;
     int kind = 0, ox = 0, oy = 0, frames = 0;
     size_t es = 4;
     int64_t pitch = 0, frame = 0;   // elements
@@ -136,6 +143,35 @@ struct dwtb200_volume {
     float *buf[2] = {nullptr, nullptr};
     int cur = 0;
 };
+
+namespace {
+// every call that works on one image issues on that image's stream
+struct ImageScope {
+    cudaStream_t prev;
+    explicit ImageScope(const dwtb200_image *im) : prev(g.st)
+    {
+        if (im && im->st) g.st = im->st;
+    }
+    ~ImageScope() { g.st = prev; }
+};
+// make stream `waiter` wait for everything queued so far on the stream of `im`
+void wait_for_image(cudaStream_t waiter, dwtb200_image *im)
+{
+    if (!im || !im->st || im->st == waiter) return;
+    cudaEventRecord(im->ev, im->st);
+    cudaStreamWaitEvent(waiter, im->ev, 0);
+}
+// the shared staging buffer is used by one copy at a time, whatever stream it runs on
+void stage_acquire()
+{
+    if (g.stage_ev) cudaStreamWaitEvent(g.st, g.stage_ev, 0);
+}
+void stage_release()
+{
+    if (!g.stage_ev) cudaEventCreateWithFlags(&g.stage_ev, cudaEventDisableTiming);
+    cudaEventRecord(g.stage_ev, g.st);
+}
+}  // namespace
 
 extern "C" {
 
@@ -176,7 +212,8 @@ int dwtb200_init(int device)
     CK(preload_generic());
     CK(preload_util());
     CK(preload_tile(g.sm_count, g.mid_ctas_per_sm));
-    CK(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.st0, cudaStreamNonBlocking));
+    g.st = g.st0;
     CK(cudaEventCreate(&g.e0));
     CK(cudaEventCreate(&g.e1));
     const char *ng = getenv("DWTB200_NO_GRAPH");
@@ -189,16 +226,18 @@ void dwtb200_release_host_cache(void);
 void dwtb200_finish(void)
 {
     if (g.dev < 0) return;
-    cudaStreamSynchronize(g.st);
+    cudaDeviceSynchronize();
     dwtb200_release_host_cache();
+    if (g.stage_ev) cudaEventDestroy(g.stage_ev);
+    g.stage_ev = nullptr;
     if (g.flush) cudaFree(g.flush);
     if (g.stage) cudaFree(g.stage);
     g.flush = g.stage = nullptr;
     g.flush_bytes = g.stage_bytes = 0;
     cudaEventDestroy(g.e0);
     cudaEventDestroy(g.e1);
-    cudaStreamDestroy(g.st);
-    g.st = nullptr;
+    cudaStreamDestroy(g.st0);
+    g.st = g.st0 = nullptr;
     g.dev = -1;
 }
 
@@ -279,6 +318,14 @@ dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
         return nullptr;
     }
     dwtb200_image *im = new dwtb200_image;
+    if (cudaStreamCreateWithFlags(&im->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&im->ev, cudaEventDisableTiming) != cudaSuccess) {
+        fail(DWTB200_ECUDA, "image_create: stream: %s", cudaGetErrorString(cudaGetLastError()));
+        delete im;
+        return nullptr;
+    }
+    g.live.insert(im);
+    ImageScope scope(im);
     im->kind = kind;
     im->ox = ox;
     im->oy = oy;
@@ -311,7 +358,10 @@ dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
 void dwtb200_image_destroy(dwtb200_image *im)
 {
     if (!im) return;
-    if (g.st) cudaStreamSynchronize(g.st);
+    if (im->st) cudaStreamSynchronize(im->st);
+    g.live.erase(im);
+    if (im->ev) cudaEventDestroy(im->ev);
+    if (im->st) cudaStreamDestroy(im->st);
     for (auto &kv : im->graphs) {
         cudaGraphExecDestroy(kv.second.exec);
         if (kv.second.sync) cudaFree(kv.second.sync);
@@ -345,8 +395,10 @@ static int upload_region(dwtb200_image *im, int frame, const void *host, int64_t
         const size_t span = host_span(w, h, sx, sy, im->es);
         int r = ensure_stage(span);
         if (r) return r;
+        stage_acquire();
         CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
         launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, w, h, 1, g.st);
+        stage_release();
         CK(cudaGetLastError());
     }
     return DWTB200_OK;
@@ -354,6 +406,7 @@ static int upload_region(dwtb200_image *im, int frame, const void *host, int64_t
 
 int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t sx, int64_t sy)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_upload: bad arguments");
     return upload_region(im, frame, host, sx, sy, im->ox, im->oy);
@@ -361,6 +414,7 @@ int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t
 
 int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx, int64_t sy)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_download: bad arguments");
     char *d = frame_ptr(im, im->cur, frame);
@@ -372,10 +426,12 @@ int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx,
         const size_t span = host_span(im->ox, im->oy, sx, sy, im->es);
         int r = ensure_stage(span);
         if (r) return r;
+        stage_acquire();
         CK(cudaMemcpyAsync(g.stage, host, span, cudaMemcpyDefault, g.st));
         launch_repack((int)im->es, d, im->pitch, g.stage, sx, sy, im->ox, im->oy, 0, g.st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(host, g.stage, span, cudaMemcpyDefault, g.st));
+        stage_release();
     }
     CK(cudaStreamSynchronize(g.st));
     return DWTB200_OK;
@@ -383,6 +439,7 @@ int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx,
 
 int dwtb200_image_fill_ex(dwtb200_image *im, int rnd, int type, int rand_mod, int y_offset, int wide)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_fill: null image");
     launch_fill(im->kind, im->plane[im->cur], im->pitch, im->frame, im->ox, im->oy, rnd, type, rand_mod, im->frames, y_offset,
@@ -396,6 +453,7 @@ int dwtb200_image_fill(dwtb200_image *im, int rnd, int type, int rand_mod) { ret
 // the halo rows of a row-strip partition travel through this (peer-mapped pointers included)
 int dwtb200_image_copy_rows(dwtb200_image *im, int frame, int row0, int rows, void *buf, int64_t buf_pitch_bytes, int to_image)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im || !buf || frame < 0 || frame >= im->frames || row0 < 0 || rows < 0 || row0 + rows > im->oy)
         return fail(DWTB200_EINVAL, "image_copy_rows: bad arguments");
@@ -447,8 +505,11 @@ int dwtb200_image_copy(dwtb200_image *dst, dwtb200_image *src)
     NEED_DEV();
     if (!dst || !src || dst->kind != src->kind || dst->ox != src->ox || dst->oy != src->oy || dst->frames != src->frames)
         return fail(DWTB200_EINVAL, "image_copy: shape mismatch");
+    ImageScope scope(dst);
+    wait_for_image(g.st, src);   // the copy reads src after everything queued on it ...
     CK(cudaMemcpyAsync(dst->plane[dst->cur], src->plane[src->cur], (size_t)src->frame * src->frames * src->es,
                        cudaMemcpyDeviceToDevice, g.st));
+    wait_for_image(src->st, dst);   // ... and later work on src must not overwrite it before the copy has read it
     return DWTB200_OK;
 }
 
@@ -1110,6 +1171,7 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
 
 int dwtb200_image_fwd2(dwtb200_image *im, int ix, int iy, int *j_max_ptr, int decompose_one, int zero_padding)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im || !j_max_ptr) return fail(DWTB200_EINVAL, "image_fwd2: null argument");
     *j_max_ptr = dwtb200_clamp_j(*j_max_ptr, im->ox, im->oy, decompose_one);   // src/libdwt.c:12807-12810
@@ -1118,6 +1180,7 @@ int dwtb200_image_fwd2(dwtb200_image *im, int ix, int iy, int *j_max_ptr, int de
 
 int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompose_one, int zero_padding)
 {
+    ImageScope scope(im);
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_inv2: null argument");
     const int J = dwtb200_clamp_j(j_max, im->ox, im->oy, decompose_one);   // src/libdwt.c:17063-17066
@@ -1151,6 +1214,7 @@ int dwtb200_image_subband(dwtb200_image *im, int frame, int ix, int iy, int j, i
 int dwtb200_image_subband_moments(dwtb200_image *im, int frame, int ix, int iy, int j, int band, double *sum, double *sum_sq,
                                   double *max_abs)
 {
+    ImageScope scope(im);
     NEED_DEV();
     void *p = nullptr;
     int sx = 0, sy = 0;
@@ -1176,6 +1240,8 @@ int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
         fail(DWTB200_EINVAL, "image_diff: shape mismatch");
         return -1;
     }
+    ImageScope scope(a);
+    wait_for_image(g.st, b);
     unsigned long long *d = nullptr, h = 0;
     if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
     cudaMemsetAsync(d, 0, 16, g.st);
@@ -1197,6 +1263,8 @@ double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
         fail(DWTB200_EINVAL, "image_maxabs: shape mismatch");
         return -1.0;
     }
+    ImageScope scope(a);
+    wait_for_image(g.st, b);
     unsigned long long *d = nullptr, h[2] = {0, 0};
     if (cudaMalloc(&d, 16) != cudaSuccess) return -1.0;
     cudaMemsetAsync(d, 0, 16, g.st);
@@ -1403,6 +1471,7 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
 {
     dwtb200_image *im = host_image(kind, ox, oy);
     if (!im) return DWTB200_ENOMEM;
+    ImageScope scope(im);
     if (!g_t0) {
         CK(cudaEventCreate(&g_t0));
         CK(cudaEventCreate(&g_t1));
@@ -1432,6 +1501,18 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
 double dwtb200_last_transform_ms(void) { return (double)g_last_ms; }
 void dwtb200_release_host_cache(void)
 {
+    // the pipelined host path's streams and events, and the transform timing events, go with the cache
+    for (cudaEvent_t e : g_pipe.ev) cudaEventDestroy(e);
+    g_pipe.ev.clear();
+    for (cudaStream_t *s : {&g_pipe.up, &g_pipe.dn, &g_pipe.dn2}) {
+        if (*s) cudaStreamDestroy(*s);
+        *s = nullptr;
+    }
+    if (g_t0) {
+        cudaEventDestroy(g_t0);
+        cudaEventDestroy(g_t1);
+        g_t0 = g_t1 = nullptr;
+    }
     for (int k = 0; k < DWTB200_KIND_COUNT; k++) {
         if (g_host_img[k]) dwtb200_image_destroy(g_host_img[k]);
         g_host_img[k] = nullptr;
@@ -1472,6 +1553,7 @@ static int host_transform2(bool inverse, int kind, const void *src, void *dst, i
     }
     dwtb200_image *im = host_image(kind, ox, oy);
     if (!im) return DWTB200_ENOMEM;
+    ImageScope scope(im);
     int r = DWTB200_OK;
     const bool covers = rw == ox && rh == oy;
     if (inverse || covers) {   // the region replaces dst's content before anything is computed: overlay, then in place
@@ -1761,24 +1843,30 @@ int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors)
 int dwtb200_sync(void)
 {
     NEED_DEV();
-    CK(cudaStreamSynchronize(g.st));
+    for (dwtb200_image *im : g.live) CK(cudaStreamSynchronize(im->st));
+    CK(cudaStreamSynchronize(g.st0));
     return DWTB200_OK;
 }
+// the timer brackets ALL device work of the library: the start event waits for everything queued so far (library stream
+// and every image's stream) and everything queued afterwards waits for it; the stop event waits for everything again
 int dwtb200_timer_start(void)
 {
     NEED_DEV();
-    CK(cudaEventRecord(g.e0, g.st));
+    for (dwtb200_image *im : g.live) wait_for_image(g.st0, im);
+    CK(cudaEventRecord(g.e0, g.st0));
+    for (dwtb200_image *im : g.live) CK(cudaStreamWaitEvent(im->st, g.e0, 0));
     return DWTB200_OK;
 }
 double dwtb200_timer_stop_ms(void)
 {
     if (g.dev < 0) return -1.0;
-    if (cudaEventRecord(g.e1, g.st) != cudaSuccess || cudaEventSynchronize(g.e1) != cudaSuccess) return -1.0;
+    for (dwtb200_image *im : g.live) wait_for_image(g.st0, im);
+    if (cudaEventRecord(g.e1, g.st0) != cudaSuccess || cudaEventSynchronize(g.e1) != cudaSuccess) return -1.0;
     float ms = 0;
     if (cudaEventElapsedTime(&ms, g.e0, g.e1) != cudaSuccess) return -1.0;
     return (double)ms;
 }
-void *dwtb200_stream(void) { return (void *)g.st; }
+void *dwtb200_stream(void) { return (void *)g.st0; }
 
 int dwtb200_flush_l2(size_t bytes)
 {
