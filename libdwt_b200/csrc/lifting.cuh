@@ -223,10 +223,13 @@ extern int g_use_pdl;   // dwtb200.cu (DWTB200_TUNE_PDL)
 __device__ __forceinline__ int reflect(int i, int n)
 {
     if ((unsigned)i < (unsigned)n) return i;
-    const int p = 2 * (n - 1);
-    i %= p;
-    if (i < 0) i += p;
-    return i < n ? i : p - i;
+    // one fold is enough unless the line is shorter than the window overhang (the last few levels of a pyramid);
+    // folding in a loop is much cheaper than the integer modulo it replaces
+    do {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    } while ((unsigned)i >= (unsigned)n);
+    return i;
 }
 
 // ---- window evaluation: one (even, odd) output pair from a 2*HALO+2 sample window -------------

@@ -17,13 +17,11 @@ for J in range(1, Jmax + 1):
     for _ in range(2):
         for im in ims: im.fwd2(J); im.inv2(J)
     tf = ti = 0.0; reps = 6
-    for _ in range(reps):
-        L.c.dwtb200_timer_start()
-        for im in ims: im.fwd2(J)
-        tf += L.c.dwtb200_timer_stop_ms()
-        L.c.dwtb200_timer_start()
-        for im in ims: im.inv2(J)
-        ti += L.c.dwtb200_timer_stop_ms()
+    for _ in range(reps):   # one image at a time: independent images would overlap on their own streams
+        for im in ims:
+            L.c.dwtb200_timer_start(); im.fwd2(J); tf += L.c.dwtb200_timer_stop_ms()
+        for im in ims:
+            L.c.dwtb200_timer_start(); im.inv2(J); ti += L.c.dwtb200_timer_stop_ms()
     tf *= 1e3 / (reps * len(ims) * frames); ti *= 1e3 / (reps * len(ims) * frames)
     print(f"{name} x{frames} n={n} J={J:2d} launches={ims[0].last_launches:2d} fwd {tf:7.1f} (+{tf-pf:6.1f})  inv {ti:7.1f} (+{ti-pi:6.1f})", flush=True)
     pf, pi = tf, ti
