@@ -500,3 +500,56 @@ def test_device_resident_subband_views_and_moments(dev, oracle):
                 for got, exp in zip((s, q, m), want):
                     assert abs(got - exp) <= 1e-12 * max(1.0, abs(exp)) * max(1, ref.size) ** 0.5, (w, t, j, band, got, exp)
         img.close()
+
+
+# ---- seeded random inputs (the reference's patterns are smooth: these are not) -------------------------------------
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_random_inputs(dev, oracle, kind):
+    w, t = kind
+    rng = np.random.default_rng(20261018)
+    fails = []
+    for (ox, oy) in ((64, 64), (517, 301), (1300, 1260), (2100, 1300), (4099, 2051)):
+        if t == "i":
+            a = rng.integers(-(1 << 20), 1 << 20, size=(oy, ox), dtype=np.int32)
+        else:
+            a = (rng.standard_normal((oy, ox)) * 10.0 ** rng.integers(-3, 4, size=(oy, ox))).astype(DT[t])
+        b = a.copy()
+        for (j, d1) in ((-1, 0), (3, 0)):
+            a2, b2 = a.copy(), b.copy()
+            Ja = oracle.fwd2(a2, w, t, j_max=j, decompose_one=d1)
+            Jb = dev.fwd2(b2, w, t, j_max=j, decompose_one=d1)
+            if Ja != Jb or not (bits(a2, t) == bits(b2, t)).all():
+                fails.append(f"random {w}{t} {ox}x{oy} j={j}: FORWARD " + describe_mismatch(b2, a2, t))
+                b2[...] = a2
+            oracle.inv2(a2, w, t, j_max=Ja, decompose_one=d1)
+            dev.inv2(b2, w, t, j_max=Ja, decompose_one=d1)
+            if not (bits(a2, t) == bits(b2, t)).all():
+                fails.append(f"random {w}{t} {ox}x{oy} j={j}: INVERSE " + describe_mismatch(b2, a2, t))
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS[:3], ids=KIDS[:3])
+def test_batch_of_ring_sized_frames(dev, oracle, kind):
+    """frames > 1 with frames large enough for the bulk-copy ring kernels on several levels."""
+    w, t = kind
+    ox, oy, frames = 2100, 1300, 3
+    img = dev.DeviceImage(dev.kind_of(w, t), ox, oy, frames)
+    img.fill(0, 0, 6)
+    J = img.fwd2()
+    fails = []
+    for k in range(frames):
+        want = oracle.fill(np.zeros((oy, ox), DT[t]), t, rand=k % 6)
+        Jo = oracle.fwd2(want, w, t)
+        got = img.download(frame=k)
+        if J != Jo or not (bits(got, t) == bits(want, t)).all():
+            fails.append(f"frame {k} forward: " + describe_mismatch(got, want, t))
+    img.inv2(J)
+    for k in range(frames):
+        want = oracle.fill(np.zeros((oy, ox), DT[t]), t, rand=k % 6)
+        oracle.fwd2(want, w, t)
+        oracle.inv2(want, w, t, j_max=J)
+        got = img.download(frame=k)
+        if not (bits(got, t) == bits(want, t)).all():
+            fails.append(f"frame {k} inverse: " + describe_mismatch(got, want, t))
+    img.close()
+    report(fails)

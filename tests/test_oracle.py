@@ -143,3 +143,21 @@ def test_out_of_place_semantics_match_reference(oracle, ref):
         ref.inv2_s2(da, ea, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
         oracle.inv2_s2(db, eb, j_max=Ja, decompose_one=d1, zero_padding=zp, inner=(iy, ix))
         assert (bits(ea, "s") == bits(eb, "s")).all(), (ox, oy, ix, iy, j, d1, zp, describe_mismatch(eb, ea, "s"))
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k[0] + k[1])
+def test_oracle_vs_reference_random_inputs(oracle, ref, kind):
+    """The reference's test patterns are smooth; seeded random data (wide dynamic range for floats) must agree bit for bit too."""
+    w, t = kind
+    rng = np.random.default_rng(20261018)
+    for (ox, oy) in ((64, 64), (517, 301), (1025, 130)):
+        if t == "i":
+            a = rng.integers(-(1 << 20), 1 << 20, size=(oy, ox), dtype=np.int32)
+        else:
+            a = (rng.standard_normal((oy, ox)) * 10.0 ** rng.integers(-3, 4, size=(oy, ox))).astype(DT[t])
+        b = a.copy()
+        Ja, Jb = ref.fwd2(a, w, t), oracle.fwd2(b, w, t)
+        assert Ja == Jb and (bits(a, t) == bits(b, t)).all(), describe_mismatch(b, a, t)
+        ref.inv2(a, w, t, j_max=Ja)
+        oracle.inv2(b, w, t, j_max=Jb)
+        assert (bits(a, t) == bits(b, t)).all(), describe_mismatch(b, a, t)
