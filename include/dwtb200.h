@@ -152,7 +152,9 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_NARROW    1: streaming kernels hold 16 instead of 32 bytes per lane: twice the warps per SM (0)
  *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips and download for large dense images (1)
  *   DWTB200_TUNE_RING      bit 0 / bit 1: forward / inverse streaming levels stage their input through a shared-memory
- *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer
+ *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer;
+ *                          bits 4-6 force a CTA shape (0 = chosen per level: 7 consumer warps x 2 CTAs per SM, or 5 x 3 for
+ *                          large batches of 2048-wide frames; 1 = 15 x 1, 2 = 8 x 2, 3 = 5 x 3, 5 = 7 x 2)
  *   DWTB200_TUNE_PYR       T > 0: runs of tile levels are fused: one launch carries T x T tiles of the last level's LL band
  *                          through up to three levels in shared memory (0 = one tile launch per level)
  *   DWTB200_TUNE_CHAIN     1: the kernels of a pyramid are launched with programmatic stream serialization and wait for

@@ -610,7 +610,17 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     const int outw = stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
     {   // ring kernels: bands of at most ring_cta_warps() column groups, as equal as possible
-        const int cw = ring_cta_warps((g.ring >> 4) & 3), nb = (p.ncg + cw - 1) / cw;
+        // CTA shape: 7 consumer warps x 2 CTAs per SM, unless the row splits into bands of exactly 5 column groups (2048-
+        // or 1080p-wide frames) AND the batch is large enough for >= 2 waves of the smaller CTAs: then 5 x 3 keeps 15 instead
+        // of 10 consumer warps per SM busy (2048^2 x 64: 419 -> 445 Gpixel/s; a 4-frame level of 2048^2 is better off with 7 x 2)
+        p.cfg = (g.ring >> 4) & 7;   // DWTB200_TUNE_RING bits 4-6 force a shape
+        if (p.cfg == 0) {
+            const int nb7 = (p.ncg + 6) / 7, bw7 = (p.ncg + nb7 - 1) / nb7;   // bands of the default shape: 5 of 7 warps busy?
+            const int nb5 = (p.ncg + 4) / 5, bw5 = (p.ncg + nb5 - 1) / nb5;
+            const int64_t est = (int64_t)nb5 * ((inverse ? (H >> 1) + 1 : p.nLy) / 28 + 1) * im->frames;
+            if (bw7 <= 5 && bw5 == 5 && est >= 2 * (int64_t)g.sm_count * ring_ctas_per_sm(3)) p.cfg = 3;
+        }
+        const int cw = ring_cta_warps(p.cfg), nb = (p.ncg + cw - 1) / cw;
         p.bw = (p.ncg + nb - 1) / nb;
         p.nbands = (p.ncg + p.bw - 1) / p.bw;
     }
@@ -627,7 +637,7 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
             // CTAs handed out dynamically beat one long CTA per slot in spite of the warm-up rows every strip re-reads;
             // and the last wave matters: 3.85 or 2.9 waves of CTAs run 5-10 % faster than 4.3 or 2.2.  Pick the strip
             // length with the lowest modelled time: (re-read overhead) / (occupancy of the last wave) + imbalance.
-            const int cfg = (g.ring >> 4) & 3;
+            const int cfg = p.cfg;
             const int64_t slots = (int64_t)g.sm_count * ring_ctas_per_sm(cfg);
             const int ns = kind_lifting_steps(im->kind), warm = inverse ? ns : ns / 2 + (ns == 4 ? 1 : 0);
             const int lo = g.ring_pps_min > 0 ? g.ring_pps_min : (ns == 4 ? 12 : 8), hi = g.ring_pps_max > 0 ? g.ring_pps_max : 40;
@@ -703,12 +713,12 @@ void inv_level_params(const dwtb200_image *im, int j, int J, char *src_plane, ch
 
 void stream_fwd(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if ((g.ring & 1) && !p.narrow) launch_fwd_ring(kind, p, frames, (g.ring >> 4) & 3, st);
+    if ((g.ring & 1) && !p.narrow) launch_fwd_ring(kind, p, frames, p.cfg, st);
     else launch_fwd_level(kind, p, frames, st);
 }
 void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
 {
-    if ((g.ring & 2) && !p.narrow && p.sub_aligned) launch_inv_ring(kind, p, frames, (g.ring >> 4) & 3, st);
+    if ((g.ring & 2) && !p.narrow && p.sub_aligned) launch_inv_ring(kind, p, frames, p.cfg, st);
     else launch_inv_level(kind, p, frames, st);
 }
 
@@ -801,7 +811,7 @@ int issue(dwtb200_image *im, std::vector<Launch> &ls)
     for (Launch &l : ls) {
         cudaError_t e = cudaSuccess;
         switch (l.type) {
-        case Launch::RING_F: launch_fwd_ring(im->kind, l.lp, im->frames, (g.ring >> 4) & 3, g.st); break;
+        case Launch::RING_F: launch_fwd_ring(im->kind, l.lp, im->frames, l.lp.cfg, g.st); break;
         case Launch::REG_F: launch_fwd_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_F: launch_fwd_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_F: launch_fwd_tail(im->kind, l.tp, im->frames, g.st); break;
@@ -810,7 +820,7 @@ int issue(dwtb200_image *im, std::vector<Launch> &ls)
             launch_fwd_pyr(im->kind, l.pin.p, l.pin.pitch, l.pin.frame, l.pout.p, l.pout.pitch, l.pout.frame, im->plane[im->cur ^ 1],
                            im->pitch, im->frame, im->ox, im->oy, l.pj0, l.pF, im->frames, g.pyr, g.st);
             break;
-        case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, (g.ring >> 4) & 3, g.st); break;
+        case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, l.lp.cfg, g.st); break;
         case Launch::REG_I: launch_inv_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_I: launch_inv_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_I: launch_inv_tail(im->kind, l.tp, im->frames, g.st); break;

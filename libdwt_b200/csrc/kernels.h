@@ -51,6 +51,7 @@ struct LevelParams {
     int sub_aligned;      // 1: hl/hh column offsets allow 16-byte vector access
     int h_room;           // elements from the hl / hh column origin to the end of the pitched plane row
     int bw, nbands;       // ring kernels: column groups per CTA (band), bands per row of CTAs
+    int cfg;              // ring kernels: CTA shape (kernels_ring.cu, dispatch_cfg)
     Chain chain;
     int pfd;              // row pairs prefetched ahead in registers: 1 (4 CTAs/SM) or 2 (3 CTAs/SM)
     int dbg;              // measurement only: 1 = no stores, 2 = no lifting arithmetic (forward streaming kernel)

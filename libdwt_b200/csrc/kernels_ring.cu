@@ -450,11 +450,14 @@ template <class K> static cudaError_t prep(K kern, int smem)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
-// cfg: 0 = 7 consumer warps x 2 CTAs per SM, 1 = 15 x 1, 2 = 8 x 2 (96 registers)
+// cfg: 0 = 7 consumer warps x 2 CTAs per SM, 1 = 15 x 1, 2 = 8 x 2 (96 registers), 3 = 5 x 3 (rows of 9-10 column groups:
+// two bands of 5 keep 15 instead of 10 consumer warps per SM busy)
+constexpr int RING_NCFG = 4;
 template <class F> static void dispatch_cfg(int cfg, F &&f)
 {
     if (cfg == 1) f(RingCfg<15, 1>{});
     else if (cfg == 2) f(RingCfg<8, 2>{});
+    else if (cfg == 3) f(RingCfg<5, 3>{});
     else f(RingCfg<7, 2>{});
 }
 cudaError_t preload_ring()
@@ -464,7 +467,7 @@ cudaError_t preload_ring()
         dispatch_kind(kind, [&](auto wv) {
             using WV = decltype(wv);
             constexpr int V = 32 / (int)sizeof(typename WV::T);
-            for (int cfg = 0; cfg < 3; cfg++)
+            for (int cfg = 0; cfg < RING_NCFG; cfg++)
                 dispatch_cfg(cfg, [&](auto c) {
                     using CFG = decltype(c);
                     if (e == cudaSuccess) e = prep(k_fwd_ring<WV, V, CFG>, CFG::SMEM);
@@ -473,7 +476,7 @@ cudaError_t preload_ring()
         });
     return e;
 }
-int ring_warps_per_sm(int cfg) { return cfg == 1 ? 15 : cfg == 2 ? 16 : 14; }
+int ring_warps_per_sm(int cfg) { return ring_cta_warps(cfg) * ring_ctas_per_sm(cfg); }
 
 void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st)
 {
@@ -500,7 +503,7 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         });
     });
 }
-int ring_cta_warps(int cfg) { return cfg == 1 ? 15 : cfg == 2 ? 8 : 7; }
-int ring_ctas_per_sm(int cfg) { return cfg == 1 ? 1 : 2; }
+int ring_cta_warps(int cfg) { return cfg == 1 ? 15 : cfg == 2 ? 8 : cfg == 3 ? 5 : 7; }
+int ring_ctas_per_sm(int cfg) { return cfg == 1 ? 1 : cfg == 3 ? 3 : 2; }
 
 }  // namespace dwtb200

@@ -103,7 +103,7 @@ FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-
             "tile+tinytail": (BIG, 16, 0), "persistent+tail": (BIG, 1024, BIG), "persistent-notail": (BIG, 0, BIG),
             "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256),
             "regstream-only": (0, 0, 0, 0), "regstream+bigtail": (0, 16384, 0, 0), "ringfwd-reginv": (0, 1024, 0, 1),
-            "ring15x1": (0, 1024, 0, 3 | 16),
+            "ring15x1": (0, 1024, 0, 3 | (1 << 4)), "ring5x3": (0, 1024, 0, 3 | (3 << 4)),
             # the same mixes without the dataflow chain between the kernels of a pyramid (DWTB200_TUNE_CHAIN = 0)
             "nochain-default": (1024 * 1024, 1024, 0, 3, 0), "nochain-stream": (0, 0, 0, 3, 0), "nochain-tile": (BIG, 16, 0, 3, 0),
             "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1),
