@@ -20,7 +20,7 @@
 
 namespace dwtb200 {
 
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_THREADS = 1024;
 
 template <class WV> struct TileCfg {
     static constexpr int TW = 64, TH = 32;
