@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH  = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
 CSRC = libdwt_b200/csrc
-OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_ring.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_tile.o $(CSRC)/kernels_pyr.o $(CSRC)/kernels_vol.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/dwtb200.o
+OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_ring.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_tile.o $(CSRC)/kernels_pyr.o $(CSRC)/kernels_inplace.o $(CSRC)/kernels_vol.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/dwtb200.o
 
 all: libdwt_b200/libdwtb200.so libdwt_b200/libdwt_compat.so oracle examples
 

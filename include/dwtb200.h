@@ -77,6 +77,17 @@ int dwtb200_fwd2_host2(int kind, const void *src, void *dst, int64_t stride_x, i
                        int size_o_big_y, int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
 int dwtb200_inv2_host2(int kind, const void *src, void *dst, int64_t stride_x, int64_t stride_y, int size_o_big_x,
                        int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+/* interleaved in-place family: dwt_cdf97_2f_inplace_s and its bit-identical twins _inplace_sep_s, _inplace_sdl_s,
+ * _inplace_sep_sdl_s, dwt_cdf97_2i_inplace_s (src/libdwt.h:586-662, 889-900; src/libdwt.c:12926, 13485, 13641, 14847,
+ * 17474) with kind DWTB200_CDF97_F32, and dwt_cdf53_2f_inplace_s / dwt_cdf53_2i_inplace_s (src/libdwt.h:599, 944;
+ * src/libdwt.c:16553, 17886) with kind DWTB200_CDF53_F32.  Coefficients stay interleaved (level j at stride 2^j,
+ * even = L, odd = H); level sizes come from the inner size, the outer size only bounds the level count; no zero
+ * padding (the reference ignores the flag).  The 9/7 results reproduce the reference's prolog / core / epilog sweep
+ * order, which is NOT the rounding of the Mallat family in the top rows and right columns of every level. */
+int dwtb200_fwd2_inplace_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
+                              int size_i_big_x, int size_i_big_y, int *j_max_ptr, int decompose_one);
+int dwtb200_inv2_inplace_host(int kind, void *ptr, int64_t stride_x, int64_t stride_y, int size_o_big_x, int size_o_big_y,
+                              int size_i_big_x, int size_i_big_y, int j_max, int decompose_one);
 /* the reference's performance protocol on the device, dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i
  * (src/libdwt.h:2498-2513, src/libdwt.c:21391, 21262): M device-resident test images, N loops of M forward then M
  * inverse transforms, minimum over the loops of the mean seconds per transform (CUDA events, no host copies) */
@@ -117,6 +128,9 @@ int dwtb200_image_fwd2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, i
                        int zero_padding);
 int dwtb200_image_inv2(dwtb200_image *img, int size_i_big_x, int size_i_big_y, int j_max, int decompose_one,
                        int zero_padding);
+/* the interleaved in-place family (see dwtb200_fwd2_inplace_host) on a device-resident image, inner == outer size */
+int dwtb200_image_fwd2_inplace(dwtb200_image *img, int *j_max_ptr, int decompose_one);
+int dwtb200_image_inv2_inplace(dwtb200_image *img, int j_max, int decompose_one);
 /* current plane of frame 0 (device pointer) and its pitch in bytes; frames are frame_bytes apart */
 void *dwtb200_image_devptr(dwtb200_image *img, size_t *pitch_bytes, size_t *frame_bytes);
 /* dwt_util_subband_{s,d,i} (src/libdwt.h:2286-2340, src/libdwt.c:20731) for a device-resident image: device pointer, pitch and

@@ -53,6 +53,24 @@ void dwt_cdf97_2f_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int
 void dwt_cdf97_2i_i(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                     int size_i_big_y, int j_max, int decompose_one, int zero_padding);
 
+/* interleaved in-place family: src/libdwt.h:586-597, 612-662, 889-900 (src/libdwt.c:12926, 13485, 13641, 14847, 17474) and the
+ * 5/3 float pair src/libdwt.h:599-610, 944-955 (src/libdwt.c:16553, 17886).  The four forward 9/7 variants are the same
+ * arithmetic in a different loop order and give bit-identical results in the reference. */
+void dwt_cdf97_2f_inplace_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                            int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2f_inplace_sep_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                                int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2f_inplace_sdl_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                                int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2f_inplace_sep_sdl_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                                    int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf97_2i_inplace_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                            int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+void dwt_cdf53_2f_inplace_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                            int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);
+void dwt_cdf53_2i_inplace_s(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                            int size_i_big_y, int j_max, int decompose_one, int zero_padding);
+
 /* out-of-place 9/7 float: src/libdwt.h:667-679, 962-974 (src/libdwt.c:12619, 17985) */
 void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                      int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding);

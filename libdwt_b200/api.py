@@ -32,6 +32,9 @@ SYMBOLS = [
     ("dwtb200_inv2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
     ("dwtb200_fwd2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
     ("dwtb200_inv2_host2", _i, [_i, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_fwd2_inplace_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i]),
+    ("dwtb200_inv2_inplace_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i]),
+    ("dwtb200_image_fwd2_inplace", _i, [_vp, _ip, _i]), ("dwtb200_image_inv2_inplace", _i, [_vp, _i, _i]),
     ("dwtb200_perf2", _i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("dwtb200_perf3", _i, [_i, _i, C.POINTER(_dbl), _ip]),
     ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
@@ -159,6 +162,50 @@ def dwt_cdf97_2i_s2(src, dst, stride_x, stride_y, size_o_big_x, size_o_big_y, si
                                    size_i_big_y, j_max, decompose_one, zero_padding))
 
 
+# ---- interleaved in-place family (src/libdwt.h:586-662, 889-900, 599-610, 944-955); zero_padding is ignored ----
+def _fwd_ip(kind, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max_ptr, decompose_one,
+            zero_padding=0):
+    j = C.c_int(j_max_ptr[0] if isinstance(j_max_ptr, list) else j_max_ptr.value)
+    L = lib()
+    L.check(L.c.dwtb200_fwd2_inplace_host(kind, _addr(ptr), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                          size_i_big_y, C.byref(j), decompose_one))
+    if isinstance(j_max_ptr, list):
+        j_max_ptr[0] = j.value
+    else:
+        j_max_ptr.value = j.value
+
+
+def _inv_ip(kind, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max, decompose_one,
+            zero_padding=0):
+    L = lib()
+    L.check(L.c.dwtb200_inv2_inplace_host(kind, _addr(ptr), stride_x, stride_y, size_o_big_x, size_o_big_y, size_i_big_x,
+                                          size_i_big_y, j_max, decompose_one))
+
+
+def dwt_cdf97_2f_inplace_s(*a): _fwd_ip(CDF97_F32, *a)
+def dwt_cdf97_2f_inplace_sep_s(*a): _fwd_ip(CDF97_F32, *a)
+def dwt_cdf97_2f_inplace_sdl_s(*a): _fwd_ip(CDF97_F32, *a)
+def dwt_cdf97_2f_inplace_sep_sdl_s(*a): _fwd_ip(CDF97_F32, *a)
+def dwt_cdf97_2i_inplace_s(*a): _inv_ip(CDF97_F32, *a)
+def dwt_cdf53_2f_inplace_s(*a): _fwd_ip(CDF53_F32, *a)
+def dwt_cdf53_2i_inplace_s(*a): _inv_ip(CDF53_F32, *a)
+
+
+def fwd2_inplace(img, wavelet, j_max=-1, decompose_one=0, inner=None):
+    """numpy convenience: img is a [y, x] float32 array, transformed in place (interleaved layout); returns achieved J."""
+    oy, ox = img.shape
+    iy, ix = inner if inner is not None else (oy, ox)
+    j = [j_max]
+    _fwd_ip(kind_of(wavelet, "s"), img, img.strides[0], img.strides[1], ox, oy, ix, iy, j, decompose_one)
+    return j[0]
+
+
+def inv2_inplace(img, wavelet, j_max=-1, decompose_one=0, inner=None):
+    oy, ox = img.shape
+    iy, ix = inner if inner is not None else (oy, ox)
+    _inv_ip(kind_of(wavelet, "s"), img, img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one)
+
+
 def perf2(kind, size_x, size_y, j_max=-1, M=1, N=1, inner=None, decompose_one=0, zero_padding=0):
     """dwt_util_perf_cdf97_2_s / dwt_util_perf_cdf53_2_i on the device: (fwd_secs, inv_secs) per transform."""
     iy, ix = inner if inner is not None else (size_y, size_x)
@@ -267,6 +314,15 @@ class DeviceImage:
     def inv2(self, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         iy, ix = inner if inner is not None else (self.size_y, self.size_x)
         self.L.check(self.L.c.dwtb200_image_inv2(self.h, ix, iy, j_max, decompose_one, zero_padding))
+
+    def fwd2_inplace(self, j_max=-1, decompose_one=0):
+        """dwt_cdf97_2f_inplace_s / dwt_cdf53_2f_inplace_s on the device-resident frames (interleaved layout)."""
+        j = C.c_int(j_max)
+        self.L.check(self.L.c.dwtb200_image_fwd2_inplace(self.h, C.byref(j), decompose_one))
+        return j.value
+
+    def inv2_inplace(self, j_max=-1, decompose_one=0):
+        self.L.check(self.L.c.dwtb200_image_inv2_inplace(self.h, j_max, decompose_one))
 
     def subband(self, j, band, frame=0, inner=None):
         """dwt_util_subband: (device pointer, pitch in bytes, size_x, size_y) of LL/HL/LH/HH (0..3) of level j."""

@@ -207,6 +207,7 @@ int dwtb200_init(int device)
     g.sm_count = prop.multiProcessorCount;
     CK(preload_stream());
     CK(preload_ring());
+    CK(preload_inplace());
     CK(preload_pyr());
     CK(preload_tail());
     CK(preload_generic());
@@ -1197,6 +1198,154 @@ int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompo
     return transform(im, true, ix, iy, J, zero_padding);
 }
 
+// =====================================================================================================
+// interleaved in-place family (src/libdwt.c:12926, 13485, 13641, 14847, 17474, 16553, 17886; kernels_inplace.cu)
+// =====================================================================================================
+namespace {
+constexpr int IP_STD_MIN = 32;            // a level with a side below this is evaluated by k_ip_phase alone
+constexpr int IP_TOP = 8, IP_RIGHT = 6;   // frame whose sweep order differs from rows-then-columns (7 / 8 rows, 5 columns)
+
+// one level of the 9/7 family: the ordinary level kernel, then the exact schedule over the top and right frame
+int ip_level(dwtb200_image *im, bool inverse, const LevelParams &lp)
+{
+    const int nx = lp.W, ny = lp.H, top = std::min(IP_TOP, ny);
+    if (std::min(nx, ny) < IP_STD_MIN) {
+        launch_ip_phase(inverse, lp, im->frames, 0, 0, nx, ny, 0, 0, 0, 0, g.st);
+        g.launches++;
+        return 0;
+    }
+    std::vector<Launch> one(1);
+    one[0].lp = lp;
+    plan_level(im, one[0], inverse, (int64_t)nx * ny * im->frames <= g.tile_max ? PLAN_TILE : PLAN_STREAM);
+    memset(&one[0].lp.chain, 0, sizeof(Chain));
+    const int r = issue(im, one);
+    if (r) return r;
+    launch_ip_phase(inverse, lp, im->frames, 0, 0, nx, top, std::max(nx - IP_RIGHT, 0), top, nx, ny, g.st);
+    g.launches++;
+    return 0;
+}
+
+int ip_run97(dwtb200_image *im, bool inverse, int J)
+{
+    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];   // A: the image (interleaved), B: Mallat scratch
+    // levels jt .. J-1 run inside one CTA per frame once their input fits its shared memory (k_ip_tail)
+    int jt = J;
+    for (int j = 0; j < J; j++)
+        if ((int64_t)cdiv_pow2(im->ox, j) * cdiv_pow2(im->oy, j) <= ip_tail_cap()) {
+            jt = j;
+            break;
+        }
+    if (jt == 0) {   // the whole image: in place, nothing to translate
+        launch_ip_tail(inverse, A, im->pitch, im->frame, im->ox, im->oy, J, im->frames, g.st);
+        g.launches++;
+        return 0;
+    }
+    const bool tail = jt < J;
+    const Band tb = ll_band(im, jt - 1);   // LL_{jt-1}: dense input of level jt, and the tail block
+    const int tw = cdiv_pow2(im->ox, jt), th = cdiv_pow2(im->oy, jt);
+    LevelParams lp;
+    if (!inverse) {
+        Band in = {A, im->pitch, im->frame};
+        for (int j = 0; j < jt; j++) {
+            const Band out = fwd_level_params(im, j, J, in, B, lp);
+            const int r = ip_level(im, false, lp);
+            if (r) return r;
+            in = out;
+        }
+        if (tail) launch_ip_tail(false, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
+        launch_ip_pack(false, B, A, im->pitch, im->frame, im->ox, im->oy, J, tail ? tb.p : nullptr, tb.pitch, tb.frame, jt, im->frames, g.st);
+    } else {
+        launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, tail ? tb.p : nullptr, tb.pitch, tb.frame, jt, im->frames, g.st);
+        if (tail) launch_ip_tail(true, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
+        for (int j = jt - 1; j >= 0; j--) {
+            inv_level_params(im, j, J, B, A, lp);
+            const int r = ip_level(im, true, lp);
+            if (r) return r;
+        }
+    }
+    g.launches += tail ? 2 : 1;
+    return 0;
+}
+
+// J levels of the family on the whole image (J as given: the host entry points clamp it against the caller's OUTER size)
+int inplace_transform(dwtb200_image *im, bool inverse, int J)
+{
+    if (im->kind != DWTB200_CDF97_F32 && im->kind != DWTB200_CDF53_F32)
+        return fail(DWTB200_EINVAL, "in-place family: CDF 9/7 float and CDF 5/3 float only (kind %d)", im->kind);
+    im->last_launches = 0;
+    if (J <= 0) return DWTB200_OK;
+    if (im->kind == DWTB200_CDF53_F32) {   // bit-identical to the Mallat transform, only laid out differently (:16583); a lone sample is scaled
+        int r = 0;
+        if (inverse) {
+            launch_ip_pack(true, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, im->frames, g.st);
+            im->cur ^= 1;
+            r = transform(im, true, im->ox, im->oy, J, 0);
+        } else {
+            r = transform(im, false, im->ox, im->oy, J, 0);
+            if (r) return r;
+            launch_ip_pack(false, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, im->frames, g.st);
+            im->cur ^= 1;
+        }
+        im->last_launches++;
+        CK(cudaGetLastError());
+        return r;
+    }
+    const int jcap = dwtb200_ceil_log2(std::max(im->ox, im->oy));   // beyond it every line has one sample: 9/7 touches nothing (:12975)
+    if (J > jcap) J = jcap;
+    if (J <= 0) return DWTB200_OK;
+    const dwtb200_image::Key key(inverse, im->ox, im->oy, J, 0x100, im->cur, g.force_generic, g.strip_rows, g.epoch);
+    auto it = g.use_graph ? im->graphs.find(key) : im->graphs.end();
+    if (it == im->graphs.end()) {
+        g.launches = 0;
+        if (!g.use_graph) {
+            const int r = ip_run97(im, inverse, J);
+            if (r) return r;
+            CK(cudaGetLastError());
+            im->last_launches = g.launches;
+            return DWTB200_OK;
+        }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
+        const int rr = ip_run97(im, inverse, J);
+        const cudaError_t le = cudaGetLastError(), ce = cudaStreamEndCapture(g.st, &graph);
+        if (rr || le != cudaSuccess || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rr ? rr : fail(DWTB200_ECUDA, "in-place launch/capture failed: %s / %s", cudaGetErrorString(le), cudaGetErrorString(ce));
+        }
+        dwtb200_image::Entry e;
+        e.launches = g.launches;
+        e.path = 0;
+        e.flips = 0;
+        e.sync = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail(DWTB200_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+        it = im->graphs.emplace(key, e).first;
+    }
+    CK(cudaGraphLaunch(it->second.exec, g.st));
+    im->last_launches = it->second.launches;
+    im->last_path = 0;
+    return DWTB200_OK;
+}
+}  // namespace
+
+int dwtb200_image_fwd2_inplace(dwtb200_image *im, int *j_max_ptr, int decompose_one)
+{
+    ImageScope scope(im);
+    NEED_DEV();
+    if (!im || !j_max_ptr) return fail(DWTB200_EINVAL, "image_fwd2_inplace: null argument");
+    *j_max_ptr = dwtb200_clamp_j(*j_max_ptr, im->ox, im->oy, decompose_one);   // src/libdwt.c:12948-12951
+    return inplace_transform(im, false, *j_max_ptr);
+}
+
+int dwtb200_image_inv2_inplace(dwtb200_image *im, int j_max, int decompose_one)
+{
+    ImageScope scope(im);
+    NEED_DEV();
+    if (!im) return fail(DWTB200_EINVAL, "image_inv2_inplace: null argument");
+    return inplace_transform(im, true, dwtb200_clamp_j(j_max, im->ox, im->oy, decompose_one));   // src/libdwt.c:17493-17496
+}
+
 // dwt_util_subband (src/libdwt.c:20731): where subband `band` of level j lives inside the Mallat plane, and its inner size
 int dwtb200_image_subband(dwtb200_image *im, int frame, int ix, int iy, int j, int band, void **dev_ptr, size_t *pitch_bytes,
                           int *size_x, int *size_y)
@@ -1543,6 +1692,46 @@ int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int o
     NEED_DEV();
     if (!ptr) return fail(DWTB200_EINVAL, "inv2_host: null argument");
     return host_transform(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
+}
+
+// The in-place family on host memory.  Its level geometry comes from the INNER size alone and the outer size only
+// bounds the level count (src/libdwt.c:12948, 12964), so the device works on an image of the inner size.
+static int host_inplace(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_io, int decompose_one)
+{
+    if (ix < 1 || iy < 1 || ix > ox || iy > oy) return fail(DWTB200_EINVAL, "inner size %d x %d outside outer %d x %d", ix, iy, ox, oy);
+    const int J = dwtb200_clamp_j(*j_io, ox, oy, decompose_one);
+    if (!inverse) *j_io = J;
+    dwtb200_image *im = host_image(kind, ix, iy);
+    if (!im) return DWTB200_ENOMEM;
+    ImageScope scope(im);
+    if (!g_t0) {
+        CK(cudaEventCreate(&g_t0));
+        CK(cudaEventCreate(&g_t1));
+    }
+    int r = dwtb200_image_upload(im, 0, ptr, sx, sy);
+    if (r) return r;
+    CK(cudaEventRecord(g_t0, g.st));
+    r = inplace_transform(im, inverse, J);
+    if (r) return r;
+    CK(cudaEventRecord(g_t1, g.st));
+    r = dwtb200_image_download(im, 0, ptr, sx, sy);   // synchronises the stream
+    if (r) return r;
+    CK(cudaEventElapsedTime(&g_last_ms, g_t0, g_t1));
+    return DWTB200_OK;
+}
+
+int dwtb200_fwd2_inplace_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr, int decompose_one)
+{
+    NEED_DEV();
+    if (!ptr || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_inplace_host: null argument");
+    return host_inplace(false, kind, ptr, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one);
+}
+
+int dwtb200_inv2_inplace_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max, int decompose_one)
+{
+    NEED_DEV();
+    if (!ptr) return fail(DWTB200_EINVAL, "inv2_inplace_host: null argument");
+    return host_inplace(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one);
 }
 
 // Out of place (dwt_cdf97_2f_s2 / 2i_s2, src/libdwt.c:12619, 17985): the first pass of the first level reads `src`

@@ -109,6 +109,22 @@ cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st);
 int mid_tail_max_elems(int kind);
 int mid_tail_buf_elems(int kind);
 
+// ---- interleaved in-place family (kernels_inplace.cu) --------------------------------------------------------
+cudaError_t preload_inplace();
+// exact evaluation of the reference's prolog / core / epilog sweep order for the rectangle [rx0, rx1) x [ry0, ry1) of a
+// level, and optionally a second rectangle [sx0, sx1) x [sy0, sy1), in one launch (CDF 9/7 float): forward reads p.src and
+// writes the four subbands, inverse reads them and writes p.dst
+void launch_ip_phase(bool inverse, const LevelParams &p, int frames, int rx0, int ry0, int rx1, int ry1, int sx0, int sy0, int sx1, int sy1,
+                     cudaStream_t st);
+// all levels of a small LL band (w0 x h0 <= ip_tail_cap() samples) in one launch, in place: dense LL on one side, the
+// interleaved pyramid of `nlev` levels on the other
+int ip_tail_cap();
+void launch_ip_tail(bool inverse, void *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev, int frames, cudaStream_t st);
+// Mallat pyramid of J levels -> interleaved layout (unpack: the other way), 4-byte samples, same pitch on both sides; samples of
+// the levels >= jt come from / go to the dense tail block instead (tail == nullptr: no tail block)
+void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int64_t frame, int ox, int oy, int J, void *tail, int64_t tpitch,
+                    int64_t tframe, int jt, int frames, cudaStream_t st);
+
 // ---- generic pass kernels: exact reference semantics for sparse (outer != inner) layouts ------
 struct PassParams {
     const void *src;

@@ -1,0 +1,324 @@
+// kernels_inplace.cu -- the interleaved in-place family (sm_100a): dwt_cdf97_2f_inplace_s and its _sep / _sdl twins,
+// dwt_cdf97_2i_inplace_s, dwt_cdf53_2f_inplace_s / dwt_cdf53_2i_inplace_s
+// (/root/reference/src/libdwt.c:12926, 13485, 13641, 14847, 17474, 16553, 17886).
+//
+// Coefficients of this family stay where the lifting leaves them: level j works on the samples at stride 2^j, even = L,
+// odd = H.  On the device the pyramid is still computed level by level on DENSE LL bands with the streaming / tile
+// kernels of the Mallat family; two cheap kernels translate between the layouts (k_ip_pack / k_ip_unpack).
+//
+// CDF 5/3 of this family is the Mallat result bit for bit (rows, then columns; :16583).  CDF 9/7 is not: the reference
+// runs a level as up to eight sweeps -- "exceptions" (lines of 2..4 samples forward, 2..3 inverse: the whole 1-D
+// transform at once; :10803, :11574), prolog, core, epilog -- each over all rows and then over all columns
+// (:12975-13451, :17512-17598).  The top rows therefore get their column prolog BEFORE the row core, and the right
+// columns their row epilog AFTER the column core; float rounding makes that order visible in the first 7 (forward) /
+// 8 (inverse) rows and the last 5 columns of every level.  k_ip_phase evaluates exactly that schedule for any
+// rectangle of a level: a tile plus a 4-sample halo is staged in shared memory and the eight sweeps are applied
+// operation by operation, each lifting operation (step, position) belonging to the part the reference does it in
+// (:9591 prolog, :9929 epilog, the rest core).  The host runs the ordinary level kernel and then k_ip_phase over the
+// top and right frame (and over whole levels once they are small), so the result is bit-identical everywhere.
+#include "kernels.h"
+#include "lifting.cuh"
+#include "tail_body.cuh"
+
+namespace dwtb200 {
+
+constexpr int IP_THREADS = 256;
+constexpr int IP_HALO = 4;   // lifting depth: four steps per axis, whatever the order of the sweeps
+
+enum { IP_X = 0, IP_P = 1, IP_C = 2, IP_E = 3 };
+
+// forward steps: 0 alpha (odd), 1 beta (even), 2 gamma (odd), 3 delta (even), 4 scale; lines start at offset 1 (:10831)
+__device__ __forceinline__ int ip_part_fwd(int N, int step, int i)
+{
+    if (N < 5) return IP_X;
+    if ((step == 0 && (i == 1 || i == 3)) || (step == 1 && (i == 0 || i == 2)) || (step == 2 && i == 1) || (step == 3 && i == 0) ||
+        (step == 4 && i == 0))
+        return IP_P;
+    if (N & 1) {
+        if ((step == 1 && i == N - 1) || (step == 2 && i == N - 2) || (step == 3 && (i == N - 1 || i == N - 3)) || (step == 4 && i >= N - 4))
+            return IP_E;
+    } else {
+        if ((step == 0 && i == N - 1) || (step == 1 && i == N - 2) || (step == 2 && (i == N - 1 || i == N - 3)) ||
+            (step == 3 && (i == N - 2 || i == N - 4)) || (step == 4 && i >= N - 5))
+            return IP_E;
+    }
+    return IP_C;
+}
+// inverse steps: 0 scale, 1 even += -u2, 2 odd += p2, 3 even += -u1, 4 odd += p1; offset 0 (:11604)
+__device__ __forceinline__ int ip_part_inv(int N, int step, int i)
+{
+    if (N < 4) return IP_X;
+    if ((step == 0 && i <= 3) || (step == 1 && (i == 0 || i == 2)) || (step == 2 && i == 1) || (step == 3 && i == 0)) return IP_P;
+    if (N & 1) {
+        if ((step == 0 && i == N - 1) || (step == 1 && i == N - 1) || (step == 2 && i == N - 2) || (step == 3 && (i == N - 1 || i == N - 3)) ||
+            (step == 4 && (i == N - 2 || i == N - 4)))
+            return IP_E;
+    } else {
+        if ((step == 2 && i == N - 1) || (step == 3 && i == N - 2) || (step == 4 && (i == N - 1 || i == N - 3))) return IP_E;
+    }
+    return IP_C;
+}
+
+template <bool INV> __device__ __forceinline__ float ip_coef(int lift)
+{
+    if (INV) return lift == 0 ? -W97F::U2 : lift == 1 ? W97F::P2 : lift == 2 ? -W97F::U1 : W97F::P1;
+    return lift == 0 ? -W97F::P1 : lift == 1 ? W97F::U1 : lift == 2 ? -W97F::P2 : W97F::U2;
+}
+
+// positions [a0, a1) of a line of N samples that can hold operations of `part`
+template <bool INV> __device__ __forceinline__ void ip_part_range(int N, int part, int &a0, int &a1)
+{
+    const int small = INV ? 4 : 5;
+    a0 = 0;
+    a1 = N;
+    if (N < small) {
+        if (part != IP_X) a1 = 0;
+        return;
+    }
+    if (part == IP_X) a1 = 0;
+    else if (part == IP_P) a1 = min(N, 4);
+    else if (part == IP_E) a0 = max(0, N - 5);
+}
+
+// One sweep (part, axis) over samples held in shared memory: sample (y, x) of the level lives at sm[y * ys + x * xs],
+// the staged window covers level rows [ly0, ly0 + h) and columns [lx0, lx0 + w) (a whole level, or a tile plus its halo).
+template <bool INV, bool ALONG_X>
+__device__ __forceinline__ void ip_sweep(float *sm, int ys, int xs, int w, int h, int lx0, int ly0, int N, int part)
+{
+    int a0, a1;
+    ip_part_range<INV>(N, part, a0, a1);
+    const int t0 = max(a0 - (ALONG_X ? lx0 : ly0), 0), t1 = min(a1 - (ALONG_X ? lx0 : ly0), ALONG_X ? w : h);   // window indices along the line
+    if (t1 <= t0) return;   // block-uniform
+    const int na = t1 - t0, nb = ALONG_X ? h : w, n = na * nb;
+    const int tn = ALONG_X ? w : h, d = ALONG_X ? xs : ys;
+    for (int step = 0; step < 5; step++) {
+        const bool scale = INV ? step == 0 : step == 4;
+        const int lift = INV ? step - 1 : step;
+        const int par = INV ? (lift & 1) : !(lift & 1);   // parity of the positions a lifting step updates
+        const float c = scale ? 0.f : ip_coef<INV>(lift);
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            // threads run along x (the contiguous direction of the window) in both cases
+            int ta, tb;
+            if (ALONG_X) { tb = e / na; ta = t0 + (e - tb * na); }
+            else { ta = t0 + e / nb; tb = e - (ta - t0) * nb; }
+            const int i = (ALONG_X ? lx0 : ly0) + ta;   // position along the line
+            if (!scale && (i & 1) != par) continue;
+            if ((INV ? ip_part_inv(N, step, i) : ip_part_fwd(N, step, i)) != part) continue;
+            float *x = sm + (ALONG_X ? tb * ys + ta * xs : ta * ys + tb * xs);
+            if (scale) {
+                const bool odd = i & 1;
+                *x = __fmul_rn(*x, (odd != INV) ? W97F::IZ : W97F::Z);   // forward: even * zeta, odd / zeta; inverse the other way
+                continue;
+            }
+            float l, r;
+            if (i == 0) {   // whole-sample mirror: (2c) * neighbour == c * (nb + nb)
+                if (ta + 1 >= tn) continue;
+                l = r = x[d];
+            } else if (i == N - 1) {
+                if (ta < 1) continue;
+                l = r = x[-d];
+            } else {
+                if (ta < 1 || ta + 1 >= tn) continue;   // neighbour outside the staged window: this sample is halo, its value is not used
+                l = x[-d];
+                r = x[d];
+            }
+            *x = __fadd_rn(*x, __fmul_rn(c, __fadd_rn(l, r)));
+        }
+        __syncthreads();
+    }
+}
+
+// the eight sweeps of one level, in the reference's order (:12975-13451, :17512-17598)
+template <bool INV> __device__ __forceinline__ void ip_level_sweeps(float *sm, int ys, int xs, int w, int h, int lx0, int ly0, int nx, int ny)
+{
+    for (int part = IP_X; part <= IP_E; part++) {
+        if (nx > 1) ip_sweep<INV, true>(sm, ys, xs, w, h, lx0, ly0, nx, part);
+        if (ny > 1) ip_sweep<INV, false>(sm, ys, xs, w, h, lx0, ly0, ny, part);
+    }
+}
+
+// up to two rectangles of a level per launch (the top and the right frame), each cut into tiles of tw x th outputs
+struct IpRects {
+    int n;
+    int x0[2], y0[2], x1[2], y1[2], tw[2], th[2], ntx[2], nt[2];
+};
+
+template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(const LevelParams p, const IpRects rc)
+{
+    extern __shared__ float sm[];
+    const int frame = blockIdx.z;
+    const int nx = p.W, ny = p.H;
+    int b = blockIdx.x, r = 0;
+    if (b >= rc.nt[0]) {
+        b -= rc.nt[0];
+        r = 1;
+    }
+    const int tw = rc.tw[r], th = rc.th[r];
+    const int ox0 = rc.x0[r] + (b % rc.ntx[r]) * tw, oy0 = rc.y0[r] + (b / rc.ntx[r]) * th;
+    const int ox1 = min(ox0 + tw, rc.x1[r]), oy1 = min(oy0 + th, rc.y1[r]);
+    const int lx0 = max(ox0 - IP_HALO, 0), lx1 = min(ox1 + IP_HALO, nx), ly0 = max(oy0 - IP_HALO, 0), ly1 = min(oy1 + IP_HALO, ny);
+    const int w = lx1 - lx0, h = ly1 - ly0, pitch = tw + 2 * IP_HALO + 1, n = w * h;
+    const float *ll = (const float *)p.ll + (size_t)frame * p.ll_frame;
+    const float *hl = (const float *)p.hl + (size_t)frame * p.sub_frame, *lh = (const float *)p.lh + (size_t)frame * p.sub_frame,
+                *hh = (const float *)p.hh + (size_t)frame * p.sub_frame;
+    for (int e = threadIdx.x; e < n; e += IP_THREADS) {
+        const int ty = e / w, tx = e - ty * w, gy = ly0 + ty, gx = lx0 + tx;
+        float v;
+        if (!INV) {
+            v = ((const float *)p.src)[(size_t)frame * p.src_frame + (size_t)gy * p.src_pitch + gx];
+        } else {
+            const int by = gy >> 1, bx = gx >> 1;
+            if (gy & 1) v = (gx & 1) ? hh[(size_t)by * p.sub_pitch + bx] : lh[(size_t)by * p.sub_pitch + bx];
+            else v = (gx & 1) ? hl[(size_t)by * p.sub_pitch + bx] : ll[(size_t)by * p.ll_pitch + bx];
+        }
+        sm[ty * pitch + tx] = v;
+    }
+    __syncthreads();
+    ip_level_sweeps<INV>(sm, pitch, 1, w, h, lx0, ly0, nx, ny);
+    const int ow = ox1 - ox0, oh = oy1 - oy0;
+    for (int e = threadIdx.x; e < ow * oh; e += IP_THREADS) {
+        const int ty = e / ow, tx = e - ty * ow, gy = oy0 + ty, gx = ox0 + tx;
+        const float v = sm[(gy - ly0) * pitch + (gx - lx0)];
+        if (INV) {
+            ((float *)p.dst)[(size_t)frame * p.dst_frame + (size_t)gy * p.dst_pitch + gx] = v;
+        } else {
+            const int by = gy >> 1, bx = gx >> 1;
+            float *o;
+            if (gy & 1) o = ((gx & 1) ? (float *)p.hh : (float *)p.lh) + (size_t)frame * p.sub_frame + (size_t)by * p.sub_pitch + bx;
+            else o = (gx & 1) ? (float *)p.hl + (size_t)frame * p.sub_frame + (size_t)by * p.sub_pitch + bx
+                              : (float *)p.ll + (size_t)frame * p.ll_frame + (size_t)by * p.ll_pitch + bx;
+            *o = v;
+        }
+    }
+}
+
+static void ip_add_rect(IpRects &rc, int x0, int y0, int x1, int y1, size_t &smem)
+{
+    if (x1 <= x0 || y1 <= y0) return;
+    const int rw = x1 - x0, rh = y1 - y0, i = rc.n++;
+    int tw, th;   // (tw + 9) * (th + 8) floats of shared memory: at most ~20 KB
+    if (rh <= 16) { tw = 64; th = rh; }           // the top frame: a few full-width rows
+    else if (rw <= 16) { tw = rw; th = 64; }      // the right frame
+    else { tw = 56; th = 56; }                    // a whole level
+    if (tw > rw) tw = rw;
+    if (th > rh) th = rh;
+    rc.x0[i] = x0; rc.y0[i] = y0; rc.x1[i] = x1; rc.y1[i] = y1;
+    rc.tw[i] = tw; rc.th[i] = th;
+    rc.ntx[i] = (rw + tw - 1) / tw;
+    rc.nt[i] = rc.ntx[i] * ((rh + th - 1) / th);
+    const size_t need = (size_t)(tw + 2 * IP_HALO + 1) * (th + 2 * IP_HALO) * sizeof(float);
+    if (need > smem) smem = need;
+}
+// rectangle [rx0, rx1) x [ry0, ry1) of a level, and optionally a second one, in one launch
+void launch_ip_phase(bool inverse, const LevelParams &p, int frames, int rx0, int ry0, int rx1, int ry1, int sx0, int sy0, int sx1, int sy1,
+                     cudaStream_t st)
+{
+    IpRects rc;
+    memset(&rc, 0, sizeof rc);
+    size_t smem = 0;
+    ip_add_rect(rc, rx0, ry0, rx1, ry1, smem);
+    ip_add_rect(rc, sx0, sy0, sx1, sy1, smem);
+    if (!rc.n) return;
+    const dim3 grid(rc.nt[0] + rc.nt[1], 1, frames);
+    if (inverse) k_ip_phase<true><<<grid, IP_THREADS, smem, st>>>(p, rc);
+    else k_ip_phase<false><<<grid, IP_THREADS, smem, st>>>(p, rc);
+}
+
+// ---- all remaining small levels in one launch: one CTA per frame, truly in place in shared memory ------------------
+// `buf` holds LL_{j0-1} (w0 x h0, dense) on entry of the forward kernel and the interleaved pyramid of the levels j0 .. J-1
+// on exit (level j at stride 2^(j - j0)); the inverse kernel goes the other way.
+constexpr int IP_TAIL_THREADS = 512;
+constexpr int IP_TAIL_CAP = 9216;   // samples (96 x 96): 36 KB + pitch padding of shared memory
+template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail(float *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev)
+{
+    extern __shared__ float sm[];
+    float *g = buf + (size_t)blockIdx.x * frame;
+    const int sp = w0 | 1;   // odd pitch
+    for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
+        const int y = e / w0, x = e - y * w0;
+        sm[y * sp + x] = g[(size_t)y * pitch + x];
+    }
+    __syncthreads();
+    for (int q = 0; q < nlev; q++) {
+        const int k = INV ? nlev - 1 - q : q;
+        const int w = cdiv_pow2(w0, k), h = cdiv_pow2(h0, k);
+        ip_level_sweeps<INV>(sm, sp << k, 1 << k, w, h, 0, 0, w, h);
+    }
+    for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
+        const int y = e / w0, x = e - y * w0;
+        g[(size_t)y * pitch + x] = sm[y * sp + x];
+    }
+}
+int ip_tail_cap() { return IP_TAIL_CAP; }
+void launch_ip_tail(bool inverse, void *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev, int frames, cudaStream_t st)
+{
+    const size_t smem = (size_t)(w0 | 1) * h0 * sizeof(float);
+    if (inverse) k_ip_tail<true><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
+    else k_ip_tail<false><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
+}
+
+// ---- layout translation: Mallat pyramid of J levels <-> interleaved (4-byte elements) ------------------------------
+// Interleaved sample (Y, X): the lowest set bit of Y | X names its level; below bit J it is a sample of LL_J.  Samples
+// whose level is >= jt (multiples of 2^jt in both coordinates) live in the dense "tail block" instead (k_ip_tail),
+// at (Y >> jt, X >> jt).
+struct IpPack {
+    const void *src;
+    void *dst;
+    void *tail;            // tail block (nullptr: none), dense with pitch / frame stride tpitch / tframe
+    int64_t pitch, frame, tpitch, tframe;
+    int ox, oy, J, jt;
+};
+template <bool UNPACK> __global__ void __launch_bounds__(256) k_ip_pack(const IpPack p)
+{
+    const int X = blockIdx.x * 256 + threadIdx.x;
+    if (X >= p.ox) return;
+    const size_t f = (size_t)blockIdx.z * p.frame;
+    const uint32_t *src = (const uint32_t *)p.src;
+    uint32_t *dst = (uint32_t *)p.dst, *tail = (uint32_t *)p.tail;
+    for (int Y = blockIdx.y; Y < p.oy; Y += gridDim.y) {
+        const int t = Y | X;
+        const int lvl = t ? __ffs(t) - 1 : 31;
+        const size_t i = f + (size_t)Y * p.pitch + X;
+        if (tail && lvl >= p.jt) {
+            const size_t m = (size_t)blockIdx.z * p.tframe + (size_t)(Y >> p.jt) * p.tpitch + (X >> p.jt);
+            if (UNPACK) tail[m] = src[i];
+            else dst[i] = tail[m];
+            continue;
+        }
+        size_t m;
+        if (lvl >= p.J) {
+            m = (size_t)(Y >> p.J) * p.pitch + (X >> p.J);
+        } else {
+            const int a = (Y >> lvl) & 1, b = (X >> lvl) & 1, y = Y >> (lvl + 1), x = X >> (lvl + 1);
+            const int hl = cdiv_pow2(p.oy, lvl + 1), wl = cdiv_pow2(p.ox, lvl + 1);
+            m = (size_t)(a ? hl + y : y) * p.pitch + (b ? wl + x : x);
+        }
+        if (UNPACK) dst[f + m] = src[i];
+        else dst[i] = src[f + m];
+    }
+}
+void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int64_t frame, int ox, int oy, int J, void *tail, int64_t tpitch,
+                    int64_t tframe, int jt, int frames, cudaStream_t st)
+{
+    IpPack p;
+    p.src = src; p.dst = dst; p.tail = tail;
+    p.pitch = pitch; p.frame = frame; p.tpitch = tpitch; p.tframe = tframe;
+    p.ox = ox; p.oy = oy; p.J = J; p.jt = jt;
+    const dim3 grid((ox + 255) / 256, oy < 32768 ? oy : 32768, frames);
+    if (unpack) k_ip_pack<true><<<grid, 256, 0, st>>>(p);
+    else k_ip_pack<false><<<grid, 256, 0, st>>>(p);
+}
+
+cudaError_t preload_inplace()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, k_ip_phase<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_phase<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<true>);
+    return e;
+}
+
+}  // namespace dwtb200

@@ -46,6 +46,33 @@ INV(dwt_cdf53_2i_d, DWTB200_CDF53_F64)
 FWD(dwt_cdf97_2f_i, DWTB200_CDF97_I32)
 INV(dwt_cdf97_2i_i, DWTB200_CDF97_I32)
 
+/* interleaved in-place family: zero_padding is ignored, as in the reference */
+#define FWD_IP(NAME, KIND)                                                                                       \
+    void NAME(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,      \
+              int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)                            \
+    {                                                                                                            \
+        (void)zero_padding;                                                                                      \
+        const int rc = dwtb200_fwd2_inplace_host(KIND, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y,      \
+                                                 size_i_big_x, size_i_big_y, j_max_ptr, decompose_one);          \
+        if (rc) die(#NAME, rc);                                                                                  \
+    }
+#define INV_IP(NAME, KIND)                                                                                       \
+    void NAME(void *ptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,      \
+              int size_i_big_y, int j_max, int decompose_one, int zero_padding)                                 \
+    {                                                                                                            \
+        (void)zero_padding;                                                                                      \
+        const int rc = dwtb200_inv2_inplace_host(KIND, ptr, stride_x, stride_y, size_o_big_x, size_o_big_y,      \
+                                                 size_i_big_x, size_i_big_y, j_max, decompose_one);              \
+        if (rc) die(#NAME, rc);                                                                                  \
+    }
+FWD_IP(dwt_cdf97_2f_inplace_s, DWTB200_CDF97_F32)
+FWD_IP(dwt_cdf97_2f_inplace_sep_s, DWTB200_CDF97_F32)
+FWD_IP(dwt_cdf97_2f_inplace_sdl_s, DWTB200_CDF97_F32)
+FWD_IP(dwt_cdf97_2f_inplace_sep_sdl_s, DWTB200_CDF97_F32)
+INV_IP(dwt_cdf97_2i_inplace_s, DWTB200_CDF97_F32)
+FWD_IP(dwt_cdf53_2f_inplace_s, DWTB200_CDF53_F32)
+INV_IP(dwt_cdf53_2i_inplace_s, DWTB200_CDF53_F32)
+
 void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                      int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)
 {

@@ -23,6 +23,8 @@
  *   padding   src/libdwt.c:12080-12215
  *   constants src/inline.h:310-323, helpers 443-460, 590-607
  *   patterns  src/libdwt.c:1112-1244, fills 1247-1385, src/volume.c:41
+ *   in-place  src/libdwt.c:12926 13485 13641 14847 (9/7 fwd) 17474 (9/7 inv) 16553 17886 (5/3 float); parts 9591 9929
+ *             10803-10898 11574-11670; lines 11032 11831
  *   3-D       src/volume-dwt.c:727 (fwd, via src/dwt-simple.c:2166, 580, 981, 1469)
  *             src/volume-dwt.c:1115 (inv, via src/libdwt.c:17182)
  */
@@ -359,6 +361,151 @@ EXPORT_2D(cdf53_i, K53I)
 EXPORT_2D(cdf53_s, K53S)
 EXPORT_2D(cdf53_d, K53D)
 EXPORT_2D(cdf97_i, K97I)
+
+/* =====================================================================================
+ * Interleaved in-place family (src/libdwt.c:12926 dwt_cdf97_2f_inplace_s and its _sep / _sdl twins :13485,
+ * :13641, :14847 -- all four bit-identical on every input tried; inverse :17474).  Coefficients stay where
+ * the lifting leaves them: level j works on the samples at stride 2^j, even = L, odd = H.
+ *
+ * The reference runs every level as up to eight sweeps -- "exceptions" over rows then columns (lines of
+ * 2..4 / 2..3 samples, the whole 1-D transform at once, :10803, :11574), then prolog, core and epilog, each over
+ * all rows and then over all columns (:12975-13451, :17512-17598).  In one dimension the three parts add up to
+ * the textbook lifting; in two dimensions the top rows (column prolog before the row core) and the right
+ * columns (row epilog after the column core) get their row and column steps in a different order than
+ * rows-then-columns, which changes the rounding there.  Restated as a table: every lifting operation
+ * (step, position) of a line belongs to exactly one part (:9591 prolog, :9929 epilog, the rest core), and a sweep
+ * applies the operations of its part step by step.  A line of one sample is not touched at all (:12975, :12997).
+ * ===================================================================================== */
+enum { PH_X = 0, PH_P = 1, PH_C = 2, PH_E = 3 };
+/* forward steps: 0 alpha (odd), 1 beta (even), 2 gamma (odd), 3 delta (even), 4 scale; offset 1 (:10831) */
+static int ip_phase_fwd(int N, int step, int i)
+{
+    if (N < 5) return PH_X;
+    if ((step == 0 && (i == 1 || i == 3)) || (step == 1 && (i == 0 || i == 2)) || (step == 2 && i == 1) ||
+        (step == 3 && i == 0) || (step == 4 && i == 0))
+        return PH_P;
+    if (N & 1) {
+        if ((step == 1 && i == N - 1) || (step == 2 && i == N - 2) || (step == 3 && (i == N - 1 || i == N - 3)) ||
+            (step == 4 && i >= N - 4))
+            return PH_E;
+    } else {
+        if ((step == 0 && i == N - 1) || (step == 1 && i == N - 2) || (step == 2 && (i == N - 1 || i == N - 3)) ||
+            (step == 3 && (i == N - 2 || i == N - 4)) || (step == 4 && i >= N - 5))
+            return PH_E;
+    }
+    return PH_C;
+}
+/* inverse steps: 0 scale, 1 even += -u2, 2 odd += p2, 3 even += -u1, 4 odd += p1; offset 0 (:11604) */
+static int ip_phase_inv(int N, int step, int i)
+{
+    if (N < 4) return PH_X;
+    if ((step == 0 && i <= 3) || (step == 1 && (i == 0 || i == 2)) || (step == 2 && i == 1) || (step == 3 && i == 0))
+        return PH_P;
+    if (N & 1) {
+        if ((step == 0 && i == N - 1) || (step == 1 && i == N - 1) || (step == 2 && i == N - 2) ||
+            (step == 3 && (i == N - 1 || i == N - 3)) || (step == 4 && (i == N - 2 || i == N - 4)))
+            return PH_E;
+    } else {
+        if ((step == 2 && i == N - 1) || (step == 3 && i == N - 2) || (step == 4 && (i == N - 1 || i == N - 3)))
+            return PH_E;
+    }
+    return PH_C;
+}
+#define IP(i) (*(float *)(line + (ptrdiff_t)(i) * st))
+static void ip_lift(char *line, ptrdiff_t st, int N, int i, float c)
+{
+    if (i == 0) IP(0) += (2 * c) * IP(1);
+    else if (i == N - 1) IP(N - 1) += (2 * c) * IP(N - 2);
+    else IP(i) += c * (IP(i - 1) + IP(i + 1));
+}
+static void ip_sweep(char *line, ptrdiff_t st, int N, int inverse, int part)
+{
+    const float z = S1s, iz = 1 / z;
+    static const float cf[4] = {-P1s, U1s, -P2s, U2s}, ci[4] = {-U2s, P2s, -U1s, P1s};
+    for (int step = 0; step < 5; step++) {
+        const int scale = inverse ? step == 0 : step == 4;
+        const int lift = inverse ? step - 1 : step;            /* index into cf / ci */
+        const int par = scale ? -1 : (inverse ? !(lift & 1) ? 0 : 1 : !(lift & 1) ? 1 : 0);
+        for (int i = 0; i < N; i++) {
+            if (par >= 0 && (i & 1) != par) continue;
+            if ((inverse ? ip_phase_inv(N, step, i) : ip_phase_fwd(N, step, i)) != part) continue;
+            if (scale) IP(i) *= ((i & 1) != inverse) ? iz : z;   /* fwd: even*z odd*iz; inv: even*iz odd*z */
+            else ip_lift(line, st, N, i, inverse ? ci[lift] : cf[lift]);
+        }
+    }
+}
+#undef IP
+static void ip_level(char *ptr, ptrdiff_t sxj, ptrdiff_t syj, int nx, int ny, int inverse)
+{
+    for (int part = PH_X; part <= PH_E; part++) {
+        if (nx > 1)
+            for (int y = 0; y < ny; y++) ip_sweep(ptr + (ptrdiff_t)y * sxj, syj, nx, inverse, part);
+        if (ny > 1)
+            for (int x = 0; x < nx; x++) ip_sweep(ptr + (ptrdiff_t)x * syj, sxj, ny, inverse, part);
+    }
+}
+/* sx = bytes between rows, sy = bytes between samples of a row (the reference's stride_x / stride_y) */
+void orc_cdf97_s_2f_inplace(void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
+                            int decompose_one)
+{
+    const int omin = ox < oy ? ox : oy, omax = ox < oy ? oy : ox;
+    const int j_limit = orc_ceil_log2(decompose_one ? omax : omin);
+    if (*j_max_ptr < 0 || *j_max_ptr > j_limit) *j_max_ptr = j_limit;
+    for (int j = 0; j < *j_max_ptr; j++)
+        ip_level((char *)ptr, (ptrdiff_t)sx << j, (ptrdiff_t)sy << j, orc_ceil_div_pow2(ix, j), orc_ceil_div_pow2(iy, j), 0);
+}
+void orc_cdf97_s_2i_inplace(void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
+                            int decompose_one)
+{
+    const int omin = ox < oy ? ox : oy, omax = ox < oy ? oy : ox;
+    int j = orc_ceil_log2(decompose_one ? omax : omin);
+    if (j_max >= 0 && j_max < j) j = j_max;
+    for (; j > 0; j--)
+        ip_level((char *)ptr, (ptrdiff_t)sx << (j - 1), (ptrdiff_t)sy << (j - 1), orc_ceil_div_pow2(ix, j - 1),
+                 orc_ceil_div_pow2(iy, j - 1), 1);
+}
+
+/* CDF 5/3 float of the same family (src/libdwt.c:16553, 17886; lines :11032, :11831): every level transforms all rows,
+ * then all columns, in place at stride 2^j -- the textbook lifting of fwd53_s / inv53_s; a line of one sample is scaled. */
+static void ip53_lines(char *ptr, ptrdiff_t line_step, int nlines, ptrdiff_t st, int N, int inverse)
+{
+    float *tmp = (float *)malloc((size_t)(N > 2 ? N : 2) * sizeof(float));
+    for (int l = 0; l < nlines; l++) {
+        char *line = ptr + (ptrdiff_t)l * line_step;
+        if (N == 1) {
+            if (inverse) one_inv53_s(line); else one_fwd53_s(line);
+            continue;
+        }
+        gather(tmp, 4, line, st, N, 4);
+        if (inverse) inv53_s(tmp, N); else fwd53_s(tmp, N);
+        gather(line, st, tmp, 4, N, 4);
+    }
+    free(tmp);
+}
+void orc_cdf53_s_2f_inplace(void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
+                            int decompose_one)
+{
+    const int omin = ox < oy ? ox : oy, omax = ox < oy ? oy : ox;
+    const int j_limit = orc_ceil_log2(decompose_one ? omax : omin);
+    if (*j_max_ptr < 0 || *j_max_ptr > j_limit) *j_max_ptr = j_limit;
+    for (int j = 0; j < *j_max_ptr; j++) {
+        const int nx = orc_ceil_div_pow2(ix, j), ny = orc_ceil_div_pow2(iy, j);
+        ip53_lines((char *)ptr, (ptrdiff_t)sx << j, ny, (ptrdiff_t)sy << j, nx, 0);
+        ip53_lines((char *)ptr, (ptrdiff_t)sy << j, nx, (ptrdiff_t)sx << j, ny, 0);
+    }
+}
+void orc_cdf53_s_2i_inplace(void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
+                            int decompose_one)
+{
+    const int omin = ox < oy ? ox : oy, omax = ox < oy ? oy : ox;
+    int j = orc_ceil_log2(decompose_one ? omax : omin);
+    if (j_max >= 0 && j_max < j) j = j_max;
+    for (; j > 0; j--) {
+        const int nx = orc_ceil_div_pow2(ix, j - 1), ny = orc_ceil_div_pow2(iy, j - 1);
+        ip53_lines((char *)ptr, (ptrdiff_t)sx << (j - 1), ny, (ptrdiff_t)sy << (j - 1), nx, 1);
+        ip53_lines((char *)ptr, (ptrdiff_t)sy << (j - 1), nx, (ptrdiff_t)sx << (j - 1), ny, 1);
+    }
+}
 
 /* =====================================================================================
  * Test patterns (src/libdwt.c:1112-1244).  wrap32 != 0 reproduces the reference's 32-bit

@@ -38,6 +38,9 @@ class Oracle:
         for name in ("cdf97_s", "cdf97_d", "cdf53_i", "cdf53_s", "cdf53_d", "cdf97_i"):
             getattr(L, f"orc_{name}_2f").argtypes = [vp, i64, i64, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
             getattr(L, f"orc_{name}_2i").argtypes = [vp, i64, i64, ci, ci, ci, ci, ci, ci, ci]
+        for name in ("cdf97_s", "cdf53_s"):
+            getattr(L, f"orc_{name}_2f_inplace").argtypes = [vp, i64, i64, ci, ci, ci, ci, C.POINTER(ci), ci]
+            getattr(L, f"orc_{name}_2i_inplace").argtypes = [vp, i64, i64, ci, ci, ci, ci, ci, ci]
         L.orc_fill_s.argtypes = [vp, i64, i64, ci, ci, ci, ci, ci]
         L.orc_fill_d.argtypes = [vp, i64, i64, ci, ci, ci, ci]
         L.orc_fill_i.argtypes = [vp, i64, i64, ci, ci, ci, ci, ci]
@@ -68,6 +71,19 @@ class Oracle:
         iy, ix = inner if inner is not None else (oy, ox)
         getattr(self.lib, f"orc_{self._fn(wavelet, t)}_2i")(
             _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, zero_padding)
+
+    def fwd2_inplace(self, img, wavelet, j_max=-1, decompose_one=0, inner=None):
+        """dwt_cdf97_2f_inplace_s (and its _sep/_sdl twins) / dwt_cdf53_2f_inplace_s: float32, interleaved layout."""
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        j = C.c_int(j_max)
+        getattr(self.lib, f"orc_cdf{wavelet}_s_2f_inplace")(_ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one)
+        return j.value
+
+    def inv2_inplace(self, img, wavelet, j_max=-1, decompose_one=0, inner=None):
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        getattr(self.lib, f"orc_cdf{wavelet}_s_2i_inplace")(_ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one)
 
     def fwd2_s2(self, src, dst, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         """dwt_cdf97_2f_s2 (src/libdwt.c:12619): the first pass of level 0 that runs reads its lines from src and writes
@@ -193,6 +209,11 @@ class Ref:
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci]
         for n in ("dwt_util_test_image_fill2_s", "dwt_util_test_image_fill2_i"):
             getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci]
+        for n in ("dwt_cdf97_2f_inplace_s", "dwt_cdf97_2f_inplace_sep_s", "dwt_cdf97_2f_inplace_sdl_s", "dwt_cdf97_2f_inplace_sep_sdl_s",
+                  "dwt_cdf53_2f_inplace_s"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
+        for n in ("dwt_cdf97_2i_inplace_s", "dwt_cdf53_2i_inplace_s"):
+            getattr(L, n).argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         L.dwt_cdf97_2f_s2.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, C.POINTER(ci), ci, ci]
         L.dwt_cdf97_2i_s2.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         L.dwt_util_set_num_threads.argtypes = [ci]
@@ -226,6 +247,25 @@ class Ref:
         getattr(self.lib, self._fn(wavelet, t, "f"))(
             _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one, zero_padding)
         return j.value
+
+    def fwd2_inplace(self, img, wavelet, j_max=-1, decompose_one=0, inner=None, variant=""):
+        """variant: "", "sep_", "sdl_", "sep_sdl_" (9/7 only).  The in-place drivers assert a single worker."""
+        self._check(img)
+        self.lib.dwt_util_set_num_workers(1)
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        j = C.c_int(j_max)
+        getattr(self.lib, f"dwt_cdf{wavelet}_2f_inplace_{variant}s")(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, C.byref(j), decompose_one, 0)
+        return j.value
+
+    def inv2_inplace(self, img, wavelet, j_max=-1, decompose_one=0, inner=None):
+        self._check(img)
+        self.lib.dwt_util_set_num_workers(1)
+        oy, ox = img.shape
+        iy, ix = inner if inner is not None else (oy, ox)
+        getattr(self.lib, f"dwt_cdf{wavelet}_2i_inplace_s")(
+            _ptr(img), img.strides[0], img.strides[1], ox, oy, ix, iy, j_max, decompose_one, 0)
 
     def inv2(self, img, wavelet, t, j_max=-1, decompose_one=0, zero_padding=0, inner=None):
         self._check(img)

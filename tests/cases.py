@@ -42,6 +42,31 @@ def sparse_cases():
     return out
 
 
+# interleaved in-place family: (wavelet, ox, oy, ix, iy, j_max, decompose_one), float32 only
+INPLACE_SHAPES = [
+    (512, 512), (517, 301), (1000, 37), (64, 3), (5, 1000), (2, 2), (3, 7), (1, 1), (1, 9), (9, 1), (2, 5), (4, 4), (5, 5), (6, 7), (8, 6),
+    (16, 16), (31, 33), (33, 32), (40, 100), (128, 128), (129, 127), (241, 250), (256, 256), (300, 200), (720, 486), (1025, 1023), (1920, 1080),
+]
+
+
+def inplace_cases():
+    out = []
+    for w in ("97", "53"):
+        for (ox, oy) in INPLACE_SHAPES:
+            for (j, d1) in DEPTHS:
+                if (j, d1) != (-1, 0) and max(ox, oy) > 600 and (ox, oy) not in ((1000, 37), (5, 1000)):
+                    continue
+                out.append((w, ox, oy, ox, oy, j, d1))
+        for (ox, oy, ix, iy) in [(64, 64, 50, 37), (128, 96, 128, 50), (300, 280, 255, 270), (40, 40, 1, 1), (33, 70, 17, 5)]:
+            for (j, d1) in [(-1, 0), (-1, 1)]:
+                out.append((w, ox, oy, ix, iy, j, d1))
+    return out
+
+
+def inplace_id(c):
+    return "ip-" + "-".join(str(v) for v in c)
+
+
 def case_id(c):
     return "-".join(str(v) for v in c)
 

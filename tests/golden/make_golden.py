@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from cases import DT, case_id, dense_cases, digest, sparse_cases  # noqa: E402
+from cases import DT, case_id, dense_cases, digest, inplace_cases, inplace_id, sparse_cases  # noqa: E402
 from oracle.orc import Ref  # noqa: E402
 
 
@@ -70,6 +70,18 @@ def main():
             keep["vol-16-16-16/fwd"] = b.copy()
         ref.inv3(b)
         out[f"vol-{nx}-{ny}-{nz}"] = {"fwd": fwd, "inv": digest(b)}
+    # interleaved in-place family (src/libdwt.c:12926, 17474, 16553, 17886)
+    for c in inplace_cases():
+        w, ox, oy, ix, iy, j, d1 = c
+        img = np.zeros((oy, ox), dtype=np.float32)
+        ref.fill(img, "s", rand=0, type_=0)
+        J = ref.fwd2_inplace(img, w, j_max=j, decompose_one=d1, inner=(iy, ix))
+        fwd = img.copy()
+        ref.inv2_inplace(img, w, j_max=J, decompose_one=d1, inner=(iy, ix))
+        out[inplace_id(c)] = {"J": J, "fwd": digest(fwd), "inv": digest(img)}
+        if c in (("97", 31, 33, 31, 33, -1, 0), ("97", 64, 64, 50, 37, -1, 0), ("53", 31, 33, 31, 33, -1, 0)):
+            keep[inplace_id(c) + "/fwd"] = fwd
+            keep[inplace_id(c) + "/inv"] = img.copy()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "vectors.npz"), **keep)
