@@ -1225,9 +1225,11 @@ int ip_level(dwtb200_image *im, bool inverse, const LevelParams &lp)
     return 0;
 }
 
-int ip_run97(dwtb200_image *im, bool inverse, int J)
+// `flips`: the result is left in the other plane
+int ip_run97(dwtb200_image *im, bool inverse, int J, int &flips)
 {
-    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];   // A: the image (interleaved), B: Mallat scratch
+    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];   // A: the image (interleaved), B: scratch
+    flips = 0;
     // levels jt .. J-1 run inside one CTA per frame once their input fits its shared memory (k_ip_tail)
     int jt = J;
     for (int j = 0; j < J; j++)
@@ -1244,26 +1246,55 @@ int ip_run97(dwtb200_image *im, bool inverse, int J)
     const Band tb = ll_band(im, jt - 1);   // LL_{jt-1}: dense input of level jt, and the tail block
     const int tw = cdiv_pow2(im->ox, jt), th = cdiv_pow2(im->oy, jt);
     LevelParams lp;
+    // Level 0 on the ring kernels reads / writes the interleaved layout directly (LevelParams::il): the image is then
+    // translated only at its even rows and columns, where the deeper levels live.
+    level_geometry(im, 0, inverse, lp);
+    const bool il0 = std::min(im->ox, im->oy) >= IP_STD_MIN && (int64_t)im->ox * im->oy * im->frames > g.tile_max && !lp.narrow &&
+                     (g.ring & (inverse ? 2 : 1)) && ring_interleaved_ok(im->kind) && !g.force_generic;
+    char *M = il0 ? A : B;   // Mallat scratch of the levels the translation kernels handle (forward: level 0 has been read by then)
+    const int shift = il0 ? 1 : 0;
+    void *tailp = tail ? tb.p : nullptr;
     if (!inverse) {
         Band in = {A, im->pitch, im->frame};
         for (int j = 0; j < jt; j++) {
-            const Band out = fwd_level_params(im, j, J, in, B, lp);
+            Band out = fwd_level_params(im, j, J, in, il0 ? (j == 0 ? B : A) : B, lp);
+            if (il0 && j == 0) {
+                lp.il = B;
+                lp.il_pitch = im->pitch;
+                lp.il_frame = im->frame;
+                out = ll_band(im, 0);   // also when J == 1: the interleaved rows hold LL already
+                lp.ll = out.p;
+                lp.ll_pitch = out.pitch;
+                lp.ll_frame = out.frame;
+            }
             const int r = ip_level(im, false, lp);
             if (r) return r;
             in = out;
         }
         if (tail) launch_ip_tail(false, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
-        launch_ip_pack(false, B, A, im->pitch, im->frame, im->ox, im->oy, J, tail ? tb.p : nullptr, tb.pitch, tb.frame, jt, im->frames, g.st);
+        if (!il0 || J > 1) launch_ip_pack(false, M, il0 ? B : A, im->pitch, im->frame, im->ox, im->oy, J, tailp, tb.pitch, tb.frame, jt, shift, im->frames, g.st);
     } else {
-        launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, tail ? tb.p : nullptr, tb.pitch, tb.frame, jt, im->frames, g.st);
+        if (!il0 || J > 1) launch_ip_pack(true, A, il0 ? B : B, im->pitch, im->frame, im->ox, im->oy, J, tailp, tb.pitch, tb.frame, jt, shift, im->frames, g.st);
         if (tail) launch_ip_tail(true, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
         for (int j = jt - 1; j >= 0; j--) {
-            inv_level_params(im, j, J, B, A, lp);
+            inv_level_params(im, j, J, B, il0 ? B : A, lp);
+            if (il0 && j == 0) {
+                if (J > 1) {   // LL_0 joins the level-0 subbands in the interleaved plane
+                    const Band l0 = ll_band(im, 0);
+                    launch_ip_scatter(l0.p, l0.pitch, l0.frame, A, im->pitch, im->frame, lp.nLx, lp.nLy, im->frames, g.st);
+                    g.launches++;
+                }
+                lp.il = A;
+                lp.il_pitch = im->pitch;
+                lp.il_frame = im->frame;
+                lp.sub_aligned = 1;   // no HL / HH column origins to align in this layout: always the ring kernel
+            }
             const int r = ip_level(im, true, lp);
             if (r) return r;
         }
     }
     g.launches += tail ? 2 : 1;
+    flips = il0 ? 1 : 0;
     return 0;
 }
 
@@ -1277,13 +1308,13 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
     if (im->kind == DWTB200_CDF53_F32) {   // bit-identical to the Mallat transform, only laid out differently (:16583); a lone sample is scaled
         int r = 0;
         if (inverse) {
-            launch_ip_pack(true, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, im->frames, g.st);
+            launch_ip_pack(true, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 0, im->frames, g.st);
             im->cur ^= 1;
             r = transform(im, true, im->ox, im->oy, J, 0);
         } else {
             r = transform(im, false, im->ox, im->oy, J, 0);
             if (r) return r;
-            launch_ip_pack(false, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, im->frames, g.st);
+            launch_ip_pack(false, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 0, im->frames, g.st);
             im->cur ^= 1;
         }
         im->last_launches++;
@@ -1298,15 +1329,18 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
     if (it == im->graphs.end()) {
         g.launches = 0;
         if (!g.use_graph) {
-            const int r = ip_run97(im, inverse, J);
+            int flips = 0;
+            const int r = ip_run97(im, inverse, J, flips);
             if (r) return r;
             CK(cudaGetLastError());
             im->last_launches = g.launches;
+            if (flips) im->cur ^= 1;
             return DWTB200_OK;
         }
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
-        const int rr = ip_run97(im, inverse, J);
+        int flips = 0;
+        const int rr = ip_run97(im, inverse, J, flips);
         const cudaError_t le = cudaGetLastError(), ce = cudaStreamEndCapture(g.st, &graph);
         if (rr || le != cudaSuccess || ce != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
@@ -1315,7 +1349,7 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
         dwtb200_image::Entry e;
         e.launches = g.launches;
         e.path = 0;
-        e.flips = 0;
+        e.flips = flips;
         e.sync = nullptr;
         const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
         cudaGraphDestroy(graph);
@@ -1325,6 +1359,7 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
     CK(cudaGraphLaunch(it->second.exec, g.st));
     im->last_launches = it->second.launches;
     im->last_path = 0;
+    if (it->second.flips) im->cur ^= 1;
     return DWTB200_OK;
 }
 }  // namespace

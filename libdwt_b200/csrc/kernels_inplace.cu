@@ -80,60 +80,83 @@ template <bool INV> __device__ __forceinline__ void ip_part_range(int N, int par
     else if (part == IP_E) a0 = max(0, N - 5);
 }
 
-// One sweep (part, axis) over samples held in shared memory: sample (y, x) of the level lives at sm[y * ys + x * xs],
-// the staged window covers level rows [ly0, ly0 + h) and columns [lx0, lx0 + w) (a whole level, or a tile plus its halo).
-template <bool INV, bool ALONG_X>
-__device__ __forceinline__ void ip_sweep(float *sm, int ys, int xs, int w, int h, int lx0, int ly0, int N, int part)
+// Per position of a line: which part does each of its five steps belong to (3 bits per step; 7 = the step does not
+// touch this position).  Built once per staged window so that the sweeps are a table lookup per sample.
+template <bool INV> __device__ __forceinline__ uint32_t ip_codes(int N, int i)
 {
-    int a0, a1;
-    ip_part_range<INV>(N, part, a0, a1);
-    const int t0 = max(a0 - (ALONG_X ? lx0 : ly0), 0), t1 = min(a1 - (ALONG_X ? lx0 : ly0), ALONG_X ? w : h);   // window indices along the line
-    if (t1 <= t0) return;   // block-uniform
-    const int na = t1 - t0, nb = ALONG_X ? h : w, n = na * nb;
-    const int tn = ALONG_X ? w : h, d = ALONG_X ? xs : ys;
+    uint32_t m = 0;
+#pragma unroll
     for (int step = 0; step < 5; step++) {
         const bool scale = INV ? step == 0 : step == 4;
         const int lift = INV ? step - 1 : step;
         const int par = INV ? (lift & 1) : !(lift & 1);   // parity of the positions a lifting step updates
-        const float c = scale ? 0.f : ip_coef<INV>(lift);
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            // threads run along x (the contiguous direction of the window) in both cases
-            int ta, tb;
-            if (ALONG_X) { tb = e / na; ta = t0 + (e - tb * na); }
-            else { ta = t0 + e / nb; tb = e - (ta - t0) * nb; }
-            const int i = (ALONG_X ? lx0 : ly0) + ta;   // position along the line
-            if (!scale && (i & 1) != par) continue;
-            if ((INV ? ip_part_inv(N, step, i) : ip_part_fwd(N, step, i)) != part) continue;
-            float *x = sm + (ALONG_X ? tb * ys + ta * xs : ta * ys + tb * xs);
-            if (scale) {
-                const bool odd = i & 1;
-                *x = __fmul_rn(*x, (odd != INV) ? W97F::IZ : W97F::Z);   // forward: even * zeta, odd / zeta; inverse the other way
-                continue;
+        const uint32_t code = (!scale && (i & 1) != par) ? 7u : (uint32_t)(INV ? ip_part_inv(N, step, i) : ip_part_fwd(N, step, i));
+        m |= code << (3 * step);
+    }
+    return m;
+}
+// tx[0..w) / ty[0..h): codes of the window's columns / rows
+template <bool INV> __device__ __forceinline__ void ip_build_tables(uint32_t *tx, uint32_t *ty, int w, int h, int lx0, int ly0, int nx, int ny)
+{
+    for (int e = threadIdx.x; e < w + h; e += blockDim.x) {
+        if (e < w) tx[e] = ip_codes<INV>(nx, lx0 + e);
+        else ty[e - w] = ip_codes<INV>(ny, ly0 + e - w);
+    }
+}
+
+// One sweep (part, axis) over samples held in shared memory: sample (y, x) of the level lives at sm[y * ys + x * xs],
+// the staged window covers level rows [ly0, ly0 + h) and columns [lx0, lx0 + w) (a whole level, or a tile plus its halo).
+// Warps walk the rows, lanes the columns.
+template <bool INV, bool ALONG_X>
+__device__ __forceinline__ void ip_sweep(float *sm, const uint32_t *tab, int ys, int xs, int w, int h, int lx0, int ly0, int N, int part)
+{
+    int a0, a1;
+    ip_part_range<INV>(N, part, a0, a1);
+    const int o = ALONG_X ? lx0 : ly0, tn = ALONG_X ? w : h, d = ALONG_X ? xs : ys;
+    const int t0 = max(a0 - o, 0), t1 = min(a1 - o, tn);   // window indices along the line
+    if (t1 <= t0) return;   // block-uniform
+    const int x0 = ALONG_X ? t0 : 0, x1 = ALONG_X ? t1 : w, y0 = ALONG_X ? 0 : t0, y1 = ALONG_X ? h : t1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int step = 0; step < 5; step++) {
+        const bool scale = INV ? step == 0 : step == 4;
+        const float c = scale ? 0.f : ip_coef<INV>(INV ? step - 1 : step);
+        for (int y = y0 + warp; y < y1; y += nwarps) {
+            for (int x = x0 + lane; x < x1; x += 32) {
+                const int t = ALONG_X ? x : y, i = o + t;   // window index and position along the line
+                if (((tab[t] >> (3 * step)) & 7u) != (uint32_t)part) continue;
+                float *q = sm + y * ys + x * xs;
+                if (scale) {
+                    *q = __fmul_rn(*q, ((i & 1) != INV) ? W97F::IZ : W97F::Z);   // forward: even * zeta, odd / zeta; inverse the other way
+                    continue;
+                }
+                float l, r;
+                if (i == 0) {   // whole-sample mirror: (2c) * neighbour == c * (nb + nb)
+                    if (t + 1 >= tn) continue;
+                    l = r = q[d];
+                } else if (i == N - 1) {
+                    if (t < 1) continue;
+                    l = r = q[-d];
+                } else {
+                    if (t < 1 || t + 1 >= tn) continue;   // neighbour outside the staged window: this sample is halo, its value is not used
+                    l = q[-d];
+                    r = q[d];
+                }
+                *q = __fadd_rn(*q, __fmul_rn(c, __fadd_rn(l, r)));
             }
-            float l, r;
-            if (i == 0) {   // whole-sample mirror: (2c) * neighbour == c * (nb + nb)
-                if (ta + 1 >= tn) continue;
-                l = r = x[d];
-            } else if (i == N - 1) {
-                if (ta < 1) continue;
-                l = r = x[-d];
-            } else {
-                if (ta < 1 || ta + 1 >= tn) continue;   // neighbour outside the staged window: this sample is halo, its value is not used
-                l = x[-d];
-                r = x[d];
-            }
-            *x = __fadd_rn(*x, __fmul_rn(c, __fadd_rn(l, r)));
         }
         __syncthreads();
     }
 }
 
 // the eight sweeps of one level, in the reference's order (:12975-13451, :17512-17598)
-template <bool INV> __device__ __forceinline__ void ip_level_sweeps(float *sm, int ys, int xs, int w, int h, int lx0, int ly0, int nx, int ny)
+template <bool INV>
+__device__ __forceinline__ void ip_level_sweeps(float *sm, uint32_t *tx, uint32_t *ty, int ys, int xs, int w, int h, int lx0, int ly0, int nx, int ny)
 {
+    ip_build_tables<INV>(tx, ty, w, h, lx0, ly0, nx, ny);
+    __syncthreads();
     for (int part = IP_X; part <= IP_E; part++) {
-        if (nx > 1) ip_sweep<INV, true>(sm, ys, xs, w, h, lx0, ly0, nx, part);
-        if (ny > 1) ip_sweep<INV, false>(sm, ys, xs, w, h, lx0, ly0, ny, part);
+        if (nx > 1) ip_sweep<INV, true>(sm, tx, ys, xs, w, h, lx0, ly0, nx, part);
+        if (ny > 1) ip_sweep<INV, false>(sm, ty, ys, xs, w, h, lx0, ly0, ny, part);
     }
 }
 
@@ -166,6 +189,8 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
         float v;
         if (!INV) {
             v = ((const float *)p.src)[(size_t)frame * p.src_frame + (size_t)gy * p.src_pitch + gx];
+        } else if (p.il) {   // interleaved source (level 0 of the ring path): all four subbands lie where they belong
+            v = ((const float *)p.il)[(size_t)frame * p.il_frame + (size_t)gy * p.il_pitch + gx];
         } else {
             const int by = gy >> 1, bx = gx >> 1;
             if (gy & 1) v = (gx & 1) ? hh[(size_t)by * p.sub_pitch + bx] : lh[(size_t)by * p.sub_pitch + bx];
@@ -174,13 +199,17 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
         sm[ty * pitch + tx] = v;
     }
     __syncthreads();
-    ip_level_sweeps<INV>(sm, pitch, 1, w, h, lx0, ly0, nx, ny);
+    uint32_t *tabx = (uint32_t *)(sm + pitch * (th + 2 * IP_HALO)), *taby = tabx + (tw + 2 * IP_HALO);
+    ip_level_sweeps<INV>(sm, tabx, taby, pitch, 1, w, h, lx0, ly0, nx, ny);
     const int ow = ox1 - ox0, oh = oy1 - oy0;
     for (int e = threadIdx.x; e < ow * oh; e += IP_THREADS) {
         const int ty = e / ow, tx = e - ty * ow, gy = oy0 + ty, gx = ox0 + tx;
         const float v = sm[(gy - ly0) * pitch + (gx - lx0)];
         if (INV) {
             ((float *)p.dst)[(size_t)frame * p.dst_frame + (size_t)gy * p.dst_pitch + gx] = v;
+        } else if (p.il) {
+            ((float *)p.il)[(size_t)frame * p.il_frame + (size_t)gy * p.il_pitch + gx] = v;
+            if (!((gy | gx) & 1)) ((float *)p.ll)[(size_t)frame * p.ll_frame + (size_t)(gy >> 1) * p.ll_pitch + (gx >> 1)] = v;
         } else {
             const int by = gy >> 1, bx = gx >> 1;
             float *o;
@@ -206,7 +235,7 @@ static void ip_add_rect(IpRects &rc, int x0, int y0, int x1, int y1, size_t &sme
     rc.tw[i] = tw; rc.th[i] = th;
     rc.ntx[i] = (rw + tw - 1) / tw;
     rc.nt[i] = rc.ntx[i] * ((rh + th - 1) / th);
-    const size_t need = (size_t)(tw + 2 * IP_HALO + 1) * (th + 2 * IP_HALO) * sizeof(float);
+    const size_t need = ((size_t)(tw + 2 * IP_HALO + 1) * (th + 2 * IP_HALO) + (tw + 2 * IP_HALO) + (th + 2 * IP_HALO)) * sizeof(float);
     if (need > smem) smem = need;
 }
 // rectangle [rx0, rx1) x [ry0, ry1) of a level, and optionally a second one, in one launch
@@ -234,6 +263,7 @@ template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail
     extern __shared__ float sm[];
     float *g = buf + (size_t)blockIdx.x * frame;
     const int sp = w0 | 1;   // odd pitch
+    uint32_t *tabx = (uint32_t *)(sm + sp * h0);
     for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
         const int y = e / w0, x = e - y * w0;
         sm[y * sp + x] = g[(size_t)y * pitch + x];
@@ -242,7 +272,8 @@ template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail
     for (int q = 0; q < nlev; q++) {
         const int k = INV ? nlev - 1 - q : q;
         const int w = cdiv_pow2(w0, k), h = cdiv_pow2(h0, k);
-        ip_level_sweeps<INV>(sm, sp << k, 1 << k, w, h, 0, 0, w, h);
+        ip_level_sweeps<INV>(sm, tabx, tabx + w0, sp << k, 1 << k, w, h, 0, 0, w, h);
+        __syncthreads();
     }
     for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
         const int y = e / w0, x = e - y * w0;
@@ -252,7 +283,7 @@ template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail
 int ip_tail_cap() { return IP_TAIL_CAP; }
 void launch_ip_tail(bool inverse, void *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev, int frames, cudaStream_t st)
 {
-    const size_t smem = (size_t)(w0 | 1) * h0 * sizeof(float);
+    const size_t smem = ((size_t)(w0 | 1) * h0 + w0 + h0) * sizeof(float);
     if (inverse) k_ip_tail<true><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
     else k_ip_tail<false><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
 }
@@ -267,15 +298,16 @@ struct IpPack {
     void *tail;            // tail block (nullptr: none), dense with pitch / frame stride tpitch / tframe
     int64_t pitch, frame, tpitch, tframe;
     int ox, oy, J, jt;
+    int shift;             // only the samples at multiples of 2^shift in both coordinates are translated (1: level 0 is already interleaved)
 };
 template <bool UNPACK> __global__ void __launch_bounds__(256) k_ip_pack(const IpPack p)
 {
-    const int X = blockIdx.x * 256 + threadIdx.x;
+    const int X = (blockIdx.x * 256 + threadIdx.x) << p.shift;
     if (X >= p.ox) return;
     const size_t f = (size_t)blockIdx.z * p.frame;
     const uint32_t *src = (const uint32_t *)p.src;
     uint32_t *dst = (uint32_t *)p.dst, *tail = (uint32_t *)p.tail;
-    for (int Y = blockIdx.y; Y < p.oy; Y += gridDim.y) {
+    for (int Y = blockIdx.y << p.shift; Y < p.oy; Y += gridDim.y << p.shift) {
         const int t = Y | X;
         const int lvl = t ? __ffs(t) - 1 : 31;
         const size_t i = f + (size_t)Y * p.pitch + X;
@@ -298,15 +330,33 @@ template <bool UNPACK> __global__ void __launch_bounds__(256) k_ip_pack(const Ip
     }
 }
 void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int64_t frame, int ox, int oy, int J, void *tail, int64_t tpitch,
-                    int64_t tframe, int jt, int frames, cudaStream_t st)
+                    int64_t tframe, int jt, int shift, int frames, cudaStream_t st)
 {
     IpPack p;
     p.src = src; p.dst = dst; p.tail = tail;
     p.pitch = pitch; p.frame = frame; p.tpitch = tpitch; p.tframe = tframe;
-    p.ox = ox; p.oy = oy; p.J = J; p.jt = jt;
-    const dim3 grid((ox + 255) / 256, oy < 32768 ? oy : 32768, frames);
+    p.ox = ox; p.oy = oy; p.J = J; p.jt = jt; p.shift = shift;
+    const int nx = cdiv_pow2(ox, shift), ny = cdiv_pow2(oy, shift);
+    const dim3 grid((nx + 255) / 256, ny < 32768 ? ny : 32768, frames);
     if (unpack) k_ip_pack<true><<<grid, 256, 0, st>>>(p);
     else k_ip_pack<false><<<grid, 256, 0, st>>>(p);
+}
+
+// dense band -> the samples at even rows and even columns of an interleaved plane (LL_0 on its way into the level-0 inverse)
+__global__ void __launch_bounds__(256) k_ip_scatter(const uint32_t *src, int64_t spitch, int64_t sframe, uint32_t *dst, int64_t dpitch, int64_t dframe,
+                                                   int w, int h)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= w) return;
+    src += (size_t)blockIdx.z * sframe;
+    dst += (size_t)blockIdx.z * dframe;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) dst[(size_t)(2 * y) * dpitch + 2 * x] = src[(size_t)y * spitch + x];
+}
+void launch_ip_scatter(const void *src, int64_t spitch, int64_t sframe, void *dst, int64_t dpitch, int64_t dframe, int w, int h, int frames,
+                       cudaStream_t st)
+{
+    const dim3 grid((w + 255) / 256, h < 32768 ? h : 32768, frames);
+    k_ip_scatter<<<grid, 256, 0, st>>>((const uint32_t *)src, spitch, sframe, (uint32_t *)dst, dpitch, dframe, w, h);
 }
 
 cudaError_t preload_inplace()
@@ -316,6 +366,7 @@ cudaError_t preload_inplace()
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_phase<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_scatter);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<true>);
     return e;

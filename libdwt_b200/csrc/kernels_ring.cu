@@ -21,6 +21,7 @@
 //
 // Same reference semantics and bit-identical results as kernels_stream.cu (see there for the
 // /root/reference/src/libdwt.c lines each pass replaces).
+#include <type_traits>
 #include "chain.cuh"
 #include "stream_common.cuh"
 
@@ -130,7 +131,7 @@ struct RingState {   // position in a consumer's ring, advanced identically by p
 // forward level
 // =====================================================================================================
 // CTA (band, strip): band = p.bw adjacent column groups (one consumer warp each), strip = p.pps row pairs.
-template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::THREADS, CFG::NCTA) k_fwd_ring(const LevelParams p)
+template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launch_bounds__(CFG::THREADS, CFG::NCTA) k_fwd_ring(const LevelParams p)
 {
     using T = typename WV::T;
     static_assert(VPL * sizeof(T) == 32, "a lane holds 32 bytes of a row");
@@ -263,6 +264,27 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         T oL[VPL], oH[VPL];   // column-lifted low / high outputs of this iteration
         vfwd<WV, VPL>(a, b, st, oL, oH);
         const int kk = m - DELAY;
+        if constexpr (IL) {   // interleaved layout: the lane's columns as they are, rows 2 kk and 2 kk + 1; LL also goes to `ll`
+            if (kk >= k0 && producer) {
+                T o[HV];
+#pragma unroll
+                for (int i = 0; i < HV; i++) o[i] = oL[2 * i];
+                put(ll, p.ll_pitch, kk, o, p.nLx, whole);
+                T *q = (T *)p.il + (int64_t)blockIdx.y * p.il_frame + (int64_t)(2 * kk) * p.il_pitch + xl;
+                if (whole) {
+                    st_vec<T, VPL>(q, oL);
+                    if (kk < p.nHy) st_vec<T, VPL>(q + p.il_pitch, oH);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VPL; i++)
+                        if (xl + i < W) {
+                            q[i] = oL[i];
+                            if (kk < p.nHy) q[p.il_pitch + i] = oH[i];
+                        }
+                }
+            }
+            continue;
+        }
         if (kk >= k0 && producer) {
             T o[HV];
 #pragma unroll
@@ -293,7 +315,7 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
 // A slot holds the four subband row segments one iteration consumes: [LL | HL] of coefficient row 2k and
 // [LH | HH] of row 2k+1, half a staged row each.  Needs 16-byte aligned HL / HH column origins
 // (p.sub_aligned); the host falls back to k_inv_level otherwise.
-template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::THREADS, CFG::NCTA) k_inv_ring(const LevelParams p)
+template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launch_bounds__(CFG::THREADS, CFG::NCTA) k_inv_ring(const LevelParams p)
 {
     using T = typename WV::T;
     static_assert(VPL * sizeof(T) == 32, "a lane holds 32 bytes of an output row");
@@ -338,6 +360,22 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         RingState rs;
         ChainWindow win;
         const bool dep = p.chain.in != nullptr;
+        if constexpr (IL) {   // interleaved layout: coefficient rows 2k and 2k+1 as they lie, a full staged row each
+            const int xs0 = 2 * cs0, x0 = max(xs0, 0);
+            const uint32_t nb = (uint32_t)((int)min((int64_t)xs0 + nact * OUTW + 2 * VPL, p.il_pitch) - x0) * ES;
+            const T *il = (const T *)p.il + (int64_t)blockIdx.y * p.il_frame + x0;
+            const uint32_t d0 = ring0 + (x0 - xs0) * ES;
+            for (int q = 0; q < nitems; q++) {
+                if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
+                const uint32_t d = d0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
+                const int k = ka + q;
+                mbar_expect_tx(fb, 2 * nb);
+                bulk_g2s(d, il + (int64_t)reflect(2 * k, H) * p.il_pitch, nb, fb);
+                bulk_g2s(d + 2 * SEGB, il + (int64_t)reflect(2 * k + 1, H) * p.il_pitch, nb, fb);
+                rs.next();
+            }
+            return;
+        }
         for (int q = 0; q < nitems; q++) {
             if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
             const uint32_t d = dst0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
@@ -367,12 +405,29 @@ template <class WV, int VPL, class CFG> __global__ void __launch_bounds__(CFG::T
         const int hi = nact * (OUTW / 2) + 2 * HV - 1;
 #pragma unroll
         for (int i = 0; i < HV; i++) {
-            cL[i] = min(max((reflect(xl + 2 * i, W) >> 1) - cs0, 0), hi) * ES;
-            cH[i] = min(max((reflect(xl + 2 * i + 1, W) >> 1) - cs0, 0), hi) * ES;
+            if constexpr (IL) {
+                cL[i] = min(max(reflect(xl + 2 * i, W) - 2 * cs0, 0), 2 * hi + 1) * ES;
+                cH[i] = min(max(reflect(xl + 2 * i + 1, W) - 2 * cs0, 0), 2 * hi + 1) * ES;
+            } else {
+                cL[i] = min(max((reflect(xl + 2 * i, W) >> 1) - cs0, 0), hi) * ES;
+                cH[i] = min(max((reflect(xl + 2 * i + 1, W) >> 1) - cs0, 0), hi) * ES;
+            }
         }
     }
     // one interleaved row: even positions from the L segment, odd positions from the H segment
     auto read = [&](uint32_t lo, uint32_t hi, T(&v)[VPL]) {
+        if constexpr (IL) {   // the row is staged interleaved, starting at `lo` (hi unused); cL / cH hold the even / odd columns' offsets
+            if (fast) {
+                lds_vec<T, VPL>(lo + 2 * wofs + lane * 32, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < HV; i++) {
+                    v[2 * i] = lds_one<T>(lo + cL[i]);
+                    v[2 * i + 1] = lds_one<T>(lo + cH[i]);
+                }
+            }
+            return;
+        }
         T l[HV], h[HV];
         if (fast) {
             lds_vec<T, HV>(lo + wofs + lane * 16, l);
@@ -453,6 +508,9 @@ template <class K> static cudaError_t prep(K kern, int smem)
 // cfg: 0 = 7 consumer warps x 2 CTAs per SM, 1 = 15 x 1, 2 = 8 x 2 (96 registers), 3 = 5 x 3 (rows of 9-10 column groups:
 // two bands of 5 keep 15 instead of 10 consumer warps per SM busy)
 constexpr int RING_NCFG = 4;
+// kinds with an interleaved in-place family in the reference: float 9/7 and float 5/3
+template <class WV> constexpr bool ring_il() { return std::is_same<WV, W97F>::value || std::is_same<WV, W53F>::value; }
+bool ring_interleaved_ok(int kind) { return kind == K_CDF97_F32 || kind == K_CDF53_F32; }
 template <class F> static void dispatch_cfg(int cfg, F &&f)
 {
     if (cfg == 1) f(RingCfg<15, 1>{});
@@ -472,6 +530,10 @@ cudaError_t preload_ring()
                     using CFG = decltype(c);
                     if (e == cudaSuccess) e = prep(k_fwd_ring<WV, V, CFG>, CFG::SMEM);
                     if (e == cudaSuccess) e = prep(k_inv_ring<WV, V, CFG>, CFG::SMEM);
+                    if constexpr (ring_il<WV>()) {
+                        if (e == cudaSuccess) e = prep(k_fwd_ring<WV, V, CFG, true>, CFG::SMEM);
+                        if (e == cudaSuccess) e = prep(k_inv_ring<WV, V, CFG, true>, CFG::SMEM);
+                    }
                 });
         });
     return e;
@@ -486,6 +548,12 @@ void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         dispatch_cfg(cfg, [&](auto c) {
             using CFG = decltype(c);
             const dim3 grid(p.nbands * p.nstrips, frames);
+            if constexpr (ring_il<WV>()) {
+                if (p.il) {
+                    launch_pdl(k_fwd_ring<WV, V, CFG, true>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
+                    return;
+                }
+            }
             launch_pdl(k_fwd_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
         });
     });
@@ -499,6 +567,12 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         dispatch_cfg(cfg, [&](auto c) {
             using CFG = decltype(c);
             const dim3 grid(p.nbands * p.nstrips, frames);
+            if constexpr (ring_il<WV>()) {
+                if (p.il) {
+                    launch_pdl(k_inv_ring<WV, V, CFG, true>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
+                    return;
+                }
+            }
             launch_pdl(k_inv_ring<WV, V, CFG>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
         });
     });
