@@ -22,7 +22,7 @@
 
 namespace dwtb200 {
 
-constexpr int IP_THREADS = 256;
+constexpr int IP_THREADS = 512;
 constexpr int IP_HALO = 4;   // lifting depth: four steps per axis, whatever the order of the sweeps
 
 enum { IP_X = 0, IP_P = 1, IP_C = 2, IP_E = 3 };
@@ -166,9 +166,43 @@ struct IpRects {
     int x0[2], y0[2], x1[2], y1[2], tw[2], th[2], ntx[2], nt[2];
 };
 
+// One sample per thread: the window (tile + halo) holds at most IP_THREADS samples, every thread keeps its sample's
+// position codes in registers and the 8 x 5 rounds are straight-line code -- the kernel is latency-bound (a few hundred
+// samples per CTA), so what counts is instructions per round, not throughput.
+template <bool INV, bool ALONG_X>
+__device__ __forceinline__ void ip_round1(float *q, bool live, uint32_t codes, int i, int t, int tn, int d, int N, int part)
+{
+#pragma unroll
+    for (int step = 0; step < 5; step++) {
+        const bool scale = INV ? step == 0 : step == 4;
+        if (live && ((codes >> (3 * step)) & 7u) == (uint32_t)part) {
+            if (scale) {
+                *q = __fmul_rn(*q, ((i & 1) != INV) ? W97F::IZ : W97F::Z);
+            } else {
+                const float c = ip_coef<INV>(INV ? step - 1 : step);
+                bool ok = true;
+                float l, r;
+                if (i == 0) {
+                    ok = t + 1 < tn;
+                    l = r = ok ? q[d] : 0.f;
+                } else if (i == N - 1) {
+                    ok = t >= 1;
+                    l = r = ok ? q[-d] : 0.f;
+                } else {
+                    ok = t >= 1 && t + 1 < tn;   // neighbour outside the staged window: this sample is halo, its value is not used
+                    l = ok ? q[-d] : 0.f;
+                    r = ok ? q[d] : 0.f;
+                }
+                if (ok) *q = __fadd_rn(*q, __fmul_rn(c, __fadd_rn(l, r)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(const LevelParams p, const IpRects rc)
 {
-    extern __shared__ float sm[];
+    __shared__ float sm[IP_THREADS];
     const int frame = blockIdx.z;
     const int nx = p.W, ny = p.H;
     int b = blockIdx.x, r = 0;
@@ -180,12 +214,11 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
     const int ox0 = rc.x0[r] + (b % rc.ntx[r]) * tw, oy0 = rc.y0[r] + (b / rc.ntx[r]) * th;
     const int ox1 = min(ox0 + tw, rc.x1[r]), oy1 = min(oy0 + th, rc.y1[r]);
     const int lx0 = max(ox0 - IP_HALO, 0), lx1 = min(ox1 + IP_HALO, nx), ly0 = max(oy0 - IP_HALO, 0), ly1 = min(oy1 + IP_HALO, ny);
-    const int w = lx1 - lx0, h = ly1 - ly0, pitch = tw + 2 * IP_HALO + 1, n = w * h;
-    const float *ll = (const float *)p.ll + (size_t)frame * p.ll_frame;
-    const float *hl = (const float *)p.hl + (size_t)frame * p.sub_frame, *lh = (const float *)p.lh + (size_t)frame * p.sub_frame,
-                *hh = (const float *)p.hh + (size_t)frame * p.sub_frame;
-    for (int e = threadIdx.x; e < n; e += IP_THREADS) {
-        const int ty = e / w, tx = e - ty * w, gy = ly0 + ty, gx = lx0 + tx;
+    const int w = lx1 - lx0, h = ly1 - ly0;
+    const int e = threadIdx.x, ty = e / w, tx = e - ty * w, gy = ly0 + ty, gx = lx0 + tx;
+    const bool live = e < w * h;
+    float *q = sm + e;   // the window is stored densely: pitch w
+    if (live) {
         float v;
         if (!INV) {
             v = ((const float *)p.src)[(size_t)frame * p.src_frame + (size_t)gy * p.src_pitch + gx];
@@ -193,18 +226,23 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
             v = ((const float *)p.il)[(size_t)frame * p.il_frame + (size_t)gy * p.il_pitch + gx];
         } else {
             const int by = gy >> 1, bx = gx >> 1;
-            if (gy & 1) v = (gx & 1) ? hh[(size_t)by * p.sub_pitch + bx] : lh[(size_t)by * p.sub_pitch + bx];
-            else v = (gx & 1) ? hl[(size_t)by * p.sub_pitch + bx] : ll[(size_t)by * p.ll_pitch + bx];
+            const float *bp = (gy & 1) ? ((gx & 1) ? (const float *)p.hh : (const float *)p.lh) : ((gx & 1) ? (const float *)p.hl : nullptr);
+            if (bp) v = bp[(size_t)frame * p.sub_frame + (size_t)by * p.sub_pitch + bx];
+            else v = ((const float *)p.ll)[(size_t)frame * p.ll_frame + (size_t)by * p.ll_pitch + bx];
         }
-        sm[ty * pitch + tx] = v;
+        *q = v;
     }
+    const uint32_t cx = live ? ip_codes<INV>(nx, gx) : 0x7fffu, cy = live ? ip_codes<INV>(ny, gy) : 0x7fffu;
     __syncthreads();
-    uint32_t *tabx = (uint32_t *)(sm + pitch * (th + 2 * IP_HALO)), *taby = tabx + (tw + 2 * IP_HALO);
-    ip_level_sweeps<INV>(sm, tabx, taby, pitch, 1, w, h, lx0, ly0, nx, ny);
-    const int ow = ox1 - ox0, oh = oy1 - oy0;
-    for (int e = threadIdx.x; e < ow * oh; e += IP_THREADS) {
-        const int ty = e / ow, tx = e - ty * ow, gy = oy0 + ty, gx = ox0 + tx;
-        const float v = sm[(gy - ly0) * pitch + (gx - lx0)];
+    for (int part = IP_X; part <= IP_E; part++) {
+        int a0, a1;
+        ip_part_range<INV>(nx, part, a0, a1);
+        if (nx > 1 && max(a0, lx0) < min(a1, lx1)) ip_round1<INV, true>(q, live, cx, gx, tx, w, 1, nx, part);   // block-uniform tests
+        ip_part_range<INV>(ny, part, a0, a1);
+        if (ny > 1 && max(a0, ly0) < min(a1, ly1)) ip_round1<INV, false>(q, live, cy, gy, ty, h, w, ny, part);
+    }
+    if (live && gx >= ox0 && gx < ox1 && gy >= oy0 && gy < oy1) {
+        const float v = *q;
         if (INV) {
             ((float *)p.dst)[(size_t)frame * p.dst_frame + (size_t)gy * p.dst_pitch + gx] = v;
         } else if (p.il) {
@@ -221,22 +259,20 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
     }
 }
 
-static void ip_add_rect(IpRects &rc, int x0, int y0, int x1, int y1, size_t &smem)
+static void ip_add_rect(IpRects &rc, int x0, int y0, int x1, int y1)
 {
     if (x1 <= x0 || y1 <= y0) return;
     const int rw = x1 - x0, rh = y1 - y0, i = rc.n++;
-    int tw, th;   // (tw + 9) * (th + 8) floats of shared memory: at most ~20 KB
-    if (rh <= 16) { tw = 64; th = rh; }           // the top frame: a few full-width rows
-    else if (rw <= 16) { tw = rw; th = 64; }      // the right frame
-    else { tw = 56; th = 56; }                    // a whole level
+    int tw, th;   // (tw + 8) * (th + 8) <= IP_THREADS samples
+    if (rh <= 8) { th = rh; tw = IP_THREADS / (rh + 2 * IP_HALO) - 2 * IP_HALO; }        // the top frame: a few full-width rows
+    else if (rw <= 8) { tw = rw; th = IP_THREADS / (rw + 2 * IP_HALO) - 2 * IP_HALO; }   // the right frame
+    else { tw = 14; th = 14; }                                                            // a whole level
     if (tw > rw) tw = rw;
     if (th > rh) th = rh;
     rc.x0[i] = x0; rc.y0[i] = y0; rc.x1[i] = x1; rc.y1[i] = y1;
     rc.tw[i] = tw; rc.th[i] = th;
     rc.ntx[i] = (rw + tw - 1) / tw;
     rc.nt[i] = rc.ntx[i] * ((rh + th - 1) / th);
-    const size_t need = ((size_t)(tw + 2 * IP_HALO + 1) * (th + 2 * IP_HALO) + (tw + 2 * IP_HALO) + (th + 2 * IP_HALO)) * sizeof(float);
-    if (need > smem) smem = need;
 }
 // rectangle [rx0, rx1) x [ry0, ry1) of a level, and optionally a second one, in one launch
 void launch_ip_phase(bool inverse, const LevelParams &p, int frames, int rx0, int ry0, int rx1, int ry1, int sx0, int sy0, int sx1, int sy1,
@@ -244,20 +280,19 @@ void launch_ip_phase(bool inverse, const LevelParams &p, int frames, int rx0, in
 {
     IpRects rc;
     memset(&rc, 0, sizeof rc);
-    size_t smem = 0;
-    ip_add_rect(rc, rx0, ry0, rx1, ry1, smem);
-    ip_add_rect(rc, sx0, sy0, sx1, sy1, smem);
+    ip_add_rect(rc, rx0, ry0, rx1, ry1);
+    ip_add_rect(rc, sx0, sy0, sx1, sy1);
     if (!rc.n) return;
     const dim3 grid(rc.nt[0] + rc.nt[1], 1, frames);
-    if (inverse) k_ip_phase<true><<<grid, IP_THREADS, smem, st>>>(p, rc);
-    else k_ip_phase<false><<<grid, IP_THREADS, smem, st>>>(p, rc);
+    if (inverse) k_ip_phase<true><<<grid, IP_THREADS, 0, st>>>(p, rc);
+    else k_ip_phase<false><<<grid, IP_THREADS, 0, st>>>(p, rc);
 }
 
 // ---- all remaining small levels in one launch: one CTA per frame, truly in place in shared memory ------------------
 // `buf` holds LL_{j0-1} (w0 x h0, dense) on entry of the forward kernel and the interleaved pyramid of the levels j0 .. J-1
 // on exit (level j at stride 2^(j - j0)); the inverse kernel goes the other way.
-constexpr int IP_TAIL_THREADS = 512;
-constexpr int IP_TAIL_CAP = 9216;   // samples (96 x 96): 36 KB + pitch padding of shared memory
+constexpr int IP_TAIL_THREADS = 1024;
+constexpr int IP_TAIL_CAP = 4096;   // samples (64 x 64)
 template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail(float *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev)
 {
     extern __shared__ float sm[];
