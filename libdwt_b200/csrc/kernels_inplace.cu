@@ -292,35 +292,43 @@ void launch_ip_phase(bool inverse, const LevelParams &p, int frames, int rx0, in
 // `buf` holds LL_{j0-1} (w0 x h0, dense) on entry of the forward kernel and the interleaved pyramid of the levels j0 .. J-1
 // on exit (level j at stride 2^(j - j0)); the inverse kernel goes the other way.
 constexpr int IP_TAIL_THREADS = 1024;
-constexpr int IP_TAIL_CAP = 4096;   // samples (64 x 64)
+constexpr int IP_TAIL_CAP = IP_TAIL_THREADS;   // samples of the tail's first level (32 x 32): one per thread
 template <bool INV> __global__ void __launch_bounds__(IP_TAIL_THREADS) k_ip_tail(float *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev)
 {
-    extern __shared__ float sm[];
+    __shared__ float sm[2 * IP_TAIL_CAP];   // (w0 | 1) * h0 <= 2 * w0 * h0
     float *g = buf + (size_t)blockIdx.x * frame;
+    const int e = threadIdx.x;
     const int sp = w0 | 1;   // odd pitch
-    uint32_t *tabx = (uint32_t *)(sm + sp * h0);
-    for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
+    {
         const int y = e / w0, x = e - y * w0;
-        sm[y * sp + x] = g[(size_t)y * pitch + x];
+        if (e < w0 * h0) sm[y * sp + x] = g[(size_t)y * pitch + x];
     }
     __syncthreads();
-    for (int q = 0; q < nlev; q++) {
-        const int k = INV ? nlev - 1 - q : q;
-        const int w = cdiv_pow2(w0, k), h = cdiv_pow2(h0, k);
-        ip_level_sweeps<INV>(sm, tabx, tabx + w0, sp << k, 1 << k, w, h, 0, 0, w, h);
-        __syncthreads();
+    for (int qq = 0; qq < nlev; qq++) {
+        const int k = INV ? nlev - 1 - qq : qq;
+        const int w = cdiv_pow2(w0, k), h = cdiv_pow2(h0, k);   // this level's samples sit at stride 2^k
+        const int y = e / w, x = e - y * w;
+        const bool live = e < w * h;
+        float *q = sm + (y << k) * sp + (x << k);
+        const uint32_t cx = live ? ip_codes<INV>(w, x) : 0x7fffu, cy = live ? ip_codes<INV>(h, y) : 0x7fffu;
+        for (int part = IP_X; part <= IP_E; part++) {
+            int a0, a1;
+            ip_part_range<INV>(w, part, a0, a1);
+            if (w > 1 && a0 < a1) ip_round1<INV, true>(q, live, cx, x, x, w, 1 << k, w, part);
+            ip_part_range<INV>(h, part, a0, a1);
+            if (h > 1 && a0 < a1) ip_round1<INV, false>(q, live, cy, y, y, h, sp << k, h, part);
+        }
     }
-    for (int e = threadIdx.x; e < w0 * h0; e += IP_TAIL_THREADS) {
+    {
         const int y = e / w0, x = e - y * w0;
-        g[(size_t)y * pitch + x] = sm[y * sp + x];
+        if (e < w0 * h0) g[(size_t)y * pitch + x] = sm[y * sp + x];
     }
 }
 int ip_tail_cap() { return IP_TAIL_CAP; }
 void launch_ip_tail(bool inverse, void *buf, int64_t pitch, int64_t frame, int w0, int h0, int nlev, int frames, cudaStream_t st)
 {
-    const size_t smem = ((size_t)(w0 | 1) * h0 + w0 + h0) * sizeof(float);
-    if (inverse) k_ip_tail<true><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
-    else k_ip_tail<false><<<frames, IP_TAIL_THREADS, smem, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
+    if (inverse) k_ip_tail<true><<<frames, IP_TAIL_THREADS, 0, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
+    else k_ip_tail<false><<<frames, IP_TAIL_THREADS, 0, st>>>((float *)buf, pitch, frame, w0, h0, nlev);
 }
 
 // ---- layout translation: Mallat pyramid of J levels <-> interleaved (4-byte elements) ------------------------------
