@@ -1298,6 +1298,112 @@ int ip_run97(dwtb200_image *im, bool inverse, int J, int &flips)
     return 0;
 }
 
+// CDF 5/3 float of the family is the Mallat transform bit for bit; with level 0 on the ring kernels it takes the same
+// route as above without the frame kernels: interleaved level 0, the other levels in a Mallat scratch plane (streaming / tile
+// kernels and the Mallat tail kernel), translation of the even rows and columns only.  false: this route does not apply.
+bool ip_53_fast(const dwtb200_image *im, bool inverse, int J, DensePlan &pl)
+{
+    if (g.force_generic || std::min(im->ox, im->oy) < IP_STD_MIN || (int64_t)im->ox * im->oy * im->frames <= g.tile_max) return false;
+    LevelParams lp;
+    level_geometry(im, 0, inverse, lp);
+    if (lp.narrow || !(g.ring & (inverse ? 2 : 1)) || !ring_interleaved_ok(im->kind)) return false;
+    pl = dense_plan(im, J);
+    if (pl.jt < 1 || pl.jm < pl.jt) return false;   // degenerate pyramid, or the persistent mid-level launch is switched on
+    for (int j = 0; j < pl.jt; j++)
+        if (pl.pyr_len[j]) return false;
+    return true;
+}
+int ip_run53(dwtb200_image *im, bool inverse, int J, const DensePlan &pl)
+{
+    char *A = (char *)im->plane[im->cur], *B = (char *)im->plane[im->cur ^ 1];
+    const int jt = pl.jt;
+    std::vector<Launch> ls;
+    auto level = [&](LevelParams &lp, int j) {
+        ls.emplace_back();
+        ls.back().lp = lp;
+        plan_level(im, ls.back(), inverse, j == 0 ? PLAN_STREAM : pl.type[j]);
+    };
+    auto run = [&]() {
+        for (Launch &l : ls) memset(l.chain(), 0, sizeof(Chain));
+        const int r = issue(im, ls);
+        ls.clear();
+        return r;
+    };
+    LevelParams lp;
+    TailParams t;
+    memset(&t, 0, sizeof t);
+    t.W0 = im->ox;
+    t.H0 = im->oy;
+    t.j0 = jt;
+    t.j1 = J;
+    if (!inverse) {
+        Band in = {A, im->pitch, im->frame};
+        for (int j = 0; j < jt; j++) {
+            Band out = fwd_level_params(im, j, J, in, j == 0 ? B : A, lp);
+            if (j == 0) {
+                lp.il = B;
+                lp.il_pitch = im->pitch;
+                lp.il_frame = im->frame;
+                out = ll_band(im, 0);
+                lp.ll = out.p;
+                lp.ll_pitch = out.pitch;
+                lp.ll_frame = out.frame;
+            }
+            level(lp, j);
+            in = out;
+        }
+        if (jt < J) {
+            ls.emplace_back();
+            ls.back().type = Launch::TAIL_F;
+            t.src = in.p;
+            t.src_pitch = in.pitch;
+            t.src_frame = in.frame;
+            t.dst = A;
+            t.dst_pitch = im->pitch;
+            t.dst_frame = im->frame;
+            ls.back().tp = t;
+        }
+        const int r = run();
+        if (r) return r;
+        if (J > 1) launch_ip_pack(false, A, B, im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 1, im->frames, g.st);
+    } else {
+        if (J > 1) launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 1, im->frames, g.st);
+        if (jt < J) {
+            const Band out = ll_band(im, jt - 1);
+            ls.emplace_back();
+            ls.back().type = Launch::TAIL_I;
+            t.src = B;
+            t.src_pitch = im->pitch;
+            t.src_frame = im->frame;
+            t.dst = out.p;
+            t.dst_pitch = out.pitch;
+            t.dst_frame = out.frame;
+            ls.back().tp = t;
+        }
+        for (int j = jt - 1; j >= 1; j--) {
+            inv_level_params(im, j, J, B, B, lp);
+            level(lp, j);
+        }
+        int r = run();
+        if (r) return r;
+        inv_level_params(im, 0, J, B, B, lp);
+        if (J > 1) {
+            const Band l0 = ll_band(im, 0);
+            launch_ip_scatter(l0.p, l0.pitch, l0.frame, A, im->pitch, im->frame, lp.nLx, lp.nLy, im->frames, g.st);
+            g.launches++;
+        }
+        lp.il = A;
+        lp.il_pitch = im->pitch;
+        lp.il_frame = im->frame;
+        lp.sub_aligned = 1;
+        level(lp, 0);
+        r = run();
+        if (r) return r;
+    }
+    g.launches++;
+    return 0;
+}
+
 // J levels of the family on the whole image (J as given: the host entry points clamp it against the caller's OUTER size)
 int inplace_transform(dwtb200_image *im, bool inverse, int J)
 {
@@ -1305,7 +1411,9 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
         return fail(DWTB200_EINVAL, "in-place family: CDF 9/7 float and CDF 5/3 float only (kind %d)", im->kind);
     im->last_launches = 0;
     if (J <= 0) return DWTB200_OK;
-    if (im->kind == DWTB200_CDF53_F32) {   // bit-identical to the Mallat transform, only laid out differently (:16583); a lone sample is scaled
+    DensePlan pl53;
+    const bool is53 = im->kind == DWTB200_CDF53_F32;
+    if (is53 && !ip_53_fast(im, inverse, J, pl53)) {   // the Mallat transform and a translation of the whole plane (:16583; a lone sample is scaled)
         int r = 0;
         if (inverse) {
             launch_ip_pack(true, im->plane[im->cur], im->plane[im->cur ^ 1], im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 0, im->frames, g.st);
@@ -1322,15 +1430,22 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
         return r;
     }
     const int jcap = dwtb200_ceil_log2(std::max(im->ox, im->oy));   // beyond it every line has one sample: 9/7 touches nothing (:12975)
-    if (J > jcap) J = jcap;
+    if (!is53 && J > jcap) J = jcap;
     if (J <= 0) return DWTB200_OK;
+    auto body = [&](int &flips) {
+        if (is53) {
+            flips = 1;
+            return ip_run53(im, inverse, J, pl53);
+        }
+        return ip_run97(im, inverse, J, flips);
+    };
     const dwtb200_image::Key key(inverse, im->ox, im->oy, J, 0x100, im->cur, g.force_generic, g.strip_rows, g.epoch);
     auto it = g.use_graph ? im->graphs.find(key) : im->graphs.end();
     if (it == im->graphs.end()) {
         g.launches = 0;
         if (!g.use_graph) {
             int flips = 0;
-            const int r = ip_run97(im, inverse, J, flips);
+            const int r = body(flips);
             if (r) return r;
             CK(cudaGetLastError());
             im->last_launches = g.launches;
@@ -1340,7 +1455,7 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(g.st, cudaStreamCaptureModeThreadLocal));
         int flips = 0;
-        const int rr = ip_run97(im, inverse, J, flips);
+        const int rr = body(flips);
         const cudaError_t le = cudaGetLastError(), ce = cudaStreamEndCapture(g.st, &graph);
         if (rr || le != cudaSuccess || ce != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);

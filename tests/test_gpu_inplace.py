@@ -145,7 +145,8 @@ def test_inplace_device_resident_batch(dev, oracle, wavelet):
     report(fails)
 
 
-def test_inplace_interleaved_level0_path(dev, oracle):
+@pytest.mark.parametrize("wavelet", ["97", "53"])
+def test_inplace_interleaved_level0_path(dev, oracle, wavelet):
     """images whose level 0 runs on the bulk-copy ring kernels: those read / write the interleaved layout directly
     (LevelParams::il), only the even rows and columns are translated; odd sizes, one / two / all levels, a batch, and the same
     shapes with that path switched off (DWTB200_TUNE_RING = 0: register kernels + full translation) must give the same bits"""
@@ -158,25 +159,25 @@ def test_inplace_interleaved_level0_path(dev, oracle):
             for (oy, ox) in ((1301, 2101), (2047, 1031), (1500, 1501), (1056, 1000), (40, 30000)):
                 for j in (1, 2, -1):
                     a = (rng.standard_normal((oy, ox)) * 10.0 ** rng.integers(-2, 3, size=(oy, ox))).astype(np.float32)
-                    fails += both(dev, oracle, "97", a, j, 0, tag=f"ring={ring}")
+                    fails += both(dev, oracle, wavelet, a, j, 0, tag=f"ring={ring}")
         finally:
             L.check(L.c.dwtb200_set_tuning(6, 3))
     ox, oy, frames = 1100, 1000, 3
-    img = dev.DeviceImage(dev.kind_of("97", "s"), ox, oy, frames)
+    img = dev.DeviceImage(dev.kind_of(wavelet, "s"), ox, oy, frames)
     for rep in range(2):
         img.fill(0, 0, 6)
         J = img.fwd2_inplace()
         for k in range(frames):
             want = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=k % 6)
-            oracle.fwd2_inplace(want, "97")
+            oracle.fwd2_inplace(want, wavelet)
             got = img.download(frame=k)
             if not (bits(got, "s") == bits(want, "s")).all():
                 fails.append(f"batch rep {rep} frame {k} forward: " + describe_mismatch(got, want, "s"))
         img.inv2_inplace(J)
         for k in range(frames):
             want = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=k % 6)
-            oracle.fwd2_inplace(want, "97")
-            oracle.inv2_inplace(want, "97", j_max=J)
+            oracle.fwd2_inplace(want, wavelet)
+            oracle.inv2_inplace(want, wavelet, j_max=J)
             got = img.download(frame=k)
             if not (bits(got, "s") == bits(want, "s")).all():
                 fails.append(f"batch rep {rep} frame {k} inverse: " + describe_mismatch(got, want, "s"))
