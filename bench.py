@@ -271,6 +271,37 @@ def run_ours(args):
         for im in singles:
             im.close()
 
+    # ---- the interleaved in-place family (dwt_cdf97_2f_inplace_s / dwt_cdf53_2f_inplace_s) on the same
+    # shape: one image at a time and the batch of M, same byte accounting (the layout translation is overhead, not algorithmic bytes)
+    inplace = {}
+    if rank == 0 and world == 1:
+        for wname, kind in (("97s", d.CDF97_F32), ("53s", d.CDF53_F32)):
+            for frames in (1, M):
+                ims = [d.DeviceImage(kind, W, H, frames) for _ in range(3 if frames == 1 else 1)]
+                for im in ims:
+                    im.fill(0, 0, 6)
+                    jj = im.fwd2_inplace(); im.inv2_inplace(jj)
+                L.check(L.c.dwtb200_sync())
+                tf = ti = 0.0
+                reps = 5
+                for _ in range(reps):
+                    for im in ims:
+                        L.check(L.c.dwtb200_timer_start())
+                        im.fwd2_inplace()
+                        tf += L.c.dwtb200_timer_stop_ms()
+                    for im in ims:
+                        L.check(L.c.dwtb200_timer_start())
+                        im.inv2_inplace(jj)
+                        ti += L.c.dwtb200_timer_stop_ms()
+                for direction, t in (("fwd", tf), ("inv", ti)):
+                    t = t / (reps * len(ims)) * 1e-3
+                    b = algorithmic_bytes(W, H, jj, 4) * frames
+                    inplace[f"{wname}_{direction}_{'single' if frames == 1 else 'batch%d' % frames}"] = {
+                        "us_per_image": t / frames * 1e6, "gpixel_s": PIX * frames / t / 1e9, "roofline_frac": b / t / 1e9 / peak,
+                        "launches": ims[0].last_launches}
+                for im in ims:
+                    im.close()
+
     # ---- one image far larger than L2 and than the launch overheads: BASELINE config 5a on a single GPU ----
     large = None
     if rank == 0 and world == 1 and not args.no_large:
@@ -384,7 +415,7 @@ def run_ours(args):
                        "l2": "each batch is M x 256 MiB per plane (>> 126 MB L2): inputs larger than L2",
                        "sharding": "independent frames per GPU, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
-            "breakdown": breakdown, "large_image": large,
+            "breakdown": breakdown, "inplace_family": inplace, "large_image": large,
         }
         print(json.dumps(line))
     if world > 1:
