@@ -1250,7 +1250,7 @@ int ip_run97(dwtb200_image *im, bool inverse, int J, int &flips)
     // translated only at its even rows and columns, where the deeper levels live.
     level_geometry(im, 0, inverse, lp);
     const bool il0 = std::min(im->ox, im->oy) >= IP_STD_MIN && (int64_t)im->ox * im->oy * im->frames > g.tile_max && !lp.narrow &&
-                     (g.ring & (inverse ? 2 : 1)) && ring_interleaved_ok(im->kind) && !g.force_generic;
+                     (g.ring & (inverse ? 2 : 1)) && ring_interleaved_ok(im->kind) && ring_interleaved_cfg_ok(lp.cfg) && !g.force_generic;
     char *M = il0 ? A : B;   // Mallat scratch of the levels the translation kernels handle (forward: level 0 has been read by then)
     const int shift = il0 ? 1 : 0;
     void *tailp = tail ? tb.p : nullptr;
@@ -1274,16 +1274,17 @@ int ip_run97(dwtb200_image *im, bool inverse, int J, int &flips)
         if (tail) launch_ip_tail(false, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
         if (!il0 || J > 1) launch_ip_pack(false, M, il0 ? B : A, im->pitch, im->frame, im->ox, im->oy, J, tailp, tb.pitch, tb.frame, jt, shift, im->frames, g.st);
     } else {
-        if (!il0 || J > 1) launch_ip_pack(true, A, il0 ? B : B, im->pitch, im->frame, im->ox, im->oy, J, tailp, tb.pitch, tb.frame, jt, shift, im->frames, g.st);
+        // (J == 1 on the interleaved route: LL_1 goes to the dense band of LL_0, not to the plane the level writes its output to)
+        const Band l0 = ll_band(im, 0);
+        if (il0 && J == 1) launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, l0.p, l0.pitch, l0.frame, 1, shift, im->frames, g.st);
+        else launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, tailp, tb.pitch, tb.frame, jt, shift, im->frames, g.st);
         if (tail) launch_ip_tail(true, tb.p, tb.pitch, tb.frame, tw, th, J - jt, im->frames, g.st);
         for (int j = jt - 1; j >= 0; j--) {
             inv_level_params(im, j, J, B, il0 ? B : A, lp);
-            if (il0 && j == 0) {
-                if (J > 1) {   // LL_0 joins the level-0 subbands in the interleaved plane
-                    const Band l0 = ll_band(im, 0);
-                    launch_ip_scatter(l0.p, l0.pitch, l0.frame, A, im->pitch, im->frame, lp.nLx, lp.nLy, im->frames, g.st);
-                    g.launches++;
-                }
+            if (il0 && j == 0) {   // HL, LH, HH from the interleaved plane, LL_0 from its dense band
+                lp.ll = l0.p;
+                lp.ll_pitch = l0.pitch;
+                lp.ll_frame = l0.frame;
                 lp.il = A;
                 lp.il_pitch = im->pitch;
                 lp.il_frame = im->frame;
@@ -1306,7 +1307,7 @@ bool ip_53_fast(const dwtb200_image *im, bool inverse, int J, DensePlan &pl)
     if (g.force_generic || std::min(im->ox, im->oy) < IP_STD_MIN || (int64_t)im->ox * im->oy * im->frames <= g.tile_max) return false;
     LevelParams lp;
     level_geometry(im, 0, inverse, lp);
-    if (lp.narrow || !(g.ring & (inverse ? 2 : 1)) || !ring_interleaved_ok(im->kind)) return false;
+    if (lp.narrow || !(g.ring & (inverse ? 2 : 1)) || !ring_interleaved_ok(im->kind) || !ring_interleaved_cfg_ok(lp.cfg)) return false;
     pl = dense_plan(im, J);
     if (pl.jt < 1 || pl.jm < pl.jt) return false;   // degenerate pyramid, or the persistent mid-level launch is switched on
     for (int j = 0; j < pl.jt; j++)
@@ -1367,7 +1368,8 @@ int ip_run53(dwtb200_image *im, bool inverse, int J, const DensePlan &pl)
         if (r) return r;
         if (J > 1) launch_ip_pack(false, A, B, im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 1, im->frames, g.st);
     } else {
-        if (J > 1) launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, nullptr, 0, 0, 0, 1, im->frames, g.st);
+        const Band l0 = ll_band(im, 0);   // J == 1: LL_1 goes straight to the dense band the level reads, not into the plane it writes
+        launch_ip_pack(true, A, B, im->pitch, im->frame, im->ox, im->oy, J, J == 1 ? l0.p : nullptr, l0.pitch, l0.frame, 1, 1, im->frames, g.st);
         if (jt < J) {
             const Band out = ll_band(im, jt - 1);
             ls.emplace_back();
@@ -1387,12 +1389,10 @@ int ip_run53(dwtb200_image *im, bool inverse, int J, const DensePlan &pl)
         int r = run();
         if (r) return r;
         inv_level_params(im, 0, J, B, B, lp);
-        if (J > 1) {
-            const Band l0 = ll_band(im, 0);
-            launch_ip_scatter(l0.p, l0.pitch, l0.frame, A, im->pitch, im->frame, lp.nLx, lp.nLy, im->frames, g.st);
-            g.launches++;
-        }
-        lp.il = A;
+        lp.ll = l0.p;
+        lp.ll_pitch = l0.pitch;
+        lp.ll_frame = l0.frame;
+        lp.il = A;   // HL, LH, HH from the interleaved plane, LL_0 from its dense band
         lp.il_pitch = im->pitch;
         lp.il_frame = im->frame;
         lp.sub_aligned = 1;

@@ -57,7 +57,7 @@ struct LevelParams {
     int dbg;              // measurement only: 1 = no stores, 2 = no lifting arithmetic (forward streaming kernel)
     int narrow;           // 1: 16 bytes per lane instead of 32 (half the registers, twice the warps per SM)
     // interleaved layout (in-place family, ring kernels only): forward writes its four subbands as rows 2k / 2k+1 of `il` (even
-    // = L, odd = H in both directions) and LL additionally to `ll`; inverse reads all four subbands from `il`
+    // = L, odd = H in both directions) and LL additionally to `ll`; inverse reads HL, LH, HH from `il` and LL from `ll`
     void *il;
     int64_t il_pitch, il_frame;
 };
@@ -67,7 +67,8 @@ void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t s
 cudaError_t preload_ring();
 void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
 void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
-bool ring_interleaved_ok(int kind);   // p.il != nullptr is supported for this kind
+bool ring_interleaved_ok(int kind);   // p.il != nullptr is supported for this kind ...
+bool ring_interleaved_cfg_ok(int cfg);   // ... and this CTA shape
 int ring_warps_per_sm(int cfg);
 int ring_cta_warps(int cfg);
 int ring_ctas_per_sm(int cfg);
@@ -130,9 +131,6 @@ void launch_ip_tail(bool inverse, void *buf, int64_t pitch, int64_t frame, int w
 // (shift = 1: only the samples at even rows and columns, level 0 being interleaved already)
 void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int64_t frame, int ox, int oy, int J, void *tail, int64_t tpitch,
                     int64_t tframe, int jt, int shift, int frames, cudaStream_t st);
-// dense band (w x h) -> samples (2y, 2x) of an interleaved plane
-void launch_ip_scatter(const void *src, int64_t spitch, int64_t sframe, void *dst, int64_t dpitch, int64_t dframe, int w, int h, int frames,
-                       cudaStream_t st);
 
 // ---- generic pass kernels: exact reference semantics for sparse (outer != inner) layouts ------
 struct PassParams {

@@ -222,7 +222,7 @@ template <bool INV> __global__ void __launch_bounds__(IP_THREADS) k_ip_phase(con
         float v;
         if (!INV) {
             v = ((const float *)p.src)[(size_t)frame * p.src_frame + (size_t)gy * p.src_pitch + gx];
-        } else if (p.il) {   // interleaved source (level 0 of the ring path): all four subbands lie where they belong
+        } else if (p.il && ((gy | gx) & 1)) {   // interleaved source (level 0 of the ring path): HL, LH, HH lie where they belong
             v = ((const float *)p.il)[(size_t)frame * p.il_frame + (size_t)gy * p.il_pitch + gx];
         } else {
             const int by = gy >> 1, bx = gx >> 1;
@@ -385,23 +385,6 @@ void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int6
     else k_ip_pack<false><<<grid, 256, 0, st>>>(p);
 }
 
-// dense band -> the samples at even rows and even columns of an interleaved plane (LL_0 on its way into the level-0 inverse)
-__global__ void __launch_bounds__(256) k_ip_scatter(const uint32_t *src, int64_t spitch, int64_t sframe, uint32_t *dst, int64_t dpitch, int64_t dframe,
-                                                   int w, int h)
-{
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    if (x >= w) return;
-    src += (size_t)blockIdx.z * sframe;
-    dst += (size_t)blockIdx.z * dframe;
-    for (int y = blockIdx.y; y < h; y += gridDim.y) dst[(size_t)(2 * y) * dpitch + 2 * x] = src[(size_t)y * spitch + x];
-}
-void launch_ip_scatter(const void *src, int64_t spitch, int64_t sframe, void *dst, int64_t dpitch, int64_t dframe, int w, int h, int frames,
-                       cudaStream_t st)
-{
-    const dim3 grid((w + 255) / 256, h < 32768 ? h : 32768, frames);
-    k_ip_scatter<<<grid, 256, 0, st>>>((const uint32_t *)src, spitch, sframe, (uint32_t *)dst, dpitch, dframe, w, h);
-}
-
 cudaError_t preload_inplace()
 {
     cudaFuncAttributes a;
@@ -409,7 +392,6 @@ cudaError_t preload_inplace()
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_phase<true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_pack<true>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_scatter);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_ip_tail<true>);
     return e;

@@ -38,6 +38,11 @@ template <int CW_, int NCTA_> struct RingCfg {
     static constexpr int SLOTB = 2 * ROWB;               // a row pair (inverse: four half-width subband segments)
     static constexpr int DATA = (RING_SLOTS * SLOTB + 127) / 128 * 128;
     static constexpr int SMEM = DATA + 2 * RING_SLOTS * 8;
+    // inverse level reading the interleaved layout: five segments per slot (LL of row 2k from its dense band, the interleaved
+    // rows 2k and 2k+1 at full width)
+    static constexpr int SLOTB_IL = 5 * (SLOTB / 4);
+    static constexpr int DATA_IL = (RING_SLOTS * SLOTB_IL + 127) / 128 * 128;
+    static constexpr int SMEM_IL = DATA_IL + 2 * RING_SLOTS * 8;
 };
 
 // ---- mbarrier / bulk-copy primitives -------------------------------------------------------------------
@@ -320,10 +325,11 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
     using T = typename WV::T;
     static_assert(VPL * sizeof(T) == 32, "a lane holds 32 bytes of an output row");
     constexpr int OUTW = 30 * VPL, HV = VPL / 2, ES = (int)sizeof(T), SEGB = CFG::SLOTB / 4;
+    constexpr int SLOTB = IL ? CFG::SLOTB_IL : CFG::SLOTB, DATA = IL ? CFG::DATA_IL : CFG::DATA;
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ring0 = smem_u32(ring_smem);
-    const uint32_t full = ring0 + CFG::DATA, empty = full + 8 * RING_SLOTS;
+    const uint32_t full = ring0 + DATA, empty = full + 8 * RING_SLOTS;
     const int band = blockIdx.x % p.nbands, strip = blockIdx.x / p.nbands + p.strip0;
     const int cg0 = band * p.bw, nact = min(p.bw, p.ncg - cg0);
     if (threadIdx.x == 0) {
@@ -360,18 +366,19 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
         RingState rs;
         ChainWindow win;
         const bool dep = p.chain.in != nullptr;
-        if constexpr (IL) {   // interleaved layout: coefficient rows 2k and 2k+1 as they lie, a full staged row each
+        if constexpr (IL) {   // interleaved layout: LL of row 2k from its dense band, rows 2k and 2k+1 as they lie (full staged rows)
             const int xs0 = 2 * cs0, x0 = max(xs0, 0);
             const uint32_t nb = (uint32_t)((int)min((int64_t)xs0 + nact * OUTW + 2 * VPL, p.il_pitch) - x0) * ES;
             const T *il = (const T *)p.il + (int64_t)blockIdx.y * p.il_frame + x0;
-            const uint32_t d0 = ring0 + (x0 - xs0) * ES;
+            const uint32_t d0 = ring0 + SEGB + (x0 - xs0) * ES;
             for (int q = 0; q < nitems; q++) {
                 if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
-                const uint32_t d = d0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
+                const uint32_t fb = full + 8 * rs.slot;
                 const int k = ka + q;
-                mbar_expect_tx(fb, 2 * nb);
-                bulk_g2s(d, il + (int64_t)reflect(2 * k, H) * p.il_pitch, nb, fb);
-                bulk_g2s(d + 2 * SEGB, il + (int64_t)reflect(2 * k + 1, H) * p.il_pitch, nb, fb);
+                mbar_expect_tx(fb, nll + 2 * nb);
+                bulk_g2s(dst0 + rs.slot * SLOTB, ll + (int64_t)(reflect(2 * k, H) >> 1) * p.ll_pitch, nll, fb);
+                bulk_g2s(d0 + rs.slot * SLOTB, il + (int64_t)reflect(2 * k, H) * p.il_pitch, nb, fb);
+                bulk_g2s(d0 + rs.slot * SLOTB + 2 * SEGB, il + (int64_t)reflect(2 * k + 1, H) * p.il_pitch, nb, fb);
                 rs.next();
             }
             return;
@@ -401,37 +408,34 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
 
     const bool fast = __all_sync(FULL, xl >= 0 && xl + VPL <= W);
     int cL[HV], cH[HV];   // border path: byte offsets of the mirrored subband columns inside a segment
+    int cE[IL ? HV : 1];  // interleaved layout: byte offsets of the mirrored EVEN columns inside a staged interleaved row (cH: the odd ones)
     if (!fast) {
         const int hi = nact * (OUTW / 2) + 2 * HV - 1;
 #pragma unroll
         for (int i = 0; i < HV; i++) {
+            cL[i] = min(max((reflect(xl + 2 * i, W) >> 1) - cs0, 0), hi) * ES;
             if constexpr (IL) {
-                cL[i] = min(max(reflect(xl + 2 * i, W) - 2 * cs0, 0), 2 * hi + 1) * ES;
+                cE[i] = min(max(reflect(xl + 2 * i, W) - 2 * cs0, 0), 2 * hi + 1) * ES;
                 cH[i] = min(max(reflect(xl + 2 * i + 1, W) - 2 * cs0, 0), 2 * hi + 1) * ES;
             } else {
-                cL[i] = min(max((reflect(xl + 2 * i, W) >> 1) - cs0, 0), hi) * ES;
                 cH[i] = min(max((reflect(xl + 2 * i + 1, W) >> 1) - cs0, 0), hi) * ES;
             }
         }
     }
     // one interleaved row: even positions from the L segment, odd positions from the H segment
+    // (interleaved layout: `hi` is a staged interleaved row, of which only the odd columns are used)
     auto read = [&](uint32_t lo, uint32_t hi, T(&v)[VPL]) {
-        if constexpr (IL) {   // the row is staged interleaved, starting at `lo` (hi unused); cL / cH hold the even / odd columns' offsets
-            if (fast) {
-                lds_vec<T, VPL>(lo + 2 * wofs + lane * 32, v);
-            } else {
-#pragma unroll
-                for (int i = 0; i < HV; i++) {
-                    v[2 * i] = lds_one<T>(lo + cL[i]);
-                    v[2 * i + 1] = lds_one<T>(lo + cH[i]);
-                }
-            }
-            return;
-        }
         T l[HV], h[HV];
         if (fast) {
             lds_vec<T, HV>(lo + wofs + lane * 16, l);
-            lds_vec<T, HV>(hi + wofs + lane * 16, h);
+            if constexpr (IL) {
+                T r[VPL];
+                lds_vec<T, VPL>(hi + 2 * wofs + lane * 32, r);
+#pragma unroll
+                for (int i = 0; i < HV; i++) h[i] = r[2 * i + 1];
+            } else {
+                lds_vec<T, HV>(hi + wofs + lane * 16, h);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < HV; i++) {
@@ -443,6 +447,18 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
         for (int i = 0; i < HV; i++) {
             v[2 * i] = l[i];
             v[2 * i + 1] = h[i];
+        }
+    };
+    // interleaved layout: a staged interleaved row used as it is (coefficient row 2k+1: LH | HH)
+    auto read_row = [&](uint32_t row, T(&v)[VPL]) {
+        if (fast) {
+            lds_vec<T, VPL>(row + 2 * wofs + lane * 32, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < HV; i++) {
+                v[2 * i] = lds_one<T>(row + cE[IL ? i : 0]);
+                v[2 * i + 1] = lds_one<T>(row + cH[i]);
+            }
         }
     };
     const bool producer = lane >= 1 && lane <= 30 && xl < W;
@@ -469,9 +485,10 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
     RingState rs;
     for (int k = ka; k <= kb; k++) {
         mbar_wait(full + 8 * rs.slot, rs.phase);
-        const uint32_t base = ring0 + rs.slot * CFG::SLOTB;
+        const uint32_t base = ring0 + rs.slot * SLOTB;
         read(base, base + SEGB, a);
-        read(base + 2 * SEGB, base + 3 * SEGB, b);
+        if constexpr (IL) read_row(base + 3 * SEGB, b);
+        else read(base + 2 * SEGB, base + 3 * SEGB, b);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8 * rs.slot);
         rs.next();
@@ -511,6 +528,8 @@ constexpr int RING_NCFG = 4;
 // kinds with an interleaved in-place family in the reference: float 9/7 and float 5/3
 template <class WV> constexpr bool ring_il() { return std::is_same<WV, W97F>::value || std::is_same<WV, W53F>::value; }
 bool ring_interleaved_ok(int kind) { return kind == K_CDF97_F32 || kind == K_CDF53_F32; }
+// CTA shapes whose five-segment inverse ring still fits the SM's shared memory NCTA times (all but 8 x 2)
+bool ring_interleaved_cfg_ok(int cfg) { return cfg != 2; }
 template <class F> static void dispatch_cfg(int cfg, F &&f)
 {
     if (cfg == 1) f(RingCfg<15, 1>{});
@@ -532,7 +551,7 @@ cudaError_t preload_ring()
                     if (e == cudaSuccess) e = prep(k_inv_ring<WV, V, CFG>, CFG::SMEM);
                     if constexpr (ring_il<WV>()) {
                         if (e == cudaSuccess) e = prep(k_fwd_ring<WV, V, CFG, true>, CFG::SMEM);
-                        if (e == cudaSuccess) e = prep(k_inv_ring<WV, V, CFG, true>, CFG::SMEM);
+                        if (e == cudaSuccess && CFG::SMEM_IL * CFG::NCTA <= 226 * 1024) e = prep(k_inv_ring<WV, V, CFG, true>, CFG::SMEM_IL);
                     }
                 });
         });
@@ -569,7 +588,7 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
             const dim3 grid(p.nbands * p.nstrips, frames);
             if constexpr (ring_il<WV>()) {
                 if (p.il) {
-                    launch_pdl(k_inv_ring<WV, V, CFG, true>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM, st, p.chain.pdl, p);
+                    launch_pdl(k_inv_ring<WV, V, CFG, true>, grid, dim3(CFG::THREADS), (size_t)CFG::SMEM_IL, st, p.chain.pdl, p);
                     return;
                 }
             }
