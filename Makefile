@@ -20,7 +20,7 @@ libdwt_b200/libdwt_compat.so: $(CSRC)/libdwt_compat.c include/libdwt_compat.h in
 # B200 library first and the compiled reference (for everything outside the hot path) second.
 # Build container only (needs $(REF)); the binaries travel to the GPU box in build/ (git-ignored).
 REF ?= /root/reference
-EXAMPLES = simple simple-int simple-double simple-perf simple-perf-int
+EXAMPLES = simple simple-int simple-double simple-perf simple-perf-int simple-single-loop simple-perf-single
 examples: libdwt_b200/libdwt_compat.so oracle
 	@if [ -d $(REF)/examples ]; then mkdir -p build/examples; for e in $(EXAMPLES); do \
 	  src=$(REF)/examples/$$e/simple.c; \

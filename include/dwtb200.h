@@ -94,6 +94,11 @@ int dwtb200_inv2_inplace_host(int kind, void *ptr, int64_t stride_x, int64_t str
 int dwtb200_perf2(int kind, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max,
                   int decompose_one, int zero_padding, int M, int N, float *fwd_secs, float *inv_secs);
 
+/* the same protocol for the interleaved in-place family, dwt_util_perf_cdf97_2_inplace_s and its _sep_s / _sdl_s / _sep_sdl_s
+ * twins (src/libdwt.h:2520-2590) */
+int dwtb200_perf2_inplace(int kind, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max,
+                          int decompose_one, int M, int N, float *fwd_secs, float *inv_secs);
+
 /* device time (CUDA events on the library stream) of the transform inside the last *_host call, in
  * milliseconds, host<->device copies excluded; replaces dwt_util_get_clock() brackets (src/libdwt.c:18701) */
 double dwtb200_last_transform_ms(void);

@@ -85,6 +85,20 @@ void dwt_util_perf_cdf53_2_i(int stride_x, int stride_y, int size_o_big_x, int s
                              int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
                              float *inv_secs);
 
+/* the same harness for the in-place family: src/libdwt.h:2520-2590 (four loop orders of one transform) */
+void dwt_util_perf_cdf97_2_inplace_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                                     int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                                     float *inv_secs);
+void dwt_util_perf_cdf97_2_inplace_sep_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                                         int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                                         float *inv_secs);
+void dwt_util_perf_cdf97_2_inplace_sdl_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y,
+                                         int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs,
+                                         float *inv_secs);
+void dwt_util_perf_cdf97_2_inplace_sep_sdl_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
+                                             int size_i_big_y, int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type,
+                                             float *fwd_secs, float *inv_secs);
+
 /* src/libdwt.h:1382-1409 (src/libdwt.c:1437, 1482): page-locked host memory instead of memalign(16, ...) */
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y);
 void dwt_util_free_image(void **pptr);

@@ -12,5 +12,5 @@ from .api import (  # noqa: F401
     dwt_cdf53_2f_s, dwt_cdf53_2i_s, dwt_cdf53_2f_d, dwt_cdf53_2i_d, dwt_cdf97_2f_i, dwt_cdf97_2i_i,
     dwt_cdf97_2f_s2, dwt_cdf97_2i_s2, dwt_cdf97_2f_inplace_s, dwt_cdf97_2f_inplace_sep_s, dwt_cdf97_2f_inplace_sdl_s,
     dwt_cdf97_2f_inplace_sep_sdl_s, dwt_cdf97_2i_inplace_s, dwt_cdf53_2f_inplace_s, dwt_cdf53_2i_inplace_s, fwd2_inplace, inv2_inplace,
-    perf2, perf3, fwd2, inv2, fwd3, inv3, kind_of,
+    perf2, perf2_inplace, perf3, fwd2, inv2, fwd3, inv3, kind_of,
 )

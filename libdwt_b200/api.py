@@ -36,6 +36,7 @@ SYMBOLS = [
     ("dwtb200_inv2_inplace_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i]),
     ("dwtb200_image_fwd2_inplace", _i, [_vp, _ip, _i]), ("dwtb200_image_inv2_inplace", _i, [_vp, _i, _i]),
     ("dwtb200_perf2", _i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("dwtb200_perf2_inplace", _i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("dwtb200_perf3", _i, [_i, _i, C.POINTER(_dbl), _ip]),
     ("dwtb200_last_transform_ms", _dbl, []), ("dwtb200_release_host_cache", None, []),
     ("dwtb200_image_create", _vp, [_i, _i, _i, _i]), ("dwtb200_image_destroy", None, [_vp]),
@@ -212,6 +213,15 @@ def perf2(kind, size_x, size_y, j_max=-1, M=1, N=1, inner=None, decompose_one=0,
     f, i = C.c_float(), C.c_float()
     L = lib()
     L.check(L.c.dwtb200_perf2(kind, size_x, size_y, ix, iy, j_max, decompose_one, zero_padding, M, N, C.byref(f), C.byref(i)))
+    return f.value, i.value
+
+
+def perf2_inplace(kind, size_x, size_y, j_max=-1, M=1, N=1, inner=None, decompose_one=0):
+    """dwt_util_perf_cdf97_2_inplace_s (and twins) on the device: (fwd_secs, inv_secs) per transform."""
+    iy, ix = inner if inner is not None else (size_y, size_x)
+    f, i = C.c_float(), C.c_float()
+    L = lib()
+    L.check(L.c.dwtb200_perf2_inplace(kind, size_x, size_y, ix, iy, j_max, decompose_one, M, N, C.byref(f), C.byref(i)))
     return f.value, i.value
 
 

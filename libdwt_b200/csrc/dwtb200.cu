@@ -1991,6 +1991,45 @@ int dwtb200_perf2(int kind, int ox, int oy, int ix, int iy, int j_max, int decom
 
 // =====================================================================================================
 // 3-D, one level, interleaved subbands
+// dwt_util_perf_cdf97_2_inplace_s and its _sep / _sdl twins (src/libdwt.h:2520-2590): the protocol of dwtb200_perf2 for the
+// in-place family.  Level sizes come from the inner size, the level count from the outer one.
+int dwtb200_perf2_inplace(int kind, int ox, int oy, int ix, int iy, int j_max, int decompose_one, int M, int N, float *fwd_secs,
+                          float *inv_secs)
+{
+    NEED_DEV();
+    if (M < 1 || N < 1 || !fwd_secs || !inv_secs || ix < 1 || iy < 1 || ix > ox || iy > oy) return fail(DWTB200_EINVAL, "perf2_inplace: bad arguments");
+    const int J = dwtb200_clamp_j(j_max, ox, oy, decompose_one);
+    std::vector<dwtb200_image *> imgs;
+    int r = DWTB200_OK;
+    for (int m = 0; m < M && !r; m++) {
+        dwtb200_image *im = dwtb200_image_create(kind, ix, iy, 1);
+        if (!im) r = DWTB200_ENOMEM;
+        else {
+            imgs.push_back(im);
+            r = dwtb200_image_fill(im, 0, 0, 0);
+        }
+    }
+    float best_f = 1e30f, best_i = 1e30f;
+    for (int n = -1; n < N && !r; n++) {   // loop -1 warms up (graph capture)
+        for (int inverse = 0; inverse < 2 && !r; inverse++) {
+            r = dwtb200_timer_start();
+            for (int m = 0; m < M && !r; m++) {
+                ImageScope scope(imgs[m]);
+                r = inplace_transform(imgs[m], inverse != 0, J);
+            }
+            if (!r) {
+                const float ms = (float)dwtb200_timer_stop_ms();
+                float &best = inverse ? best_i : best_f;
+                if (n >= 0 && ms / M < best) best = ms / M;
+            }
+        }
+    }
+    for (dwtb200_image *im : imgs) dwtb200_image_destroy(im);
+    *fwd_secs = best_f * 1e-3f;
+    *inv_secs = best_i * 1e-3f;
+    return r;
+}
+
 // =====================================================================================================
 dwtb200_volume *dwtb200_volume_create(int nx, int ny, int nz)
 {

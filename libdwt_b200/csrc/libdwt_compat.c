@@ -73,6 +73,20 @@ INV_IP(dwt_cdf97_2i_inplace_s, DWTB200_CDF97_F32)
 FWD_IP(dwt_cdf53_2f_inplace_s, DWTB200_CDF53_F32)
 INV_IP(dwt_cdf53_2i_inplace_s, DWTB200_CDF53_F32)
 
+#define PERF_IP(NAME)                                                                                                       \
+    void NAME(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x, int size_i_big_y, int j_max,    \
+              int decompose_one, int zero_padding, int M, int N, int clock_type, float *fwd_secs, float *inv_secs)              \
+    {                                                                                                                           \
+        (void)stride_x; (void)stride_y; (void)zero_padding; (void)clock_type;                                                   \
+        const int rc = dwtb200_perf2_inplace(DWTB200_CDF97_F32, size_o_big_x, size_o_big_y, size_i_big_x, size_i_big_y, j_max,  \
+                                             decompose_one, M, N, fwd_secs, inv_secs);                                          \
+        if (rc) die(#NAME, rc);                                                                                                 \
+    }
+PERF_IP(dwt_util_perf_cdf97_2_inplace_s)
+PERF_IP(dwt_util_perf_cdf97_2_inplace_sep_s)
+PERF_IP(dwt_util_perf_cdf97_2_inplace_sdl_s)
+PERF_IP(dwt_util_perf_cdf97_2_inplace_sep_sdl_s)
+
 void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                      int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)
 {

@@ -1,7 +1,8 @@
 """GPU: the reference's UNMODIFIED example programs (examples/simple, simple-int, simple-double), linked
 against libdwt_compat.so ahead of the compiled reference (Makefile target `examples`), must print
 "success": they allocate with dwt_util_alloc_image, use a prime row stride (2053 bytes for 512 floats),
-call dwt_cdfXX_2f_* / 2i_* and compare the round trip with the reference's own dwt_util_compare_*."""
+call dwt_cdfXX_2f_* / 2i_* and compare the round trip with the reference's own dwt_util_compare_*.
+simple-single-loop is the in-place family's example (dwt_cdf97_2f_inplace_sdl_s / dwt_cdf97_2i_inplace_s, decompose_one = 1)."""
 import os
 import subprocess
 
@@ -11,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["simple", "simple-int", "simple-double", "simple-perf", "simple-perf-int"])
+@pytest.mark.parametrize("name", ["simple", "simple-int", "simple-double", "simple-perf", "simple-perf-int", "simple-single-loop", "simple-perf-single"])
 def test_unmodified_example_runs_on_the_gpu(name, tmp_path):
     exe = os.path.join(ROOT, "build", "examples", name)
     assert os.path.exists(exe), f"{exe} missing: run `make examples` in the build container (it travels via gpurun)"

@@ -254,3 +254,11 @@ def test_inplace_full_size(dev, oracle):
     back = img.download()
     assert np.abs(back - x0).max() < 1e-4
     img.close()
+
+
+def test_inplace_perf_harness_on_device(dev):
+    """dwt_util_perf_cdf97_2_inplace_s re-pointed at the device (dwtb200_perf2_inplace): M resident images, N loops, CUDA events"""
+    f, i = dev.perf2_inplace(dev.CDF97_F32, 1920, 1080, j_max=-1, M=2, N=3)
+    assert 0 < f < 0.01 and 0 < i < 0.01, (f, i)
+    f, i = dev.perf2_inplace(dev.CDF53_F32, 1024, 768, j_max=3, M=1, N=2, inner=(700, 1000), decompose_one=1)
+    assert 0 < f < 0.01 and 0 < i < 0.01, (f, i)
