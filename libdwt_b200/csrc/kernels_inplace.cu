@@ -342,34 +342,43 @@ struct IpPack {
     int64_t pitch, frame, tpitch, tframe;
     int ox, oy, J, jt;
     int shift;             // only the samples at multiples of 2^shift in both coordinates are translated (1: level 0 is already interleaved)
+    int wl[32], hl[32];    // size of LL_l+1: column / row origin of the H bands of level l
 };
+constexpr int IP_PACK_ROWS = 4;   // rows per thread: the column's part of the index arithmetic is shared (the kernel is issue-bound)
 template <bool UNPACK> __global__ void __launch_bounds__(256) k_ip_pack(const IpPack p)
 {
     const int X = (blockIdx.x * 256 + threadIdx.x) << p.shift;
     if (X >= p.ox) return;
-    const size_t f = (size_t)blockIdx.z * p.frame;
+    const size_t f = (size_t)blockIdx.z * p.frame, ft = (size_t)blockIdx.z * p.tframe;
     const uint32_t *src = (const uint32_t *)p.src;
     uint32_t *dst = (uint32_t *)p.dst, *tail = (uint32_t *)p.tail;
-    for (int Y = blockIdx.y << p.shift; Y < p.oy; Y += gridDim.y << p.shift) {
-        const int t = Y | X;
-        const int lvl = t ? __ffs(t) - 1 : 31;
+    const int cx = X ? __ffs(X) - 1 : 31;
+    const int jt = tail ? p.jt : 32;
+#pragma unroll
+    for (int r = 0; r < IP_PACK_ROWS; r++) {
+        const int Y = (blockIdx.y * IP_PACK_ROWS + r) << p.shift;
+        if (Y >= p.oy) break;
+        const int lvl = min(cx, Y ? __ffs(Y) - 1 : 31);
         const size_t i = f + (size_t)Y * p.pitch + X;
-        if (tail && lvl >= p.jt) {
-            const size_t m = (size_t)blockIdx.z * p.tframe + (size_t)(Y >> p.jt) * p.tpitch + (X >> p.jt);
+        if (lvl >= jt) {
+            const size_t m = ft + (size_t)(Y >> jt) * p.tpitch + (X >> jt);
             if (UNPACK) tail[m] = src[i];
             else dst[i] = tail[m];
             continue;
         }
-        size_t m;
+        int row, col;
         if (lvl >= p.J) {
-            m = (size_t)(Y >> p.J) * p.pitch + (X >> p.J);
+            row = Y >> p.J;
+            col = X >> p.J;
         } else {
-            const int a = (Y >> lvl) & 1, b = (X >> lvl) & 1, y = Y >> (lvl + 1), x = X >> (lvl + 1);
-            const int hl = cdiv_pow2(p.oy, lvl + 1), wl = cdiv_pow2(p.ox, lvl + 1);
-            m = (size_t)(a ? hl + y : y) * p.pitch + (b ? wl + x : x);
+            row = Y >> (lvl + 1);
+            col = X >> (lvl + 1);
+            if ((Y >> lvl) & 1) row += p.hl[lvl];
+            if ((X >> lvl) & 1) col += p.wl[lvl];
         }
-        if (UNPACK) dst[f + m] = src[i];
-        else dst[i] = src[f + m];
+        const size_t m = f + (size_t)row * p.pitch + col;
+        if (UNPACK) dst[m] = src[i];
+        else dst[i] = src[m];
     }
 }
 void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int64_t frame, int ox, int oy, int J, void *tail, int64_t tpitch,
@@ -379,8 +388,12 @@ void launch_ip_pack(bool unpack, const void *src, void *dst, int64_t pitch, int6
     p.src = src; p.dst = dst; p.tail = tail;
     p.pitch = pitch; p.frame = frame; p.tpitch = tpitch; p.tframe = tframe;
     p.ox = ox; p.oy = oy; p.J = J; p.jt = jt; p.shift = shift;
+    for (int l = 0; l < 32; l++) {
+        p.wl[l] = cdiv_pow2(ox, l + 1);
+        p.hl[l] = cdiv_pow2(oy, l + 1);
+    }
     const int nx = cdiv_pow2(ox, shift), ny = cdiv_pow2(oy, shift);
-    const dim3 grid((nx + 255) / 256, ny < 32768 ? ny : 32768, frames);
+    const dim3 grid((nx + 255) / 256, (ny + IP_PACK_ROWS - 1) / IP_PACK_ROWS, frames);
     if (unpack) k_ip_pack<true><<<grid, 256, 0, st>>>(p);
     else k_ip_pack<false><<<grid, 256, 0, st>>>(p);
 }
