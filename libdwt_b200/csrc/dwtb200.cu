@@ -1203,13 +1203,15 @@ int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompo
 // =====================================================================================================
 namespace {
 constexpr int IP_STD_MIN = 32;            // a level with a side below this is evaluated by k_ip_phase alone
+constexpr int IP_WHOLE_MAX = 256 * 256;   // samples (all frames) up to which a level is evaluated by k_ip_phase alone
 constexpr int IP_TOP = 8, IP_RIGHT = 6;   // frame whose sweep order differs from rows-then-columns (7 / 8 rows, 5 columns)
 
 // one level of the 9/7 family: the ordinary level kernel, then the exact schedule over the top and right frame
 int ip_level(dwtb200_image *im, bool inverse, const LevelParams &lp)
 {
     const int nx = lp.W, ny = lp.H, top = std::min(IP_TOP, ny);
-    if (std::min(nx, ny) < IP_STD_MIN) {
+    // small levels: the exact kernel alone (one launch of ~7 us) beats tile kernel + frame kernel (5 + 7 us)
+    if (std::min(nx, ny) < IP_STD_MIN || (int64_t)nx * ny * im->frames <= IP_WHOLE_MAX) {
         launch_ip_phase(inverse, lp, im->frames, 0, 0, nx, ny, 0, 0, 0, 0, g.st);
         g.launches++;
         return 0;
