@@ -15,6 +15,7 @@
 #define LIBDWT_COMPAT_H
 
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -98,6 +99,20 @@ void dwt_util_perf_cdf97_2_inplace_sdl_s(int stride_x, int stride_y, int size_o_
 void dwt_util_perf_cdf97_2_inplace_sep_sdl_s(int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                                              int size_i_big_y, int j_max, int decompose_one, int zero_padding, int M, int N, int clock_type,
                                              float *fwd_secs, float *inv_secs);
+
+/* the harness over a range of sizes, one "pixels <TAB> seconds" line per size: src/libdwt.h:2700-2815 (src/libdwt.c:22559, 22646 ...);
+ * array_type is the reference's enum dwt_array (0 DWT_ARR_SIMPLE, 1 DWT_ARR_SPARSE, 2 DWT_ARR_PACKED), passed as int */
+void dwt_util_measure_perf_cdf97_2_s(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one, int zero_padding,
+                                     int M, int N, int clock_type, FILE *fwd_plot_data, FILE *inv_plot_data);
+void dwt_util_measure_perf_cdf97_2_inplace_s(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one,
+                                             int zero_padding, int M, int N, int clock_type, FILE *fwd_plot_data, FILE *inv_plot_data);
+void dwt_util_measure_perf_cdf97_2_inplace_sep_s(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one,
+                                                 int zero_padding, int M, int N, int clock_type, FILE *fwd_plot_data, FILE *inv_plot_data);
+void dwt_util_measure_perf_cdf97_2_inplace_sdl_s(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one,
+                                                 int zero_padding, int M, int N, int clock_type, FILE *fwd_plot_data, FILE *inv_plot_data);
+void dwt_util_measure_perf_cdf97_2_inplace_sep_sdl_s(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one,
+                                                     int zero_padding, int M, int N, int clock_type, FILE *fwd_plot_data,
+                                                     FILE *inv_plot_data);
 
 /* src/libdwt.h:1382-1409 (src/libdwt.c:1437, 1482): page-locked host memory instead of memalign(16, ...) */
 void dwt_util_alloc_image(void **pptr, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y);

@@ -87,6 +87,46 @@ PERF_IP(dwt_util_perf_cdf97_2_inplace_sep_s)
 PERF_IP(dwt_util_perf_cdf97_2_inplace_sdl_s)
 PERF_IP(dwt_util_perf_cdf97_2_inplace_sep_sdl_s)
 
+/* dwt_util_measure_perf_cdf97_2_s / _inplace_s and twins (src/libdwt.c:22559, 22646): the perf harness over a range of square sizes,
+ * x growing by g_growth_factor_s = 1.13 (:22385), sizes per dwt_util_get_sizes_s (:22296: outer size rounded up to a power of two for
+ * DWT_ARR_SIMPLE / DWT_ARR_SPARSE), one "pixels <TAB> seconds" line per size and direction.  The reference's versions call its own
+ * CPU harness from inside libdwt.a, so they are restated here on top of the device harness. */
+static int pow2_not_less(int x)
+{
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static void measure_perf(int inplace, int array_type, int min_x, int max_x, int j_max, int decompose_one, int zero_padding, int M, int N,
+                         FILE *fwd_plot_data, FILE *inv_plot_data, const char *name)
+{
+    for (int x = min_x; x <= max_x;) {
+        const int o = (array_type == 0 || array_type == 1) ? pow2_not_less(x) : x;   /* DWT_ARR_SIMPLE, DWT_ARR_SPARSE */
+        float f = 0, i = 0;
+        const int rc = inplace ? dwtb200_perf2_inplace(DWTB200_CDF97_F32, o, o, x, x, j_max, decompose_one, M, N, &f, &i)
+                               : dwtb200_perf2(DWTB200_CDF97_F32, o, o, x, x, j_max, decompose_one, zero_padding, M, N, &f, &i);
+        if (rc) die(name, rc);
+        fprintf(fwd_plot_data, "%i\t%.10f\n", x * x, f);
+        fprintf(inv_plot_data, "%i\t%.10f\n", x * x, i);
+        const float t = x * 1.13f;   /* x = ceilf(x * growth_factor) */
+        int nx = (int)t;
+        if ((float)nx < t) nx++;
+        x = nx;
+    }
+}
+#define MEASURE(NAME, INPLACE)                                                                                                 \
+    void NAME(int array_type, int min_x, int max_x, int opt_stride, int j_max, int decompose_one, int zero_padding, int M, int N, \
+              int clock_type, FILE *fwd_plot_data, FILE *inv_plot_data)                                                        \
+    {                                                                                                                          \
+        (void)opt_stride; (void)clock_type;                                                                                    \
+        measure_perf(INPLACE, array_type, min_x, max_x, j_max, decompose_one, zero_padding, M, N, fwd_plot_data, inv_plot_data, #NAME); \
+    }
+MEASURE(dwt_util_measure_perf_cdf97_2_s, 0)
+MEASURE(dwt_util_measure_perf_cdf97_2_inplace_s, 1)
+MEASURE(dwt_util_measure_perf_cdf97_2_inplace_sep_s, 1)
+MEASURE(dwt_util_measure_perf_cdf97_2_inplace_sdl_s, 1)
+MEASURE(dwt_util_measure_perf_cdf97_2_inplace_sep_sdl_s, 1)
+
 void dwt_cdf97_2f_s2(const void *src, void *dst, int stride_x, int stride_y, int size_o_big_x, int size_o_big_y, int size_i_big_x,
                      int size_i_big_y, int *j_max_ptr, int decompose_one, int zero_padding)
 {

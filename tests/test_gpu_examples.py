@@ -6,6 +6,7 @@ simple-single-loop is the in-place family's example (dwt_cdf97_2f_inplace_sdl_s 
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -24,3 +25,34 @@ def test_unmodified_example_runs_on_the_gpu(name, tmp_path):
         import re
         m = re.search(r"performance test: fwd=([0-9.eE+-]+) secs", out)
         assert m and 0 < float(m.group(1)) < 0.01, out[-2000:]   # 1920x1080, one level: well under 10 ms on a B200
+
+
+def test_measure_perf_harness_writes_plot_data(tmp_path):
+    """dwt_util_measure_perf_cdf97_2_s / _inplace_s of libdwt_compat.so (src/libdwt.c:22559, 22646): sizes min_x .. max_x growing
+    by 1.13, one 'pixels <TAB> seconds' line per size in each plot file, timed on the device"""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "libdwt_b200", "libdwt_compat.so"))
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    for name, arr in (("dwt_util_measure_perf_cdf97_2_s", 2), ("dwt_util_measure_perf_cdf97_2_s", 1), ("dwt_util_measure_perf_cdf97_2_inplace_s", 2)):
+        f = getattr(L, name)
+        f.restype = None
+        f.argtypes = [C.c_int] * 10 + [C.c_void_p, C.c_void_p]
+        pf, pi = str(tmp_path / "fwd.txt").encode(), str(tmp_path / "inv.txt").encode()
+        ff, fi = libc.fopen(pf, b"w"), libc.fopen(pi, b"w")
+        assert ff and fi
+        f(arr, 100, 200, 1, -1, 0, 0, 1, 2, 0, ff, fi)
+        libc.fclose(ff)
+        libc.fclose(fi)
+        sizes = []
+        x = 100
+        while x <= 200:
+            sizes.append(x * x)
+            t = np.float32(x) * np.float32(1.13)
+            x = int(np.ceil(t))
+        for path in (pf, pi):
+            lines = open(path).read().split("\n")[:-1]
+            assert [int(l.split("\t")[0]) for l in lines] == sizes, (name, lines)
+            assert all(0 < float(l.split("\t")[1]) < 0.01 for l in lines), (name, lines)
