@@ -128,6 +128,8 @@ struct volume_t {
 void cdf97_3f_op_sep_horizontal_s(struct volume_t *src, struct volume_t *dst);
 void cdf97_3f_ip_sep_horizontal_s(struct volume_t *volume);
 void cdf97_3i_ip_sep_horizontal_s(struct volume_t *volume);
+/* src/volume-dwt.h:227; approach: enum volume_approach, only VOL_SEP_HORIZONTAL (0) / VOL_SEP_VERTICAL (1), whose results are identical */
+void cdf97_3f_op_wrapper_s(struct volume_t *src, struct volume_t *dst, int approach);
 
 /* src/volume-dwt.h:234 (src/volume-dwt.c:2810): `approach` is enum volume_approach there (an int here: every approach is a
  * CPU schedule of the same transform); seconds per voxel of the forward transform on a device-resident volume */

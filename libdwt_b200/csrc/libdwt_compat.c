@@ -193,6 +193,18 @@ void cdf97_3i_ip_sep_horizontal_s(struct volume_t *v)
     if (rc) die("cdf97_3i_ip_sep_horizontal_s", rc);
 }
 
+/* src/volume-dwt.h:227.  Measured on the compiled reference: VOL_SEP_HORIZONTAL (0) and VOL_SEP_VERTICAL (1) give identical bits; the
+ * blocked / fused schedules 2..9 round differently in most samples and overrun their buffers on sizes that are not multiples of their
+ * block, 10..12 are single-axis passes.  Only the two parity-checked ones are served. */
+void cdf97_3f_op_wrapper_s(struct volume_t *src, struct volume_t *dst, int approach)
+{
+    if (approach != 0 && approach != 1) {
+        fprintf(stderr, "ERROR: cdf97_3f_op_wrapper_s: approach %d is a CPU loop schedule with its own rounding; only VOL_SEP_HORIZONTAL / VOL_SEP_VERTICAL run on the device\n", approach);
+        abort();
+    }
+    cdf97_3f_op_sep_horizontal_s(src, dst);
+}
+
 /* src/volume-dwt.c:2810: every `approach` is a CPU schedule of the same transform; the device has one */
 int volume_perftest_fwd97op_s(int size, int opt_stride, int approach, int N, double *secs, long unsigned *faults)
 {
