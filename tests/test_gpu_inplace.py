@@ -262,3 +262,35 @@ def test_inplace_perf_harness_on_device(dev):
     assert 0 < f < 0.01 and 0 < i < 0.01, (f, i)
     f, i = dev.perf2_inplace(dev.CDF53_F32, 1024, 768, j_max=3, M=1, N=2, inner=(700, 1000), decompose_one=1)
     assert 0 < f < 0.01 and 0 < i < 0.01, (f, i)
+
+
+def test_inplace_beyond_2g_bytes(dev):
+    """a 32768 x 20000 float image (2.6 GB per plane: byte offsets beyond 2^31, which the reference cannot address,
+    src/inline.h:188): size-independent properties -- the interior of a two-level in-place transform equals the Mallat
+    transform's coefficients bit for bit (only the frame of each level rounds differently), and the full-depth round trip
+    reconstructs the input"""
+    ox, oy = 32768, 20000
+    img = dev.DeviceImage(dev.kind_of("97", "s"), ox, oy)
+    img.fill(0, 0, 0, 0, 1)
+    x0 = img.download()
+    J = img.fwd2_inplace(j_max=2)
+    assert J == 2
+    ip = img.download()
+    img.upload(x0)
+    img.fwd2(j_max=2)
+    ml = img.download()
+    # level 1 subbands (odd rows / columns of the interleaved plane) against the Mallat quadrants
+    h, w = oy // 2, ox // 2
+    assert (bits(ip[1::2, 1::2], "s")[8:, :-8] == bits(ml[h:, w:], "s")[8:, :-8]).all()      # HH_1
+    assert (bits(ip[0::2, 1::2], "s")[8:, :-8] == bits(ml[:h, w:], "s")[8:, :-8]).all()      # HL_1
+    # level 2 subbands live at stride 4; its frame is 8 rows / 6 columns of the LL_1 grid, widened by what level 1's frame feeds into it
+    h2, w2 = oy // 4, ox // 4
+    assert (bits(ip[2::4, 2::4], "s")[16:, :-16] == bits(ml[h2:h, w2:w], "s")[16:, :-16]).all()   # HH_2
+    assert (bits(ip[0::4, 0::4], "s")[16:, :-16] == bits(ml[:h2, :w2], "s")[16:, :-16]).all()     # LL_2
+    del ip, ml
+    img.upload(x0)
+    J = img.fwd2_inplace()
+    img.inv2_inplace(J)
+    back = img.download()
+    assert float(np.abs(back - x0).max()) < 1e-4
+    img.close()
