@@ -75,6 +75,7 @@ struct Ctx {
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
     int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // strip-length search range of the ring kernels (0: defaults)
     int64_t pyr_max_in = (int64_t)512 * 512;   // only levels with at most this many input samples per frame are fused
+    int vol3 = 1;       // forward 3-D: one pass over the volume where the tile kernel applies (kernels_vol.cu, k_vol3_fwd)
     int pyr = 0;        // > 0: runs of tile levels are fused, tiles of this edge carried through up to 3 levels (kernels_pyr.cu)
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
@@ -292,6 +293,7 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
     case DWTB200_TUNE_PYR: g.pyr = (int)value; break;
+    case DWTB200_TUNE_VOL3: g.vol3 = value != 0; break;
     case 96: g.pyr_max_in = value; break;
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
@@ -2121,6 +2123,12 @@ static int volume_axes(dwtb200_volume *v, int inverse)
         p.s_slice = p.d_slice = v->slice;
         p.src = v->buf[v->cur];
         p.dst = v->buf[v->cur ^ 1];
+        if (!inverse && g.vol3 && vol3_applies(p)) {   // all three axes in one pass: buf[cur] -> buf[cur^1]
+            launch_vol3_fwd(p, g.sm_count, g.st);
+            v->cur ^= 1;
+            CK(cudaGetLastError());
+            return DWTB200_OK;
+        }
         launch_vol_xy(p, inverse, g.sm_count, g.st);
         p.src = v->buf[v->cur ^ 1];
         p.dst = v->buf[v->cur];

@@ -223,6 +223,182 @@ template <bool INV> __global__ void __launch_bounds__(128, 4) k_vol_z(const VolP
     }
 }
 
+// =====================================================================================================
+// forward, single pass: x, y and z lifting of a (V3_TX x V3_TY) column of the volume marching along z
+// =====================================================================================================
+// Two passes move every voxel four times through HBM; this kernel reads and writes it once.  A CTA owns a tile of
+// V3_TX x V3_TY (x, y) positions and a range of slice pairs.  Per slice: the tile plus a 4-sample halo is staged in
+// shared memory with cp.async (three buffers: two slices in flight), lifted along x by window evaluation (16 outputs
+// from 24 staged samples per task), then along y (8 outputs from 16 x-lifted samples) -- each thread ends up holding
+// the x/y-lifted values of ITS 8 positions (one column, 8 rows) -- and those go straight into the z register pipeline
+// of k_vol_z (vfwd), whose state (4 values per position) stays in the thread's registers from slice to slice.
+// Same operations in the same order per sample as the two-pass kernels and the reference (x, then y, then z).
+constexpr int V3_TX = 64, V3_TY = 32, V3_THREADS = 256, V3_HALO = 4, V3_NCTA = 2;
+constexpr int V3_SW = V3_TX + 2 * V3_HALO, V3_SH = V3_TY + 2 * V3_HALO;   // staged tile: 136 x 40
+constexpr int V3_SP = V3_SW + 4;      // staged row pitch (140 words: conflict-free 16-byte accesses of consecutive rows)
+constexpr int V3_XP = V3_TX + 12;     // pitch of the x-lifted buffer (140)
+constexpr int V3_NBUF = 3;
+constexpr int V3_SMEM = (V3_NBUF * V3_SH * V3_SP + V3_SH * V3_XP) * (int)sizeof(float);
+
+__device__ __forceinline__ void cp_async16(float *smem, const float *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float *smem, const float *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParams p)
+{
+    extern __shared__ __align__(16) float v3_smem[];
+    float *stage = v3_smem, *xb = v3_smem + V3_NBUF * V3_SH * V3_SP;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * V3_TX, y0 = blockIdx.y * V3_TY;
+    const int nx = p.nx, ny = p.ny, N = p.nz;
+
+    constexpr int WARM = 3, DELAY = 1;
+    const int nL = (N + 1) >> 1;
+    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, nL);
+    if (k0 >= k1) return;
+    const int m0 = k0 + DELAY - WARM, m1 = k1 - 1 + DELAY;
+    const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + 1;   // slices zfirst .. zfirst + nsl - 1 (mirrored into the volume)
+
+    // staging: groups of four columns; a thread copies the same (up to three) groups of every slice, so their offsets are
+    // computed once.  goff < 0: the group straddles the volume's edge and is copied element by element through the mirror.
+    constexpr int NG = (V3_SH * (V3_SW / 4) + V3_THREADS - 1) / V3_THREADS;
+    int soff[NG];
+    int64_t goff[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const int g = tid + k * V3_THREADS;
+        const int r = g / (V3_SW / 4), c = (g - r * (V3_SW / 4)) * 4;
+        const int gx = x0 - V3_HALO + c;
+        const int64_t row = (int64_t)reflect(y0 - V3_HALO + r, ny) * p.s_pitch;
+        soff[k] = g < V3_SH * (V3_SW / 4) ? r * V3_SP + c : -1;
+        goff[k] = (gx >= 0 && gx + 3 < nx) ? row + gx : -(row + 1);   // slow path keeps the row offset, biased to stay negative
+    }
+    auto issue = [&](int i) {
+        if (i < nsl) {
+            const float *sl = p.src + (int64_t)reflect(zfirst + i, N) * p.s_slice;
+            float *buf = stage + (i % V3_NBUF) * (V3_SH * V3_SP);
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+                if (soff[k] < 0) continue;
+                if (goff[k] >= 0) {
+                    cp_async16(buf + soff[k], sl + goff[k]);
+                } else {
+                    const float *row = sl + (-goff[k] - 1);
+                    const int c = soff[k] % V3_SP, gx = x0 - V3_HALO + c;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) cp_async4(buf + soff[k] + j, row + reflect(gx + j, nx));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // this thread's 8 positions: column x0 + px, rows y0 + 8 * ps .. + 7
+    const int px = tid % V3_TX, ps = tid / V3_TX;
+    T st[WV::NS][8];
+#pragma unroll
+    for (int s = 0; s < WV::NS; s++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[s][i] = 0.f;
+    const int rows_ok = (x0 + px < nx) ? min(max(ny - (y0 + 8 * ps), 0), 8) : 0;   // how many of the 8 rows exist
+    float *out = p.dst + (int64_t)(y0 + 8 * ps) * p.d_pitch + x0 + px;
+    const int dp = (int)p.d_pitch;
+    auto put = [&](int z, const T(&o)[8]) {
+        if (z >= N) return;
+        float *q = out + (int64_t)z * p.d_slice;
+        if (rows_ok == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j * dp] = o[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < rows_ok) q[j * dp] = o[j];
+        }
+    };
+    // x and y lifting of slice number i of the sequence; leaves this thread's 8 values in v
+    const int xr = tid % V3_SH, xsg = tid / V3_SH;   // x task of this thread (threads >= V3_SH * 8 have none)
+    auto xy = [&](int i, T(&v)[8]) {
+        issue(i + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();   // slice i is staged (and every thread is done with the x-lifted buffer of slice i - 1)
+        const float *buf = stage + (i % V3_NBUF) * (V3_SH * V3_SP);
+        if (xsg < V3_TX / 16) {   // x: (staged row, run of 16 output columns); consecutive threads take consecutive rows
+            T w[24], L[8], H[8];
+            const float4 *src4 = reinterpret_cast<const float4 *>(buf + xr * V3_SP + 16 * xsg);
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const float4 q4 = src4[j];
+                w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
+            }
+            window_fwd_p<WV, 8>(w, L, H);
+            float4 *dst4 = reinterpret_cast<float4 *>(xb + xr * V3_XP + 16 * xsg);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst4[j] = make_float4(L[2 * j], H[2 * j], L[2 * j + 1], H[2 * j + 1]);
+        }
+        __syncthreads();
+        T w[16], L[4], H[4];   // y: 8 output rows of this thread's column from 16 x-lifted rows
+        const float *col = xb + (8 * ps) * V3_XP + px;
+#pragma unroll
+        for (int j = 0; j < 16; j++) w[j] = col[j * V3_XP];
+        window_fwd_p<WV, 4>(w, L, H);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[2 * j] = L[j];
+            v[2 * j + 1] = H[j];
+        }
+    };
+
+    issue(0);
+    issue(1);
+    xy(0, st[0]);   // z: the register pipeline of k_vol_z -- slice 0 of the sequence seeds st[0], then pairs (2m+1, 2m+2)
+    for (int q = 0; q < npairs; q++) {
+        T a[8], b[8], oL[8], oH[8];
+        xy(2 * q + 1, a);
+        xy(2 * q + 2, b);
+        vfwd<WV, 8>(a, b, st, oL, oH);
+        const int kk = m0 + q - DELAY;
+        if (kk >= k0) {
+            put(2 * kk, oL);
+            put(2 * kk + 1, oH);
+        }
+    }
+}
+
+bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }
+void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st)
+{
+    static bool prepared = false;
+    if (!prepared) {
+        cudaFuncSetAttribute(k_vol3_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
+        prepared = true;
+    }
+    const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
+    const int units = (p.nz + 1) >> 1;
+    // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
+    int best = 1;
+    double best_cost = 1e30;
+    for (int zs = 1; zs <= 16; zs++) {
+        const int pps = (units + zs - 1) / zs;
+        if (zs > 1 && pps < 32) break;
+        const int64_t n = (int64_t)tx * ty * ((units + pps - 1) / pps);
+        const int64_t slots = (int64_t)sm_count * V3_NCTA, waves = (n + slots - 1) / slots;
+        const double cost = (1.0 + 3.0 / pps) * (double)(waves * slots) / (double)n;
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = zs;
+        }
+    }
+    p.pps = (units + best - 1) / best;
+    p.nstrips = (units + p.pps - 1) / p.pps;
+    const dim3 grid(tx, ty, p.nstrips);
+    k_vol3_fwd<<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+}
+
 static int pick_pps(int units, int64_t other_warps, int sm_count)
 {
     // enough warps for ~16 per SM, strips between 8 and 64 pairs (3-4 warm-up pairs are re-read per strip)
