@@ -382,12 +382,16 @@ void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st)
     // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
     int best = 1;
     double best_cost = 1e30;
-    for (int zs = 1; zs <= 16; zs++) {
+    for (int zs = 1; zs <= 32; zs++) {
         const int pps = (units + zs - 1) / zs;
-        if (zs > 1 && pps < 32) break;
+        if (zs > 1 && pps < 24) break;
         const int64_t n = (int64_t)tx * ty * ((units + pps - 1) / pps);
         const int64_t slots = (int64_t)sm_count * V3_NCTA, waves = (n + slots - 1) / slots;
-        const double cost = (1.0 + 3.0 / pps) * (double)(waves * slots) / (double)n;
+        // the CTAs of one wave start together and stay in phase, so the two CTAs of an SM sit in the same (x / y / z) phase at the
+        // same time; several waves of shorter ranges drift apart and overlap each other's phases (measured: 768^3 in one wave of
+        // 288 CTAs 1.50 ms, 1024^3 in seven waves at the same per-voxel cost 2.54 ms;
+        // delaying the second CTA of every SM by a microsecond at its start changes nothing once there are several waves)
+        const double cost = (1.0 + 3.0 / pps) * (double)(waves * slots) / (double)n * (waves < 3 ? 1.2 : 1.0);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best = zs;
