@@ -2123,8 +2123,8 @@ static int volume_axes(dwtb200_volume *v, int inverse)
         p.s_slice = p.d_slice = v->slice;
         p.src = v->buf[v->cur];
         p.dst = v->buf[v->cur ^ 1];
-        if (!inverse && g.vol3 && vol3_applies(p)) {   // all three axes in one pass: buf[cur] -> buf[cur^1]
-            launch_vol3_fwd(p, g.sm_count, g.st);
+        if (g.vol3 && vol3_applies(p)) {   // all three axes in one pass: buf[cur] -> buf[cur^1]
+            launch_vol3(p, inverse, g.sm_count, g.st);
             v->cur ^= 1;
             CK(cudaGetLastError());
             return DWTB200_OK;

@@ -182,9 +182,9 @@ struct VolParams {
 };
 void launch_vol_xy(VolParams p, int inverse, int sm_count, cudaStream_t st);
 void launch_vol_z(VolParams p, int inverse, int sm_count, cudaStream_t st);
-// forward, all three axes in ONE pass over the volume (tiles of 128 x 32 positions marching along z); volumes it applies to
+// all three axes in ONE pass over the volume (tiles of 64 x 32 positions marching along z); volumes it applies to
 bool vol3_applies(const VolParams &p);
-void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st);
+void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st);
 
 struct Axis3Params {
     const float *src;

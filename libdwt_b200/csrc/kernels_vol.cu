@@ -249,7 +249,7 @@ __device__ __forceinline__ void cp_async4(float *smem, const float *gmem)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
-__global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParams p)
+template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3(const VolParams p)
 {
     extern __shared__ __align__(16) float v3_smem[];
     float *stage = v3_smem, *xb = v3_smem + V3_NBUF * V3_SH * V3_SP;
@@ -257,12 +257,13 @@ __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParam
     const int x0 = blockIdx.x * V3_TX, y0 = blockIdx.y * V3_TY;
     const int nx = p.nx, ny = p.ny, N = p.nz;
 
-    constexpr int WARM = 3, DELAY = 1;
-    const int nL = (N + 1) >> 1;
-    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, nL);
+    // the slice schedule of k_vol_z: forward pairs (2m+1, 2m+2) after a seed slice 2 m0, inverse pairs (2k, 2k+1)
+    constexpr int WARM = INV ? 4 : 3, DELAY = 1;
+    const int units = INV ? (N >> 1) + 1 : (N + 1) >> 1;
+    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, units);
     if (k0 >= k1) return;
     const int m0 = k0 + DELAY - WARM, m1 = k1 - 1 + DELAY;
-    const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + 1;   // slices zfirst .. zfirst + nsl - 1 (mirrored into the volume)
+    const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + (INV ? 0 : 1);   // slices zfirst .. zfirst + nsl - 1 (mirrored into the volume)
 
     // staging: groups of four columns; a thread copies the same (up to three) groups of every slice, so their offsets are
     // computed once.  goff < 0: the group straddles the volume's edge and is copied element by element through the mirror.
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParam
     float *out = p.dst + (int64_t)(y0 + 8 * ps) * p.d_pitch + x0 + px;
     const int dp = (int)p.d_pitch;
     auto put = [&](int z, const T(&o)[8]) {
-        if (z >= N) return;
+        if (z < 0 || z >= N) return;
         float *q = out + (int64_t)z * p.d_slice;
         if (rows_ok == 8) {
 #pragma unroll
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParam
                 const float4 q4 = src4[j];
                 w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
             }
-            window_fwd_p<WV, 8>(w, L, H);
+            if constexpr (INV) window_inv_p<WV, 8>(w, L, H);
+            else window_fwd_p<WV, 8>(w, L, H);
             float4 *dst4 = reinterpret_cast<float4 *>(xb + xr * V3_XP + 16 * xsg);
 #pragma unroll
             for (int j = 0; j < 4; j++) dst4[j] = make_float4(L[2 * j], H[2 * j], L[2 * j + 1], H[2 * j + 1]);
@@ -345,7 +347,8 @@ __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParam
         const float *col = xb + (8 * ps) * V3_XP + px;
 #pragma unroll
         for (int j = 0; j < 16; j++) w[j] = col[j * V3_XP];
-        window_fwd_p<WV, 4>(w, L, H);
+        if constexpr (INV) window_inv_p<WV, 4>(w, L, H);
+        else window_fwd_p<WV, 4>(w, L, H);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             v[2 * j] = L[j];
@@ -355,30 +358,46 @@ __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3_fwd(const VolParam
 
     issue(0);
     issue(1);
-    xy(0, st[0]);   // z: the register pipeline of k_vol_z -- slice 0 of the sequence seeds st[0], then pairs (2m+1, 2m+2)
-    for (int q = 0; q < npairs; q++) {
-        T a[8], b[8], oL[8], oH[8];
-        xy(2 * q + 1, a);
-        xy(2 * q + 2, b);
-        vfwd<WV, 8>(a, b, st, oL, oH);
-        const int kk = m0 + q - DELAY;
-        if (kk >= k0) {
-            put(2 * kk, oL);
-            put(2 * kk + 1, oH);
+    if constexpr (!INV) {
+        xy(0, st[0]);   // z: the register pipeline of k_vol_z -- slice 0 of the sequence seeds st[0], then pairs (2m+1, 2m+2)
+        for (int q = 0; q < npairs; q++) {
+            T a[8], b[8], oL[8], oH[8];
+            xy(2 * q + 1, a);
+            xy(2 * q + 2, b);
+            vfwd<WV, 8>(a, b, st, oL, oH);
+            const int kk = m0 + q - DELAY;
+            if (kk >= k0) {
+                put(2 * kk, oL);
+                put(2 * kk + 1, oH);
+            }
+        }
+    } else {
+        for (int q = 0; q < npairs; q++) {
+            T a[8], b[8], oO[8], oE[8];
+            xy(2 * q, a);
+            xy(2 * q + 1, b);
+            vinv<WV, 8>(a, b, st, oO, oE);
+            const int kk = m0 + q - DELAY;
+            if (kk >= k0) {
+                put(2 * kk - 1, oO);
+                put(2 * kk, oE);
+            }
         }
     }
 }
 
 bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }
-void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st)
+void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st)
 {
     static bool prepared = false;
     if (!prepared) {
-        cudaFuncSetAttribute(k_vol3_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
+        cudaFuncSetAttribute(k_vol3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
+        cudaFuncSetAttribute(k_vol3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         prepared = true;
     }
     const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
-    const int units = (p.nz + 1) >> 1;
+    const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
+    const double warm = inverse ? 4.0 : 3.0;
     // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
     int best = 1;
     double best_cost = 1e30;
@@ -391,7 +410,7 @@ void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st)
         // same time; several waves of shorter ranges drift apart and overlap each other's phases (measured: 768^3 in one wave of
         // 288 CTAs 1.50 ms, 1024^3 in seven waves at the same per-voxel cost 2.54 ms;
         // delaying the second CTA of every SM by a microsecond at its start changes nothing once there are several waves)
-        const double cost = (1.0 + 3.0 / pps) * (double)(waves * slots) / (double)n * (waves < 3 ? 1.2 : 1.0);
+        const double cost = (1.0 + warm / pps) * (double)(waves * slots) / (double)n * (waves < 3 ? 1.2 : 1.0);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best = zs;
@@ -400,7 +419,8 @@ void launch_vol3_fwd(VolParams p, int sm_count, cudaStream_t st)
     p.pps = (units + best - 1) / best;
     p.nstrips = (units + p.pps - 1) / p.pps;
     const dim3 grid(tx, ty, p.nstrips);
-    k_vol3_fwd<<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+    if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+    else k_vol3<false><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
 }
 
 static int pick_pps(int units, int64_t other_warps, int sm_count)

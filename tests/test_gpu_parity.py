@@ -394,8 +394,8 @@ def test_volume_parity(dev, oracle, shape):
 
 @pytest.mark.parametrize("shape", [(128, 32, 16), (129, 33, 17), (300, 100, 31), (520, 300, 70), (1000, 64, 40), (131, 200, 130)],
                          ids=lambda s: "x".join(map(str, s)))
-def test_volume_single_pass_forward(dev, oracle, shape):
-    """k_vol3_fwd (x, y and z lifting in ONE pass: tiles of 128 x 32 positions marching along z) on seeded noise against the
+def test_volume_single_pass(dev, oracle, shape):
+    """k_vol3 (x, y and z lifting in ONE pass: tiles of 128 x 32 positions marching along z) on seeded noise against the
     oracle, and the two-pass kernels (DWTB200_TUNE_VOL3 = 0) must give the same bits"""
     nx, ny, nz = shape
     rng = np.random.default_rng(nx * 7 + nz)
@@ -412,6 +412,19 @@ def test_volume_single_pass_forward(dev, oracle, shape):
             L.check(L.c.dwtb200_set_tuning(9, 1))
         bad = got.view(np.uint32) != want.view(np.uint32)
         assert not bad.any(), f"vol3={vol3}: {bad.sum()} voxels differ, first at {np.argwhere(bad)[0]}"
+    # inverse of seeded noise (any coefficients will do): one pass, two passes, oracle
+    c = (rng.standard_normal((nz, ny, nx)) * 10.0 ** rng.integers(-2, 3, size=(nz, ny, nx))).astype(np.float32)
+    want = c.copy()
+    oracle.inv3(want)
+    for vol3 in (1, 0):
+        L.check(L.c.dwtb200_set_tuning(9, vol3))
+        try:
+            got = c.copy()
+            dev.inv3(got)
+        finally:
+            L.check(L.c.dwtb200_set_tuning(9, 1))
+        bad = got.view(np.uint32) != want.view(np.uint32)
+        assert not bad.any(), f"inverse vol3={vol3}: {bad.sum()} voxels differ, first at {np.argwhere(bad)[0]}"
 
 
 # ---- row strips: all ranks emulated on one GPU (the multi-process driver is covered on CPU with gloo) ----
