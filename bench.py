@@ -302,6 +302,32 @@ def run_ours(args):
                 for im in ims:
                     im.close()
 
+    # ---- 3-D, one level, 1024^3 float (BASELINE config 5b): cdf97_3f_op_sep_horizontal_s / cdf97_3i_ip_sep_horizontal_s ----
+    volume = None
+    if rank == 0 and world == 1:
+        try:
+            n = 1024
+            v = d.DeviceVolume(n, n, n)
+            v.fill()
+            v.fwd3(); v.inv3()
+            L.check(L.c.dwtb200_sync())
+            reps = 5
+            L.check(L.c.dwtb200_timer_start())
+            for _ in range(reps):
+                v.fwd3()
+            tf = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
+            L.check(L.c.dwtb200_timer_start())
+            for _ in range(reps):
+                v.inv3()
+            ti = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
+            v.close()
+            b = 2 * 4 * n ** 3   # every voxel read once and written once
+            volume = {"workload": f"{n}^3 float volume, one level, forward / inverse, device-resident", "fwd_ms": tf * 1e3, "inv_ms": ti * 1e3,
+                      "fwd_gvoxel_s": n ** 3 / tf / 1e9, "inv_gvoxel_s": n ** 3 / ti / 1e9,
+                      "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
+        except Exception as e:
+            volume = {"skipped": str(e)}
+
     # ---- one image far larger than L2 and than the launch overheads: BASELINE config 5a on a single GPU ----
     large = None
     if rank == 0 and world == 1 and not args.no_large:
@@ -415,7 +441,7 @@ def run_ours(args):
                        "l2": "each batch is M x 256 MiB per plane (>> 126 MB L2): inputs larger than L2",
                        "sharding": "independent frames per GPU, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
-            "breakdown": breakdown, "inplace_family": inplace, "large_image": large,
+            "breakdown": breakdown, "inplace_family": inplace, "volume": volume, "large_image": large,
         }
         print(json.dumps(line))
     if world > 1:

@@ -10,6 +10,7 @@
 //              -> blockIdx.y = z; subbands stay interleaved, so rows are stored where they were read
 //   k_vol_z    z lifting: a warp owns 32*VPL columns of one row y and streams through a strip of slice
 //              pairs with the same register pipeline (no horizontal dependency -> no halo lanes)
+//   k_vol3     volumes of at least 64 x 32 x 16: all three axes in ONE pass (tiles marching along z, see below)
 // Two passes over the volume (4*S bytes) instead of three; both directions apply x, then y, then z like
 // the reference (the inverse is NOT the mirrored order there either), so results are bit-identical.
 #include "stream_common.cuh"
@@ -386,7 +387,7 @@ template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol
     }
 }
 
-bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }
+bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }   // at least one full tile
 void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st)
 {
     static bool prepared = false;
