@@ -146,6 +146,12 @@ int dwtb200_image_subband(dwtb200_image *img, int frame, int size_i_big_x, int s
  * feature reductions (dwt_util_wps_s, _var_s, _norm_s ..., src/libdwt.c:23086-23786) without a device-to-host copy */
 int dwtb200_image_subband_moments(dwtb200_image *img, int frame, int size_i_big_x, int size_i_big_y, int j, int band, double *sum,
                                   double *sum_sq, double *max_abs);
+/* the reference's per-subband feature vectors on a device-resident Mallat plane: dwt_util_wps_s, dwt_util_mean_s, dwt_util_var_s,
+ * dwt_util_stdev_s, dwt_util_maxnorm_s, dwt_util_norm_s (src/libdwt.h; src/libdwt.c:23201, 23515, 23549, 23583, 23686, 23754): one
+ * value per non-empty HL, LH, HH band of the levels j = 1 .. j_max - 1, in that order; *count receives their number.  Sums are
+ * accumulated in double on the device (the reference sums sequentially in float), only the feature vector crosses PCIe. */
+enum { DWTB200_FEAT_WPS = 0, DWTB200_FEAT_MEAN = 1, DWTB200_FEAT_VAR = 2, DWTB200_FEAT_STDEV = 3, DWTB200_FEAT_MAXNORM = 4, DWTB200_FEAT_NORM = 5 };
+int dwtb200_image_features(dwtb200_image *img, int frame, int size_i_big_x, int size_i_big_y, int j_max, int feature, float *fv, int *count);
 /* bit-exact comparison of the current planes of two images on the device: number of differing samples */
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b);
 /* max |a-b| over the current planes (float/double kinds), cf. dwt_util_compare_s (src/libdwt.c:1593) */

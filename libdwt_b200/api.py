@@ -48,6 +48,7 @@ SYMBOLS = [
     ("dwtb200_image_devptr", _vp, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     ("dwtb200_image_subband", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_sz), _ip, _ip]),
     ("dwtb200_image_subband_moments", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl)]),
+    ("dwtb200_image_features", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _ip]),
     ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
     ("dwtb200_image_copy", _i, [_vp, _vp]),
     ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
@@ -347,6 +348,16 @@ class DeviceImage:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self.L.check(self.L.c.dwtb200_image_subband_moments(self.h, frame, ix, iy, j, band, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    FEATURES = {"wps": 0, "mean": 1, "var": 2, "stdev": 3, "maxnorm": 4, "norm": 5}
+
+    def features(self, j_max, feature, frame=0, inner=None):
+        """dwt_util_wps_s / _mean_s / _var_s / _stdev_s / _maxnorm_s / _norm_s of the device-resident Mallat plane: numpy float32 vector."""
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        fv = (C.c_float * (3 * max(j_max, 1)))()
+        n = C.c_int()
+        self.L.check(self.L.c.dwtb200_image_features(self.h, frame, ix, iy, j_max, self.FEATURES[feature], fv, C.byref(n)))
+        return np.array(fv[:n.value], dtype=np.float32)
 
     def diff(self, other):
         r = self.L.c.dwtb200_image_diff(self.h, other.h)

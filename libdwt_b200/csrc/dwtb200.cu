@@ -1200,6 +1200,41 @@ int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompo
     return transform(im, true, ix, iy, J, zero_padding);
 }
 
+// The per-subband feature vectors of the reference (dwt_util_wps_s, _mean_s, _var_s, _stdev_s, _maxnorm_s, _norm_s:
+// src/libdwt.c:23201, 23515, 23549, 23583, 23686, 23754; band functions :23086-23480) for a device-resident Mallat plane:
+// levels j = 1 .. j_max - 1 (the reference's loop bound), bands HL, LH, HH of each, skipping empty bands.  The reference
+// accumulates sequentially in float; here the sums come from the double-precision device reduction.
+int dwtb200_image_features(dwtb200_image *im, int frame, int ix, int iy, int j_max, int feature, float *fv, int *count)
+{
+    NEED_DEV();
+    if (!im || !fv || feature < 0 || feature > DWTB200_FEAT_NORM) return fail(DWTB200_EINVAL, "image_features: bad arguments");
+    int n = 0;
+    for (int j = 1; j < j_max; j++)
+        for (int band = 1; band <= 3; band++) {   // DWT_HL, DWT_LH, DWT_HH
+            int sx = 0, sy = 0;
+            void *p = nullptr;
+            int r = dwtb200_image_subband(im, frame, ix, iy, j, band, &p, nullptr, &sx, &sy);
+            if (r) return r;
+            if (!sx || !sy) continue;
+            double sum = 0, sq = 0, mx = 0;
+            r = dwtb200_image_subband_moments(im, frame, ix, iy, j, band, &sum, &sq, &mx);
+            if (r) return r;
+            const double cnt = (double)sx * sy, mean = sum / cnt;
+            double v = 0;
+            switch (feature) {
+            case DWTB200_FEAT_WPS: v = sq / (double)((int64_t)1 << j); break;      // :23112 rectification by 2^j
+            case DWTB200_FEAT_MEAN: v = mean; break;
+            case DWTB200_FEAT_VAR: v = std::max(sq / cnt - mean * mean, 0.0); break;   // second central moment (:23349)
+            case DWTB200_FEAT_STDEV: v = sqrt(std::max(sq / cnt - mean * mean, 0.0)); break;
+            case DWTB200_FEAT_MAXNORM: v = mx; break;
+            default: v = sqrt(sq); break;                                           // l2 norm (:23470)
+            }
+            fv[n++] = (float)v;
+        }
+    if (count) *count = n;
+    return DWTB200_OK;
+}
+
 // =====================================================================================================
 // interleaved in-place family (src/libdwt.c:12926, 13485, 13641, 14847, 17474, 16553, 17886; kernels_inplace.cu)
 // =====================================================================================================

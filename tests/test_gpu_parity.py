@@ -537,6 +537,48 @@ def test_device_resident_subband_views_and_moments(dev, oracle):
         img.close()
 
 
+def test_device_resident_feature_vectors(dev, oracle):
+    """dwt_util_wps_s / _mean_s / _var_s / _stdev_s / _maxnorm_s / _norm_s (src/libdwt.c:23201-23786) on the device-resident Mallat
+    plane against the same formulas in double on the oracle's coefficients (1e-6 relative; the reference itself sums sequentially in
+    float and is compared where oracle/_ref travels: 2e-3 relative on 517 x 301, sizes it can still sum accurately)"""
+    import ctypes as C
+    from oracle.orc import Ref
+    ox, oy = 517, 301
+    a = oracle.fill(np.zeros((oy, ox), np.float32), "s")
+    J = oracle.fwd2(a, "97", "s")
+    img = dev.DeviceImage(dev.kind_of("97", "s"), ox, oy)
+    img.fill(0, 0, 0)
+    assert img.fwd2() == J
+    ref = Ref() if Ref.available() else None
+    names = {"wps": "dwt_util_wps_s", "mean": "dwt_util_mean_s", "var": "dwt_util_var_s", "stdev": "dwt_util_stdev_s",
+             "maxnorm": "dwt_util_maxnorm_s", "norm": "dwt_util_norm_s"}
+    for feat, cname in names.items():
+        got = img.features(J, feat)
+        want = []
+        for j in range(1, J):
+            lx, ly, hx, hy, cx, cy = ox, oy, 0, 0, ox, oy
+            for _ in range(j):
+                hx, hy, lx, ly, cx, cy = lx // 2, ly // 2, (lx + 1) // 2, (ly + 1) // 2, (cx + 1) // 2, (cy + 1) // 2
+            for (r0, c0, sy, sx) in ((0, cx, ly, hx), (cy, 0, hy, lx), (cy, cx, hy, hx)):
+                if not sx or not sy:
+                    continue
+                b = a[r0:r0 + sy, c0:c0 + sx].astype(np.float64)
+                want.append({"wps": (b * b).sum() / 2 ** j, "mean": b.mean(), "var": b.var(), "stdev": b.std(), "maxnorm": np.abs(b).max(),
+                             "norm": np.sqrt((b * b).sum())}[feat])
+        want = np.array(want)
+        assert got.shape == want.shape, (feat, got.shape, want.shape)
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-9), (feat, np.abs(got - want).max())
+        if ref is not None:
+            f = getattr(ref.lib, cname)
+            f.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.POINTER(C.c_float)]
+            f.restype = None
+            fv = (C.c_float * (3 * J))()
+            f(a.ctypes.data, a.strides[0], a.strides[1], ox, oy, ox, oy, J, fv)
+            rv = np.array(fv[:len(got)], dtype=np.float64)
+            assert np.allclose(got, rv, rtol=2e-3, atol=1e-6), (feat, "vs reference", np.abs(got - rv).max())
+    img.close()
+
+
 # ---- seeded random inputs (the reference's patterns are smooth: these are not) -------------------------------------
 @pytest.mark.parametrize("kind", KINDS, ids=KIDS)
 def test_random_inputs(dev, oracle, kind):
