@@ -381,20 +381,20 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
                 bulk_g2s(d0 + rs.slot * SLOTB + 2 * SEGB, il + (int64_t)reflect(2 * k + 1, H) * p.il_pitch, nb, fb);
                 rs.next();
             }
-            return;
-        }
-        for (int q = 0; q < nitems; q++) {
-            if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
-            const uint32_t d = dst0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
-            const int k = ka + q;
-            const int ra = reflect(2 * k, H) >> 1, rb = reflect(2 * k + 1, H) >> 1;
-            if (dep) win.need_row(p.chain, gen, blockIdx.y, ra);   // only the LL band is produced inside this transform
-            mbar_expect_tx(fb, nll + nh + nlh + nh);
-            bulk_g2s(d, ll + (int64_t)ra * p.ll_pitch, nll, fb);
-            bulk_g2s(d + SEGB, hl + (int64_t)ra * p.sub_pitch, nh, fb);
-            bulk_g2s(d + 2 * SEGB, lh + (int64_t)rb * p.sub_pitch, nlh, fb);
-            bulk_g2s(d + 3 * SEGB, hh + (int64_t)rb * p.sub_pitch, nh, fb);
-            rs.next();
+        } else {
+            for (int q = 0; q < nitems; q++) {
+                if (q >= RING_SLOTS) mbar_wait(empty + 8 * rs.slot, rs.phase ^ 1);
+                const uint32_t d = dst0 + rs.slot * CFG::SLOTB, fb = full + 8 * rs.slot;
+                const int k = ka + q;
+                const int ra = reflect(2 * k, H) >> 1, rb = reflect(2 * k + 1, H) >> 1;
+                if (dep) win.need_row(p.chain, gen, blockIdx.y, ra);   // only the LL band is produced inside this transform
+                mbar_expect_tx(fb, nll + nh + nlh + nh);
+                bulk_g2s(d, ll + (int64_t)ra * p.ll_pitch, nll, fb);
+                bulk_g2s(d + SEGB, hl + (int64_t)ra * p.sub_pitch, nh, fb);
+                bulk_g2s(d + 2 * SEGB, lh + (int64_t)rb * p.sub_pitch, nlh, fb);
+                bulk_g2s(d + 3 * SEGB, hh + (int64_t)rb * p.sub_pitch, nh, fb);
+                rs.next();
+            }
         }
         return;
     }
