@@ -40,7 +40,8 @@ template <class WV> __global__ void __launch_bounds__(TAIL_THREADS) k_inv_tail(c
     using T = typename WV::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     chain_begin(p.chain);   // first kernel of an inverse chain: its input is complete at launch
-    inv_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc());
+    inv_tail_body<WV>(p, blockIdx.x, reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + TAIL_BUF_BYTES), LdNc(),
+                      reinterpret_cast<T *>(smem_raw + 2 * TAIL_BUF_BYTES));
     if (p.chain.gen) {
         __syncthreads();
         if (threadIdx.x == 0) chain_signal(p.chain, blockIdx.x, 0);
@@ -51,11 +52,11 @@ int tail_max_elems(int kind) { return TAIL_CAP_BYTES / kind_elem_size(kind); }
 
 // Kernels are loaded lazily by the CUDA runtime; loading (and cudaFuncSetAttribute) is not allowed while
 // a stream is being captured, so dwtb200_init() calls this once before any graph is built.
-template <class K> static cudaError_t prep(K kern)
+template <class K> static cudaError_t prep(K kern, int bufs)
 {
     cudaFuncAttributes a;
     cudaError_t e = cudaFuncGetAttributes(&a, kern);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TAIL_BUF_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bufs * TAIL_BUF_BYTES);
     return e;
 }
 cudaError_t preload_tail()
@@ -64,8 +65,8 @@ cudaError_t preload_tail()
     for (int kind = 0; kind < K_COUNT; kind++)
         dispatch_kind(kind, [&](auto wv) {
             using WV = decltype(wv);
-            if (e == cudaSuccess) e = prep(k_fwd_tail<WV>);
-            if (e == cudaSuccess) e = prep(k_inv_tail<WV>);
+            if (e == cudaSuccess) e = prep(k_fwd_tail<WV>, 2);
+            if (e == cudaSuccess) e = prep(k_inv_tail<WV>, 3);   // third buffer: the staged Mallat block
         });
     return e;
 }
@@ -76,7 +77,7 @@ void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 }
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st)
 {
-    const size_t sm = 2 * TAIL_BUF_BYTES;
+    const size_t sm = 3 * TAIL_BUF_BYTES;
     dispatch_kind(kind, [&](auto wv) { launch_pdl(k_inv_tail<decltype(wv)>, dim3(frames), dim3(TAIL_THREADS), sm, st, p.chain.pdl, p); });
 }
 

@@ -174,17 +174,28 @@ template <class WV, int P, class TAP, class EMIT> __device__ __forceinline__ voi
     for (int i = 0; i < P; i++) emit(k + i, E[i], O[i]);
 }
 
-template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, typename WV::T *bufA, typename WV::T *bufB, LD ld)
+// `mal` != nullptr: a third shared-memory buffer that receives the whole Mallat block of the tail (all its subbands, w0 x h0 samples
+// in the top left corner of the plane) in ONE load phase at the start, instead of one dependent round trip to L2 per level
+template <class WV, class LD>
+__device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, typename WV::T *bufA, typename WV::T *bufB, LD ld,
+                                              typename WV::T *mal = nullptr)
 {
     using T = typename WV::T;
     const T *src = (const T *)p.src + (int64_t)frame * p.src_frame;
     T *dst = (T *)p.dst + (int64_t)frame * p.dst_frame;
     const int tid = threadIdx.x;
     const int TAIL_THREADS = blockDim.x;
+    const int w0 = cdiv_pow2(p.W0, p.j0), pm = tail_pitch(w0);
+    if (mal) {
+        const int h0 = cdiv_pow2(p.H0, p.j0);
+        for (int t = tid; t < w0 * h0; t += TAIL_THREADS) mal[(t / w0) * pm + (t % w0)] = ld(src + (int64_t)(t / w0) * p.src_pitch + (t % w0));
+        __syncthreads();
+    }
 
     {   // coarsest LL band
         const int w = cdiv_pow2(p.W0, p.j1), h = cdiv_pow2(p.H0, p.j1);
-        for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[(t / w) * tail_pitch(w) + (t % w)] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
+        for (int t = tid; t < w * h; t += TAIL_THREADS)
+            bufA[(t / w) * tail_pitch(w) + (t % w)] = mal ? mal[(t / w) * pm + (t % w)] : ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
     }
     T *in = bufA, *tmp = bufB;
     __syncthreads();
@@ -195,7 +206,7 @@ template <class WV, class LD> __device__ __forceinline__ void inv_tail_body(cons
         const int pw = tail_pitch(w), pl = tail_pitch(nlx);   // pitches of the band being reconstructed and of the LL band
         // Mallat-arranged input of this level: LL from shared memory, the rest from the plane
         auto M = [&](int y, int x) -> T {
-            return (y < nly && x < nlx) ? in[y * pl + x] : ld(src + (int64_t)y * p.src_pitch + x);
+            return (y < nly && x < nlx) ? in[y * pl + x] : (mal ? mal[y * pm + x] : ld(src + (int64_t)y * p.src_pitch + x));
         };
         const bool do_rows = !(WV::GUARD && w <= 1), do_cols = !(WV::GUARD && h <= 1);
         if constexpr (!WV::INV_COLS_FIRST) {
