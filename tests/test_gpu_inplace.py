@@ -294,3 +294,30 @@ def test_inplace_beyond_2g_bytes(dev):
     back = img.download()
     assert float(np.abs(back - x0).max()) < 1e-4
     img.close()
+
+
+@pytest.mark.parametrize("wavelet", ["97", "53"])
+def test_inplace_batch_of_2048_wide_frames(dev, oracle, wavelet):
+    """a batch large enough for the 5-warp x 3-CTA ring shape (rows of 2048 samples split into two bands of five column groups):
+    the interleaved level-0 kernels of that shape, forward and inverse, frames 0, 11 and 23 against the oracle"""
+    ox, oy, frames = 2048, 1100, 24
+    img = dev.DeviceImage(dev.kind_of(wavelet, "s"), ox, oy, frames)
+    img.fill(0, 0, 6)
+    J = img.fwd2_inplace()
+    fails = []
+    for k in (0, 11, 23):
+        want = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=k % 6)
+        oracle.fwd2_inplace(want, wavelet)
+        got = img.download(frame=k)
+        if not (bits(got, "s") == bits(want, "s")).all():
+            fails.append(f"frame {k} forward: " + describe_mismatch(got, want, "s"))
+    img.inv2_inplace(J)
+    for k in (0, 11, 23):
+        want = oracle.fill(np.zeros((oy, ox), np.float32), "s", rand=k % 6)
+        oracle.fwd2_inplace(want, wavelet)
+        oracle.inv2_inplace(want, wavelet, j_max=J)
+        got = img.download(frame=k)
+        if not (bits(got, "s") == bits(want, "s")).all():
+            fails.append(f"frame {k} inverse: " + describe_mismatch(got, want, "s"))
+    img.close()
+    report(fails)
