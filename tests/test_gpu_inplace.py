@@ -153,10 +153,12 @@ def test_inplace_interleaved_level0_path(dev, oracle, wavelet):
     rng = np.random.default_rng(99)
     fails = []
     L = dev.lib()
-    for ring in (3, 0):
+    # ring = 3: default CTA shape; 0: register kernels, whole plane translated; bits 4-6 force a shape: 15 consumer warps x 1 CTA per SM
+    # (interleaved level 0 with a 217 KB five-segment inverse ring), 8 x 2 (no room for the fifth segment: falls back to full translation)
+    for ring in (3, 0, 3 | (1 << 4), 3 | (2 << 4)):
         L.check(L.c.dwtb200_set_tuning(6, ring))
         try:
-            for (oy, ox) in ((1301, 2101), (2047, 1031), (1500, 1501), (1056, 1000), (40, 30000)):
+            for (oy, ox) in ((1301, 2101), (2047, 1031), (1500, 1501), (1056, 1000), (40, 30000)) if ring in (3, 0) else ((1301, 2101), (1056, 1000)):
                 for j in (1, 2, -1):
                     a = (rng.standard_normal((oy, ox)) * 10.0 ** rng.integers(-2, 3, size=(oy, ox))).astype(np.float32)
                     fails += both(dev, oracle, wavelet, a, j, 0, tag=f"ring={ring}")
