@@ -276,88 +276,6 @@ def run_ours(args):
         for im in singles:
             im.close()
 
-    # ---- the interleaved in-place family (dwt_cdf97_2f_inplace_s / dwt_cdf53_2f_inplace_s, SURVEY.md section 8f rank 2) on the same
-    # shape: one image at a time and the batch of M, same byte accounting (the layout translation is overhead, not algorithmic bytes)
-    inplace = {}
-    if rank == 0 and world == 1:
-        for wname, kind in (("97s", d.CDF97_F32), ("53s", d.CDF53_F32)):
-            for frames in (1, M):
-                ims = [d.DeviceImage(kind, W, H, frames) for _ in range(3 if frames == 1 else 1)]
-                for im in ims:
-                    im.fill(0, 0, 6)
-                    jj = im.fwd2_inplace(); im.inv2_inplace(jj)
-                L.check(L.c.dwtb200_sync())
-                tf = ti = 0.0
-                reps = 5
-                for _ in range(reps):
-                    for im in ims:
-                        L.check(L.c.dwtb200_timer_start())
-                        im.fwd2_inplace()
-                        tf += L.c.dwtb200_timer_stop_ms()
-                    for im in ims:
-                        L.check(L.c.dwtb200_timer_start())
-                        im.inv2_inplace(jj)
-                        ti += L.c.dwtb200_timer_stop_ms()
-                for direction, t in (("fwd", tf), ("inv", ti)):
-                    t = t / (reps * len(ims)) * 1e-3
-                    b = algorithmic_bytes(W, H, jj, 4) * frames
-                    inplace[f"{wname}_{direction}_{'single' if frames == 1 else 'batch%d' % frames}"] = {
-                        "us_per_image": t / frames * 1e6, "gpixel_s": PIX * frames / t / 1e9, "roofline_frac": b / t / 1e9 / peak,
-                        "launches": ims[0].last_launches}
-                for im in ims:
-                    im.close()
-
-    # ---- 3-D, one level, 1024^3 float (BASELINE config 5b): cdf97_3f_op_sep_horizontal_s / cdf97_3i_ip_sep_horizontal_s ----
-    volume = None
-    if rank == 0 and world == 1:
-        try:
-            n = 1024
-            v = d.DeviceVolume(n, n, n)
-            v.fill()
-            v.fwd3(); v.inv3()
-            L.check(L.c.dwtb200_sync())
-            reps = 5
-            L.check(L.c.dwtb200_timer_start())
-            for _ in range(reps):
-                v.fwd3()
-            tf = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
-            L.check(L.c.dwtb200_timer_start())
-            for _ in range(reps):
-                v.inv3()
-            ti = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
-            v.close()
-            b = 2 * 4 * n ** 3   # every voxel read once and written once (SURVEY 8d)
-            volume = {"workload": f"{n}^3 float volume, one level, forward / inverse, device-resident", "fwd_ms": tf * 1e3, "inv_ms": ti * 1e3,
-                      "fwd_gvoxel_s": n ** 3 / tf / 1e9, "inv_gvoxel_s": n ** 3 / ti / 1e9,
-                      "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
-        except Exception as e:
-            volume = {"skipped": str(e)}
-
-    # ---- one image far larger than L2 and than the launch overheads: BASELINE config 5a on a single GPU ----
-    large = None
-    if rank == 0 and world == 1 and not args.no_large:
-        try:
-            n = 32768   # 4 GiB per float plane, 9.3 GiB per image object
-            for k, name, es in kinds:
-                big = d.DeviceImage(k, n, n, 1)
-                big.fill(0, 0, 0)
-                jb = big.fwd2()
-                big.inv2(jb)
-                L.check(L.c.dwtb200_sync())
-                L.check(L.c.dwtb200_timer_start())
-                big.fwd2()
-                tf = L.c.dwtb200_timer_stop_ms() * 1e-3
-                L.check(L.c.dwtb200_timer_start())
-                big.inv2(jb)
-                ti = L.c.dwtb200_timer_stop_ms() * 1e-3
-                big.close()
-                b = algorithmic_bytes(n, n, jb, 4)
-                large = large or {"workload": f"one {n}x{n} image, J={jb}, forward / inverse, device-resident"}
-                large[name] = {"fwd_ms": tf * 1e3, "inv_ms": ti * 1e3, "fwd_gpixel_s": n * n / tf / 1e9, "inv_gpixel_s": n * n / ti / 1e9,
-                               "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
-        except Exception as e:   # not enough memory on a shared GPU: the headline numbers do not depend on this leg
-            large = {"skipped": str(e)}
-
     # ---- roofline of the dominant kernel: level 0 of the forward 9/7 float transform ----
     # one launch = one j_max=1 transform of the batch: reads M 8192^2 planes once, writes their four subbands once
     im = imgs["97s"]
@@ -449,6 +367,91 @@ def run_ours(args):
                "packed_rows": {"value": world * 4 * PIX / res["packed"][0] / 1e9, "ms_per_step": res["packed"][0] * 1e3},
                "what": "dwt_cdf97_2f_s+2i_s and dwt_cdf53_2f_i+2i_i on a pinned host 8192x8192 image (4 transforms), rows at "
                        + ("dwt_util_get_opt_stride" if layout == "opt_stride" else "the packed stride")}
+
+    # (The legs below allocate and free multi-GB buffers.  Measured: right after an 8 GB cudaFree the level-0 kernel of the batch runs
+    # 9 % slower -- 389 instead of 357 us -- until the next large allocation; so the roofline and end-to-end legs above run first, in
+    # the state the timed steps ran in.)
+    # ---- the interleaved in-place family (dwt_cdf97_2f_inplace_s / dwt_cdf53_2f_inplace_s, SURVEY.md section 8f rank 2) on the same
+    # shape: one image at a time and the batch of M, same byte accounting (the layout translation is overhead, not algorithmic bytes)
+    inplace = {}
+    if rank == 0 and world == 1:
+        for wname, kind in (("97s", d.CDF97_F32), ("53s", d.CDF53_F32)):
+            for frames in (1, M):
+                ims = [d.DeviceImage(kind, W, H, frames) for _ in range(3 if frames == 1 else 1)]
+                for im in ims:
+                    im.fill(0, 0, 6)
+                    jj = im.fwd2_inplace(); im.inv2_inplace(jj)
+                L.check(L.c.dwtb200_sync())
+                tf = ti = 0.0
+                reps = 5
+                for _ in range(reps):
+                    for im in ims:
+                        L.check(L.c.dwtb200_timer_start())
+                        im.fwd2_inplace()
+                        tf += L.c.dwtb200_timer_stop_ms()
+                    for im in ims:
+                        L.check(L.c.dwtb200_timer_start())
+                        im.inv2_inplace(jj)
+                        ti += L.c.dwtb200_timer_stop_ms()
+                for direction, t in (("fwd", tf), ("inv", ti)):
+                    t = t / (reps * len(ims)) * 1e-3
+                    b = algorithmic_bytes(W, H, jj, 4) * frames
+                    inplace[f"{wname}_{direction}_{'single' if frames == 1 else 'batch%d' % frames}"] = {
+                        "us_per_image": t / frames * 1e6, "gpixel_s": PIX * frames / t / 1e9, "roofline_frac": b / t / 1e9 / peak,
+                        "launches": ims[0].last_launches}
+                for im in ims:
+                    im.close()
+
+    # ---- 3-D, one level, 1024^3 float (BASELINE config 5b): cdf97_3f_op_sep_horizontal_s / cdf97_3i_ip_sep_horizontal_s ----
+    volume = None
+    if rank == 0 and world == 1:
+        try:
+            n = 1024
+            v = d.DeviceVolume(n, n, n)
+            v.fill()
+            v.fwd3(); v.inv3()
+            L.check(L.c.dwtb200_sync())
+            reps = 5
+            L.check(L.c.dwtb200_timer_start())
+            for _ in range(reps):
+                v.fwd3()
+            tf = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
+            L.check(L.c.dwtb200_timer_start())
+            for _ in range(reps):
+                v.inv3()
+            ti = L.c.dwtb200_timer_stop_ms() / reps * 1e-3
+            v.close()
+            b = 2 * 4 * n ** 3   # every voxel read once and written once (SURVEY 8d)
+            volume = {"workload": f"{n}^3 float volume, one level, forward / inverse, device-resident", "fwd_ms": tf * 1e3, "inv_ms": ti * 1e3,
+                      "fwd_gvoxel_s": n ** 3 / tf / 1e9, "inv_gvoxel_s": n ** 3 / ti / 1e9,
+                      "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
+        except Exception as e:
+            volume = {"skipped": str(e)}
+
+    # ---- one image far larger than L2 and than the launch overheads: BASELINE config 5a on a single GPU ----
+    large = None
+    if rank == 0 and world == 1 and not args.no_large:
+        try:
+            n = 32768   # 4 GiB per float plane, 9.3 GiB per image object
+            for k, name, es in kinds:
+                big = d.DeviceImage(k, n, n, 1)
+                big.fill(0, 0, 0)
+                jb = big.fwd2()
+                big.inv2(jb)
+                L.check(L.c.dwtb200_sync())
+                L.check(L.c.dwtb200_timer_start())
+                big.fwd2()
+                tf = L.c.dwtb200_timer_stop_ms() * 1e-3
+                L.check(L.c.dwtb200_timer_start())
+                big.inv2(jb)
+                ti = L.c.dwtb200_timer_stop_ms() * 1e-3
+                big.close()
+                b = algorithmic_bytes(n, n, jb, 4)
+                large = large or {"workload": f"one {n}x{n} image, J={jb}, forward / inverse, device-resident"}
+                large[name] = {"fwd_ms": tf * 1e3, "inv_ms": ti * 1e3, "fwd_gpixel_s": n * n / tf / 1e9, "inv_gpixel_s": n * n / ti / 1e9,
+                               "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
+        except Exception as e:   # not enough memory on a shared GPU: the headline numbers do not depend on this leg
+            large = {"skipped": str(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
