@@ -1,13 +1,14 @@
 # Builds libdwt_b200/libdwtb200.so (CUDA kernels + C ABI, sm_100a only) and the checkers under oracle/.
 NVCC ?= nvcc
 ARCH  = -gencode arch=compute_100a,code=sm_100a
-NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v
+# DEBUG_KEYS=1 compiles the measurement-only tuning keys 96-99 and the no-store / no-arithmetic branches of k_fwd_level in
+NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v $(if $(DEBUG_KEYS),-DDWTB200_DEBUG_KEYS)
 CSRC = libdwt_b200/csrc
 OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_ring.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_tile.o $(CSRC)/kernels_pyr.o $(CSRC)/kernels_inplace.o $(CSRC)/kernels_vol.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/dwtb200.o
 
 all: libdwt_b200/libdwtb200.so libdwt_b200/libdwt_compat.so oracle examples
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/kernels.h $(CSRC)/lifting.cuh $(CSRC)/stream_common.cuh $(CSRC)/tail_body.cuh include/dwtb200.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/dwtb200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(CSRC)/$*.ptxas.log || (cat $(CSRC)/$*.ptxas.log; false)
 
 libdwt_b200/libdwtb200.so: $(OBJS)

@@ -105,55 +105,65 @@ def cpu_impl():
     return Oracle(), "port"
 
 
-def cpu_time_step(impl, threads, reps=1):
-    """One bounded sample: ONE 8192^2 image per type, forward + inverse (4 transforms = 1/M of a step)."""
+def cpu_time_step(impl, threads, images):
+    """One bounded sample: ONE 8192^2 image per type, forward + inverse (4 transforms = 1/M of a step), on pre-filled host images."""
     impl.set_threads(threads)
     secs = {}
-    from oracle.orc import strided_image
-    for (w, t, dt) in (("97", "s", np.float32), ("53", "i", np.int32)):
-        # rows at the reference's own "optimal" (prime-ish) stride where the compiled reference is the baseline: its examples allocate
-        # that way (examples/simple/simple.c: dwt_util_get_opt_stride) and its column passes run about twice as fast as on packed rows
-        row = impl.opt_stride(W * 4) if hasattr(impl, "opt_stride") else W * 4
-        img = strided_image((H, W), t, row)
+    for (w, t) in (("97", "s"), ("53", "i")):
+        img = images[t]
         impl.fill(img, t)
-        best_f = best_i = 1e30
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            j = impl.fwd2(img, w, t)
-            t1 = time.perf_counter()
-            impl.inv2(img, w, t, j_max=j)
-            t2 = time.perf_counter()
-            best_f, best_i = min(best_f, t1 - t0), min(best_i, t2 - t1)
-        secs[w + t + "_fwd"] = best_f
-        secs[w + t + "_inv"] = best_i
+        t0 = time.perf_counter()
+        j = impl.fwd2(img, w, t)
+        t1 = time.perf_counter()
+        impl.inv2(img, w, t, j_max=j)
+        t2 = time.perf_counter()
+        secs[w + t + "_fwd"] = t1 - t0
+        secs[w + t + "_inv"] = t2 - t1
     return secs
+
+
+CPU_SAMPLE = ("1 image of 8192x8192 per type (float32 9/7 + int32 5/3), forward+inverse, J=13 = 4 transforms per step (1/M of a GPU "
+              "step); rows at dwt_util_get_opt_stride (the layout of the reference's examples), all host threads")
+
+
+def cpu_protocol(trials, warmup):
+    """The reference's own measurement protocol (dwt_util_perf_cdf97_2_s, src/libdwt.c:21391-21507: M images, N trials, per direction
+    the minimum over the trials of the mean seconds per transform) with M = 1, on the host cores, after `warmup` untimed trials.
+    The same function serves `--impl reference` and the cpu_baseline leg of the GPU arm."""
+    from oracle.orc import strided_image
+    impl, kind = cpu_impl()
+    threads = os.cpu_count() or 1
+    # rows at the reference's own "optimal" (prime) stride where the compiled reference is the baseline: its examples allocate that way
+    # (examples/simple/simple.c: dwt_util_get_opt_stride) and its column passes run several times faster than on packed rows
+    row = impl.opt_stride(W * 4) if hasattr(impl, "opt_stride") else W * 4
+    images = {t: strided_image((H, W), t, row) for t in ("s", "i")}
+    for _ in range(warmup):
+        cpu_time_step(impl, threads, images)
+    per_trial = [cpu_time_step(impl, threads, images) for _ in range(trials)]
+    keys = list(per_trial[0])
+    best = {k: min(tr[k] for tr in per_trial) for k in keys}          # min over trials of the mean over M = 1 images
+    mean_step = sum(sum(tr.values()) for tr in per_trial) / trials
+    return {"kind": kind, "cores": threads, "trials": trials, "warmup": warmup, "mean_step_s": mean_step,
+            "min_of_means_s": best, "value_min_of_means": 4 * PIX / sum(best.values()) / 1e9, "value_mean": 4 * PIX / mean_step / 1e9}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    impl, kind = cpu_impl()
-    threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_time_step(impl, threads)
-    tot = 0.0
-    last = None
-    for _ in range(args.steps):
-        last = cpu_time_step(impl, threads)
-        tot += sum(last.values())
-    ms = tot / args.steps * 1e3
-    value = 4 * PIX / (ms * 1e-3) / 1e9
-    sample = ("1 image of 8192x8192 per type (float32 9/7 + int32 5/3), forward+inverse, J=13 = 4 transforms per step; rows at "
-              "dwt_util_get_opt_stride (the layout of the reference's examples), all host threads")
+    r = cpu_protocol(args.steps, args.warmup)
+    ms = r["mean_step_s"] * 1e3
+    value = r["value_mean"]
     line = {
         "impl": "reference", "metric": "cdf97_f32+cdf53_i32 fwd+inv throughput, 8192x8192 j=max", "value": value,
-        "unit": "Gpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "unit": "Gpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": "8192x8192 full-depth (J=13) 2-D DWT, CDF 9/7 float32 + CDF 5/3 int32, forward+inverse",
-                   "sample": sample, "pattern": "dwt_util_test_image_fill_{s,i}"},
-        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": threads, "kind": kind, "sample": sample,
-                         "seconds": last},
+                   "sample": CPU_SAMPLE, "pattern": "dwt_util_test_image_fill_{s,i}"},
+        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": r["cores"], "kind": r["kind"], "sample": CPU_SAMPLE,
+                         "protocol": "mean over the timed steps (= the line's value); min over the steps of the per-direction times, the "
+                                     "reference's own perf protocol (src/libdwt.c:21473-21507), in value_min_of_means",
+                         "value_min_of_means": r["value_min_of_means"], "seconds_min_of_means": r["min_of_means_s"]},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -455,11 +465,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        impl, kind = cpu_impl()
-        threads = os.cpu_count() or 1
-        secs = cpu_time_step(impl, threads)
-        cpu = {"value": 4 * PIX / sum(secs.values()) / 1e9, "unit": "Gpixel/s", "cores": threads, "kind": kind,
-               "sample": "1 image of 8192x8192 per type, forward+inverse, J=13 (4 transforms = 1/M of a GPU step); rows at dwt_util_get_opt_stride, all host threads", "seconds": secs}
+        r = cpu_protocol(5, 1)   # the protocol of `--impl reference`: 1 warm-up, 5 trials
+        cpu = {"value": r["value_mean"], "unit": "Gpixel/s", "cores": r["cores"], "kind": r["kind"], "sample": CPU_SAMPLE,
+               "protocol": "1 untimed warm-up + 5 trials, mean over the trials (same function as --impl reference); the reference's own "
+                           "min-of-means protocol (src/libdwt.c:21473-21507) in value_min_of_means",
+               "value_min_of_means": r["value_min_of_means"], "seconds_min_of_means": r["min_of_means_s"]}
 
     if rank == 0:
         line = {

@@ -14,7 +14,10 @@
  *   - functions return 0 on success, a negative DWTB200_E* code otherwise; dwtb200_last_error()
  *     describes the failure.  There is no CPU fallback: without a usable CUDA device every compute
  *     entry point fails with DWTB200_ENODEV.
- *   - not re-entrant, like the reference (process-global state, src/libdwt.c:478-756).
+ *   - threading: the library keeps process-global state like the reference (src/libdwt.c:478-756), but unlike the
+ *     reference every entry point below takes one process-wide (recursive) lock, so calls from several host threads
+ *     are safe and are serialised; device work of different images still overlaps (each image owns a stream).
+ *     One process drives one GPU; use one process per GPU (LOCAL_RANK) for several.
  */
 #ifndef DWTB200_H
 #define DWTB200_H
@@ -112,7 +115,9 @@ void dwtb200_release_host_cache(void);
 typedef struct dwtb200_image dwtb200_image;
 dwtb200_image *dwtb200_image_create(int kind, int size_o_big_x, int size_o_big_y, int frames);
 void dwtb200_image_destroy(dwtb200_image *img);
-/* host <-> device, one frame; arbitrary byte strides (dwt_util_memcpy_stride_*, src/system.c:90-180) */
+/* host <-> device, one frame; arbitrary byte strides (dwt_util_memcpy_stride_*, src/system.c:90-180).
+ * upload is ASYNCHRONOUS: it enqueues the copy on the image's stream and returns; a pinned `host` buffer must stay
+ * valid and unmodified until dwtb200_sync() or a download of the same image returns.  download synchronises. */
 int dwtb200_image_upload(dwtb200_image *img, int frame, const void *host, int64_t stride_x, int64_t stride_y);
 int dwtb200_image_download(dwtb200_image *img, int frame, void *host, int64_t stride_x, int64_t stride_y);
 /* dwt_util_test_image_fill{,2}_{s,d,i} on the device (src/libdwt.c:1247-1385); frame k uses
@@ -199,6 +204,7 @@ int dwtb200_inv3_host(void *vol, size_t stride_x, size_t stride_y, size_t stride
 typedef struct dwtb200_volume dwtb200_volume;
 dwtb200_volume *dwtb200_volume_create(int size_x, int size_y, int size_z);
 void dwtb200_volume_destroy(dwtb200_volume *v);
+/* upload is asynchronous like dwtb200_image_upload; download synchronises */
 int dwtb200_volume_upload(dwtb200_volume *v, const void *host, size_t stride_x, size_t stride_y, size_t stride_z);
 int dwtb200_volume_download(dwtb200_volume *v, void *host, size_t stride_x, size_t stride_y, size_t stride_z);
 int dwtb200_volume_fill(dwtb200_volume *v);   /* volume_fill_s, src/volume.c:41 */

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <tuple>
 #include <algorithm>
@@ -80,6 +81,12 @@ struct Ctx {
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
+
+// Threading contract (include/dwtb200.h): every extern "C" entry point takes this process-wide lock, so concurrent callers
+// (an OpenMP loop over images around dwt_cdf97_2f_s, say) are serialised instead of corrupting the shared context --
+// g.st, g.err, the staging buffer, the cached device mirrors of the *_host calls.  Recursive: entry points call each other.
+std::recursive_mutex g_api_mutex;
+#define API_LOCK() std::lock_guard<std::recursive_mutex> api_lock_(g_api_mutex)
 
 int fail(int code, const char *fmt, ...)
 {
@@ -191,6 +198,7 @@ int dwtb200_device_count(void)
 
 int dwtb200_init(int device)
 {
+    API_LOCK();
     if (g.dev >= 0) return DWTB200_OK;
     const int n = dwtb200_device_count();
     if (n <= 0) return fail(DWTB200_ENODEV, "no CUDA device (libdwtb200 has no CPU fallback)");
@@ -227,6 +235,7 @@ int dwtb200_init(int device)
 void dwtb200_release_host_cache(void);
 void dwtb200_finish(void)
 {
+    API_LOCK();
     if (g.dev < 0) return;
     cudaDeviceSynchronize();
     dwtb200_release_host_cache();
@@ -256,6 +265,7 @@ int dwtb200_device(void) { return g.dev; }
 
 void *dwtb200_host_alloc(size_t bytes)
 {
+    API_LOCK();
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
@@ -266,7 +276,14 @@ void *dwtb200_host_alloc(size_t bytes)
 }
 void dwtb200_host_free(void *ptr)
 {
-    if (ptr) cudaFreeHost(ptr);
+    API_LOCK();
+    if (!ptr) return;
+    // the compat layer interposes dwt_util_free_image process-wide: a pointer that did not come from dwtb200_host_alloc
+    // (memalign in the reference's own allocator) goes back to free(), and no CUDA error is left pending
+    if (cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        free(ptr);
+    }
 }
 
 int dwtb200_ceil_log2(int x)
@@ -286,6 +303,7 @@ void dwtb200_force_generic(int on) { g.force_generic = on; }
 void dwtb200_set_strip_rows(int rows) { g.strip_rows = rows; }
 int dwtb200_set_tuning(int key, long long value)
 {
+    API_LOCK();
     switch (key) {
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
     case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
@@ -294,10 +312,12 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
     case DWTB200_TUNE_PYR: g.pyr = (int)value; break;
     case DWTB200_TUNE_VOL3: g.vol3 = value != 0; break;
+#ifdef DWTB200_DEBUG_KEYS   // measurement-only knobs (profiles/scripts): not part of the release ABI
     case 96: g.pyr_max_in = value; break;
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
-    case 99: g.dbg = (int)value; break;   // measurement only, see kernels.h
+    case 99: g.dbg = (int)value; break;   // see kernels.h
+#endif
     case DWTB200_TUNE_NARROW: g.narrow = value != 0; break;
     case DWTB200_TUNE_PDL: dwtb200::g_use_pdl = value != 0; break;
     case DWTB200_TUNE_TAIL_MAX:
@@ -315,6 +335,7 @@ int dwtb200_set_tuning(int key, long long value)
 // =====================================================================================================
 dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
 {
+    API_LOCK();
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
     if (!kind_ok(kind) || ox < 1 || oy < 1 || frames < 1) {
         fail(DWTB200_EINVAL, "image_create: bad arguments");
@@ -360,6 +381,7 @@ dwtb200_image *dwtb200_image_create(int kind, int ox, int oy, int frames)
 
 void dwtb200_image_destroy(dwtb200_image *im)
 {
+    API_LOCK();
     if (!im) return;
     if (im->st) cudaStreamSynchronize(im->st);
     g.live.erase(im);
@@ -409,6 +431,7 @@ static int upload_region(dwtb200_image *im, int frame, const void *host, int64_t
 
 int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t sx, int64_t sy)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_upload: bad arguments");
@@ -417,6 +440,7 @@ int dwtb200_image_upload(dwtb200_image *im, int frame, const void *host, int64_t
 
 int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx, int64_t sy)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im || !host || frame < 0 || frame >= im->frames || sx <= 0 || sy <= 0) return fail(DWTB200_EINVAL, "image_download: bad arguments");
@@ -442,6 +466,7 @@ int dwtb200_image_download(dwtb200_image *im, int frame, void *host, int64_t sx,
 
 int dwtb200_image_fill_ex(dwtb200_image *im, int rnd, int type, int rand_mod, int y_offset, int wide)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_fill: null image");
@@ -456,6 +481,7 @@ int dwtb200_image_fill(dwtb200_image *im, int rnd, int type, int rand_mod) { ret
 // the halo rows of a row-strip partition travel through this (peer-mapped pointers included)
 int dwtb200_image_copy_rows(dwtb200_image *im, int frame, int row0, int rows, void *buf, int64_t buf_pitch_bytes, int to_image)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im || !buf || frame < 0 || frame >= im->frames || row0 < 0 || rows < 0 || row0 + rows > im->oy)
@@ -470,6 +496,7 @@ int dwtb200_image_copy_rows(dwtb200_image *im, int frame, int row0, int rows, vo
 // CUDA IPC: let another process on the same node map this image's current plane (NVLink P2P between ranks)
 int dwtb200_image_ipc_export(dwtb200_image *im, void *handle64)
 {
+    API_LOCK();
     NEED_DEV();
     if (!im || !handle64) return fail(DWTB200_EINVAL, "ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
@@ -478,6 +505,7 @@ int dwtb200_image_ipc_export(dwtb200_image *im, void *handle64)
 }
 void *dwtb200_ipc_open(const void *handle64)
 {
+    API_LOCK();
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
     void *p = nullptr;
     cudaIpcMemHandle_t h;
@@ -490,6 +518,7 @@ void *dwtb200_ipc_open(const void *handle64)
 }
 int dwtb200_ipc_close(void *ptr)
 {
+    API_LOCK();
     NEED_DEV();
     CK(cudaIpcCloseMemHandle(ptr));
     return DWTB200_OK;
@@ -497,6 +526,7 @@ int dwtb200_ipc_close(void *ptr)
 
 void *dwtb200_image_devptr(dwtb200_image *im, size_t *pitch_bytes, size_t *frame_bytes)
 {
+    API_LOCK();
     if (!im) return nullptr;
     if (pitch_bytes) *pitch_bytes = (size_t)im->pitch * im->es;
     if (frame_bytes) *frame_bytes = (size_t)im->frame * im->es;
@@ -505,6 +535,7 @@ void *dwtb200_image_devptr(dwtb200_image *im, size_t *pitch_bytes, size_t *frame
 
 int dwtb200_image_copy(dwtb200_image *dst, dwtb200_image *src)
 {
+    API_LOCK();
     NEED_DEV();
     if (!dst || !src || dst->kind != src->kind || dst->ox != src->ox || dst->oy != src->oy || dst->frames != src->frames)
         return fail(DWTB200_EINVAL, "image_copy: shape mismatch");
@@ -1184,6 +1215,7 @@ int transform(dwtb200_image *im, bool inverse, int ix, int iy, int J, int zero_p
 
 int dwtb200_image_fwd2(dwtb200_image *im, int ix, int iy, int *j_max_ptr, int decompose_one, int zero_padding)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im || !j_max_ptr) return fail(DWTB200_EINVAL, "image_fwd2: null argument");
@@ -1193,6 +1225,7 @@ int dwtb200_image_fwd2(dwtb200_image *im, int ix, int iy, int *j_max_ptr, int de
 
 int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompose_one, int zero_padding)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_inv2: null argument");
@@ -1206,6 +1239,7 @@ int dwtb200_image_inv2(dwtb200_image *im, int ix, int iy, int j_max, int decompo
 // accumulates sequentially in float; here the sums come from the double-precision device reduction.
 int dwtb200_image_features(dwtb200_image *im, int frame, int ix, int iy, int j_max, int feature, float *fv, int *count)
 {
+    API_LOCK();
     NEED_DEV();
     if (!im || !fv || feature < 0 || feature > DWTB200_FEAT_NORM) return fail(DWTB200_EINVAL, "image_features: bad arguments");
     int n = 0;
@@ -1520,6 +1554,7 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
 
 int dwtb200_image_fwd2_inplace(dwtb200_image *im, int *j_max_ptr, int decompose_one)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im || !j_max_ptr) return fail(DWTB200_EINVAL, "image_fwd2_inplace: null argument");
@@ -1529,6 +1564,7 @@ int dwtb200_image_fwd2_inplace(dwtb200_image *im, int *j_max_ptr, int decompose_
 
 int dwtb200_image_inv2_inplace(dwtb200_image *im, int j_max, int decompose_one)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     if (!im) return fail(DWTB200_EINVAL, "image_inv2_inplace: null argument");
@@ -1539,6 +1575,7 @@ int dwtb200_image_inv2_inplace(dwtb200_image *im, int j_max, int decompose_one)
 int dwtb200_image_subband(dwtb200_image *im, int frame, int ix, int iy, int j, int band, void **dev_ptr, size_t *pitch_bytes,
                           int *size_x, int *size_y)
 {
+    API_LOCK();
     if (!im || frame < 0 || frame >= im->frames || j < 0 || band < 0 || band > 3 || ix < 0 || iy < 0 || ix > im->ox || iy > im->oy)
         return fail(DWTB200_EINVAL, "image_subband: bad arguments");
     int hx = 0, hy = 0, lx = ix, ly = iy, ox = im->ox, oy = im->oy;
@@ -1562,6 +1599,7 @@ int dwtb200_image_subband(dwtb200_image *im, int frame, int ix, int iy, int j, i
 int dwtb200_image_subband_moments(dwtb200_image *im, int frame, int ix, int iy, int j, int band, double *sum, double *sum_sq,
                                   double *max_abs)
 {
+    API_LOCK();
     ImageScope scope(im);
     NEED_DEV();
     void *p = nullptr;
@@ -1584,6 +1622,7 @@ int dwtb200_image_subband_moments(dwtb200_image *im, int frame, int ix, int iy, 
 
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
 {
+    API_LOCK();
     if (g.dev < 0 || !a || !b || a->kind != b->kind || a->ox != b->ox || a->oy != b->oy || a->frames != b->frames) {
         fail(DWTB200_EINVAL, "image_diff: shape mismatch");
         return -1;
@@ -1607,6 +1646,7 @@ int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)
 
 double dwtb200_image_maxabs(dwtb200_image *a, dwtb200_image *b)
 {
+    API_LOCK();
     if (g.dev < 0 || !a || !b || a->kind != b->kind || a->ox != b->ox || a->oy != b->oy || a->frames != b->frames) {
         fail(DWTB200_EINVAL, "image_maxabs: shape mismatch");
         return -1.0;
@@ -1849,6 +1889,7 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
 double dwtb200_last_transform_ms(void) { return (double)g_last_ms; }
 void dwtb200_release_host_cache(void)
 {
+    API_LOCK();
     // the pipelined host path's streams and events, and the transform timing events, go with the cache
     for (cudaEvent_t e : g_pipe.ev) cudaEventDestroy(e);
     g_pipe.ev.clear();
@@ -1870,6 +1911,7 @@ void dwtb200_release_host_cache(void)
 int dwtb200_fwd2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
                       int decompose_one, int zero_padding)
 {
+    API_LOCK();
     NEED_DEV();
     if (!ptr || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_host: null argument");
     return host_transform(false, kind, ptr, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one, zero_padding);
@@ -1878,6 +1920,7 @@ int dwtb200_fwd2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int o
 int dwtb200_inv2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
                       int decompose_one, int zero_padding)
 {
+    API_LOCK();
     NEED_DEV();
     if (!ptr) return fail(DWTB200_EINVAL, "inv2_host: null argument");
     return host_transform(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
@@ -1911,6 +1954,7 @@ static int host_inplace(bool inverse, int kind, void *ptr, int64_t sx, int64_t s
 
 int dwtb200_fwd2_inplace_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr, int decompose_one)
 {
+    API_LOCK();
     NEED_DEV();
     if (!ptr || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_inplace_host: null argument");
     return host_inplace(false, kind, ptr, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one);
@@ -1918,6 +1962,7 @@ int dwtb200_fwd2_inplace_host(int kind, void *ptr, int64_t sx, int64_t sy, int o
 
 int dwtb200_inv2_inplace_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max, int decompose_one)
 {
+    API_LOCK();
     NEED_DEV();
     if (!ptr) return fail(DWTB200_EINVAL, "inv2_inplace_host: null argument");
     return host_inplace(true, kind, ptr, sx, sy, ox, oy, ix, iy, &j_max, decompose_one);
@@ -1971,6 +2016,7 @@ static int host_transform2(bool inverse, int kind, const void *src, void *dst, i
 int dwtb200_fwd2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
                        int decompose_one, int zero_padding)
 {
+    API_LOCK();
     NEED_DEV();
     if (!src || !dst || !j_max_ptr) return fail(DWTB200_EINVAL, "fwd2_host2: null argument");
     return host_transform2(false, kind, src, dst, sx, sy, ox, oy, ix, iy, j_max_ptr, decompose_one, zero_padding);
@@ -1978,6 +2024,7 @@ int dwtb200_fwd2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t
 int dwtb200_inv2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int j_max,
                        int decompose_one, int zero_padding)
 {
+    API_LOCK();
     NEED_DEV();
     if (!src || !dst) return fail(DWTB200_EINVAL, "inv2_host2: null argument");
     return host_transform2(true, kind, src, dst, sx, sy, ox, oy, ix, iy, &j_max, decompose_one, zero_padding);
@@ -1990,6 +2037,7 @@ int dwtb200_inv2_host2(int kind, const void *src, void *dst, int64_t sx, int64_t
 int dwtb200_perf2(int kind, int ox, int oy, int ix, int iy, int j_max, int decompose_one, int zero_padding, int M, int N,
                   float *fwd_secs, float *inv_secs)
 {
+    API_LOCK();
     NEED_DEV();
     if (M < 1 || N < 1 || !fwd_secs || !inv_secs) return fail(DWTB200_EINVAL, "perf2: bad arguments");
     std::vector<dwtb200_image *> imgs;
@@ -2035,6 +2083,7 @@ int dwtb200_perf2(int kind, int ox, int oy, int ix, int iy, int j_max, int decom
 int dwtb200_perf2_inplace(int kind, int ox, int oy, int ix, int iy, int j_max, int decompose_one, int M, int N, float *fwd_secs,
                           float *inv_secs)
 {
+    API_LOCK();
     NEED_DEV();
     if (M < 1 || N < 1 || !fwd_secs || !inv_secs || ix < 1 || iy < 1 || ix > ox || iy > oy) return fail(DWTB200_EINVAL, "perf2_inplace: bad arguments");
     const int J = dwtb200_clamp_j(j_max, ox, oy, decompose_one);
@@ -2072,6 +2121,7 @@ int dwtb200_perf2_inplace(int kind, int ox, int oy, int ix, int iy, int j_max, i
 // =====================================================================================================
 dwtb200_volume *dwtb200_volume_create(int nx, int ny, int nz)
 {
+    API_LOCK();
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
     if (nx < 1 || ny < 1 || nz < 1) {
         fail(DWTB200_EINVAL, "volume_create: bad size");
@@ -2093,6 +2143,7 @@ dwtb200_volume *dwtb200_volume_create(int nx, int ny, int nz)
 }
 void dwtb200_volume_destroy(dwtb200_volume *v)
 {
+    API_LOCK();
     if (!v) return;
     if (g.st) cudaStreamSynchronize(g.st);
     for (int i = 0; i < 2; i++)
@@ -2128,16 +2179,19 @@ static int volume_xfer(dwtb200_volume *v, void *host, size_t sx, size_t sy, size
 }
 int dwtb200_volume_upload(dwtb200_volume *v, const void *host, size_t sx, size_t sy, size_t sz)
 {
+    API_LOCK();
     NEED_DEV();
     return volume_xfer(v, (void *)host, sx, sy, sz, true);
 }
 int dwtb200_volume_download(dwtb200_volume *v, void *host, size_t sx, size_t sy, size_t sz)
 {
+    API_LOCK();
     NEED_DEV();
     return volume_xfer(v, host, sx, sy, sz, false);
 }
 int dwtb200_volume_fill(dwtb200_volume *v)
 {
+    API_LOCK();
     NEED_DEV();
     if (!v) return fail(DWTB200_EINVAL, "volume_fill: null");
     launch_volume_fill(v->buf[v->cur], v->pitch, v->slice, v->nx, v->ny, v->nz, g.st);
@@ -2192,6 +2246,7 @@ static int volume_axes(dwtb200_volume *v, int inverse)
 }
 int dwtb200_volume_fwd3(dwtb200_volume *v)
 {
+    API_LOCK();
     NEED_DEV();
     if (!v) return fail(DWTB200_EINVAL, "volume_fwd3: null");
     if (v->nx < 5 || v->ny < 5 || v->nz < 5) return fail(DWTB200_EINVAL, "volume_fwd3: every size must be >= 5 (src/dwt-simple.c:2172)");
@@ -2199,6 +2254,7 @@ int dwtb200_volume_fwd3(dwtb200_volume *v)
 }
 int dwtb200_volume_inv3(dwtb200_volume *v)
 {
+    API_LOCK();
     NEED_DEV();
     if (!v) return fail(DWTB200_EINVAL, "volume_inv3: null");
     return volume_axes(v, 1);
@@ -2207,6 +2263,7 @@ int dwtb200_volume_inv3(dwtb200_volume *v)
 int dwtb200_fwd3_host(const void *src, size_t ssx, size_t ssy, size_t ssz, void *dst, size_t dsx, size_t dsy, size_t dsz,
                       int nx, int ny, int nz)
 {
+    API_LOCK();
     NEED_DEV();
     dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
@@ -2218,6 +2275,7 @@ int dwtb200_fwd3_host(const void *src, size_t ssx, size_t ssy, size_t ssz, void 
 }
 int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny, int nz)
 {
+    API_LOCK();
     NEED_DEV();
     dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
@@ -2233,6 +2291,7 @@ int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny
 // round trip missed the reference's tolerance (dwt_util_compare2_s, 1e-3) in *errors
 int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors)
 {
+    API_LOCK();
     NEED_DEV();
     if (size < 5 || N < 1 || !secs_per_voxel) return fail(DWTB200_EINVAL, "perf3: bad arguments");
     dwtb200_volume *v = dwtb200_volume_create(size, size, size), *ref = dwtb200_volume_create(size, size, size);
@@ -2275,6 +2334,7 @@ int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors)
 // =====================================================================================================
 int dwtb200_sync(void)
 {
+    API_LOCK();
     NEED_DEV();
     for (dwtb200_image *im : g.live) CK(cudaStreamSynchronize(im->st));
     CK(cudaStreamSynchronize(g.st0));
@@ -2284,6 +2344,7 @@ int dwtb200_sync(void)
 // and every image's stream) and everything queued afterwards waits for it; the stop event waits for everything again
 int dwtb200_timer_start(void)
 {
+    API_LOCK();
     NEED_DEV();
     for (dwtb200_image *im : g.live) wait_for_image(g.st0, im);
     CK(cudaEventRecord(g.e0, g.st0));
@@ -2292,6 +2353,7 @@ int dwtb200_timer_start(void)
 }
 double dwtb200_timer_stop_ms(void)
 {
+    API_LOCK();
     if (g.dev < 0) return -1.0;
     for (dwtb200_image *im : g.live) wait_for_image(g.st0, im);
     if (cudaEventRecord(g.e1, g.st0) != cudaSuccess || cudaEventSynchronize(g.e1) != cudaSuccess) return -1.0;
@@ -2303,6 +2365,7 @@ void *dwtb200_stream(void) { return (void *)g.st0; }
 
 int dwtb200_flush_l2(size_t bytes)
 {
+    API_LOCK();
     NEED_DEV();
     if (bytes > g.flush_bytes) {
         if (g.flush) cudaFree(g.flush);

@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(128, PFD == 2 ? 3 : (VPL * sizeof(typename WV:
             load(2 * m + 3, na);
             load(2 * m + 4, nb);
         }
-        if (p.dbg != 2) {
+#ifdef DWTB200_DEBUG_KEYS
+        if (p.dbg != 2)
+#endif
+        {
             hfwd<WV, VPL>(a);
             hfwd<WV, VPL>(b);
         }
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(128, PFD == 2 ? 3 : (VPL * sizeof(typename WV:
                 st[1][i] = d1n;
             }
         }
+#ifdef DWTB200_DEBUG_KEYS   // measurement only (profiles/dbg_level0.py): 2 = no lifting arithmetic, 1 = no stores
         if (p.dbg == 2) {
 #pragma unroll
             for (int i = 0; i < VPL; i++) {
@@ -159,8 +163,11 @@ __global__ void __launch_bounds__(128, PFD == 2 ? 3 : (VPL * sizeof(typename WV:
                 oH[i] = b[i];
             }
         }
+#endif
         const int kk = m - DELAY;
-        if (p.dbg == 1 && oL[0] != T(123457)) continue;   // debug: no stores (the compare keeps the arithmetic alive)
+#ifdef DWTB200_DEBUG_KEYS
+        if (p.dbg == 1 && oL[0] != T(123457)) continue;   // the compare keeps the arithmetic alive
+#endif
         if (kk >= k0 && producer) {
             T o[HV];
 #pragma unroll

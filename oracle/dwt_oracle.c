@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under libdwt_b200/ may link, load or call this
  * file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can
- * check the CUDA path.  Parity status: PINNED -- tests/test_oracle_vs_ref.py compares
+ * check the CUDA path.  Parity status: PINNED -- tests/test_oracle.py compares
  * every function here bit-for-bit against the compiled reference (oracle/_ref, built
  * from /root/reference by oracle/Makefile) and tests/golden/ holds digests of reference
  * outputs produced by tests/golden/make_golden.py.

@@ -313,9 +313,40 @@ def test_device_resident_batch(dev, oracle, kind):
     report(fails)
 
 
+def test_chained_graph_replays(dev, oracle):
+    """The captured, chained pyramid of ONE image object replayed several times with the same key: from the second
+    replay on the never-reset completion counters, the (gen + 1) * need targets and the done / gen hand-off of
+    chain.cuh are what orders the levels (batch of 3 so that levels 0-2 are ring levels linked into one chain)."""
+    w, t = "97", "s"
+    ox, oy, frames = 2600, 2300, 3
+    img = dev.DeviceImage(dev.kind_of(w, t), ox, oy, frames)
+    want_f, want_i = [], []
+    for k in range(frames):
+        a = oracle.fill(np.zeros((oy, ox), DT[t]), t, rand=k % 6)
+        J = oracle.fwd2(a, w, t)
+        want_f.append(a.copy())
+        oracle.inv2(a, w, t, j_max=J)
+        want_i.append(a)
+    fails = []
+    for rep in range(4):
+        img.fill(0, 0, 6)
+        assert img.fwd2() == J
+        for k in range(frames):
+            got = img.download(frame=k)
+            if not (bits(got, t) == bits(want_f[k], t)).all():
+                fails.append(f"replay {rep} frame {k} forward: " + describe_mismatch(got, want_f[k], t))
+        img.inv2(J)
+        for k in range(frames):
+            got = img.download(frame=k)
+            if not (bits(got, t) == bits(want_i[k], t)).all():
+                fails.append(f"replay {rep} frame {k} inverse: " + describe_mismatch(got, want_i[k], t))
+    img.close()
+    report(fails)
+
+
 # ---- BASELINE.json configs at full size ---------------------------------------------------------------
 FULL = [("53", "i", 4096, 4096), ("97", "s", 8192, 8192), ("97", "s", 7919, 6007), ("97", "d", 4096, 4096),
-        ("97", "s", 2048, 2048)]
+        ("97", "d", 8192, 8192), ("97", "s", 2048, 2048)]
 
 
 @pytest.mark.parametrize("cfg", FULL, ids=lambda c: f"{c[0]}{c[1]}-{c[2]}x{c[3]}")
