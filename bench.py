@@ -471,9 +471,44 @@ def run_ours(args):
                            "min-of-means protocol (src/libdwt.c:21473-21507) in value_min_of_means",
                "value_min_of_means": r["value_min_of_means"], "seconds_min_of_means": r["min_of_means_s"]}
 
+    # ---- legs that need the memory of the batches: free them first ----
+    for name in list(imgs):
+        imgs[name].close()
+    imgs.clear()
+    link = batch = strips = None
+    if not args.no_extra:
+        for what in ("pcie", "batch_2048", "strips"):
+            try:
+                if what == "pcie":
+                    link = pcie_leg(L, d, torch, dist if world > 1 else None, world, barrier)
+                elif what == "batch_2048":
+                    batch = batch_2048_leg(L, d, torch, dist if world > 1 else None, rank, world, peak, barrier)
+                elif world > 1:
+                    strips = strips_leg(L, d, torch, dist, rank, world, peak, barrier, size=args.strips_size)
+            except Exception as e:   # an auxiliary leg must not take the headline line down with it
+                msg = {"failed": f"{type(e).__name__}: {e}"}
+                if what == "pcie":
+                    link = msg
+                elif what == "batch_2048":
+                    batch = msg
+                else:
+                    strips = msg
+    if e2e and link and "duplex_ms" in link:
+        # one transform call moves 256 MiB up and 256 MiB down; `duplex_ms` is that pair of copies with nothing else in the way
+        e2e["link_ceiling_gbs"] = link["duplex_gbs"]
+        e2e["fraction_of_link_ceiling"] = (4 * link["duplex_ms"]) / e2e["ms_per_step"]
+
+    single = None
+    try:
+        ts = sum(breakdown[f"{name}_{dr}_single"]["us_per_image"] for name in ("97s", "53i") for dr in ("fwd", "inv")) * 1e-6
+        single = {"value": world * 4 * PIX / ts / 1e9, "unit": "Gpixel/s",
+                  "what": "the same four transforms one image per call (the granularity of dwt_cdf97_2f_s), device-resident, summed device time"}
+    except Exception:
+        pass
+
     if rank == 0:
         line = {
-            "metric": "cdf97_f32+cdf53_i32 fwd+inv throughput, 8192x8192 j=max", "value": value, "unit": "Gpixel/s", "n_gpus": world,
+            "metric": "cdf97_f32+cdf53_i32 fwd+inv throughput, 8192x8192 j=max", "value": value, "value_single_image": single, "unit": "Gpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": "8192x8192 full-depth (J=13) 2-D DWT, CDF 9/7 float32 + CDF 5/3 int32, forward+inverse",
@@ -484,10 +519,274 @@ def run_ours(args):
                        "sharding": "independent frames per GPU, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0] * args.steps, "clocks": clocks,
             "breakdown": breakdown, "inplace_family": inplace, "volume": volume, "large_image": large,
+            "pcie": link, "batch_2048": batch, "strips_65536": strips,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ======================================================================================================
+# auxiliary legs of the GPU arm (each returns a dict that goes into the JSON line)
+# ======================================================================================================
+def gather_max(x, world, torch, dist):
+    if world == 1:
+        return x
+    tt = torch.tensor(x if isinstance(x, (list, tuple)) else [x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return tt.tolist() if isinstance(x, (list, tuple)) else float(tt.item())
+
+
+def pcie_leg(L, d, torch, dist, world, barrier, nbytes=256 << 20):
+    """The host link ceiling the end-to-end number is bounded by: plain pinned cudaMemcpyAsync of 256 MiB host->device,
+    device->host and both at once, all ranks concurrently (max over ranks of the time, summed bytes)."""
+    hu = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)   # cudaHostAlloc
+    hd = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    hu.fill_(1)
+    du, dd = torch.empty(nbytes, dtype=torch.uint8, device="cuda"), torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def timed(up, dn, reps=5):
+        best = 1e30
+        for _ in range(reps + 1):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s1.wait_event(e0); s2.wait_event(e0)
+            if up:
+                with torch.cuda.stream(s1):
+                    du.copy_(hu, non_blocking=True)
+            if dn:
+                with torch.cuda.stream(s2):
+                    hd.copy_(dd, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return gather_max(best, world, torch, dist)
+    t_up, t_dn, t_both = timed(True, False), timed(False, True), timed(True, True)
+    out = {"bytes_each_way": nbytes, "ranks": world, "h2d_gbs": world * nbytes / t_up / 1e9, "d2h_gbs": world * nbytes / t_dn / 1e9,
+           "duplex_gbs": 2 * world * nbytes / t_both / 1e9, "duplex_ms": t_both * 1e3,
+           "what": "pinned cudaMemcpyAsync (torch copy_ non_blocking), best of 5, all ranks at once: aggregate GB/s over the ranks"}
+    del hu, hd
+    return out
+
+
+def batch_2048_leg(L, d, torch, dist, rank, world, peak, barrier, frames_total=4096, chunk=512):
+    """BASELINE config 4: 4096 independent 2048x2048 CDF 9/7 float frames sharded over the ranks (frame k of the GLOBAL batch is
+    filled with rand = k % 6; no collective), J = 11, forward then inverse -- the reference's perf protocol
+    (dwt_util_perf_cdf97_2_s, src/libdwt.c:21391-21507) with M = frames per rank.  A rank holds its frames in chunks of at most
+    `chunk` frames (one dwtb200_image each: one launch per level for the whole chunk)."""
+    w = h = 2048
+    per_rank = frames_total // world
+    first = rank * per_rank
+    nchunk = max(1, -(-per_rank // chunk))
+    sizes = [per_rank // nchunk + (1 if i < per_rank % nchunk else 0) for i in range(nchunk)]
+    # memory: 2.33 planes of 16 MiB per frame -> 512 frames = 18.6 GiB; all of a rank's chunks stay resident when they fit
+    free_b, _ = torch.cuda.mem_get_info()
+    need = per_rank * 16 * (1 << 20) * 2.4
+    resident = need < free_b * 0.9
+    b1 = algorithmic_bytes(w, h, 11, 4)
+
+    def fill(im, k0):
+        # frame f of this chunk is global frame k0 + f: rand = (k0 + f) % 6 -> the fill takes rand_mod = 6 and a start offset
+        # through `rand` (dwtb200_image_fill: frame k uses (rand + k) % rand_mod when rand_mod > 0)
+        im.fill(k0 % 6, 0, 6)
+
+    imgs, k0s = [], []
+    k = first
+    for n in sizes:
+        if resident or not imgs:
+            imgs.append(d.DeviceImage(d.CDF97_F32, w, h, n))
+        k0s.append(k)
+        k += n
+    tf = ti = 0.0
+    reps = 3
+    for rep in range(reps + 1):   # rep 0 warms up (graph capture)
+        f_ms = i_ms = 0.0
+        for ci, n in enumerate(sizes):
+            im = imgs[ci] if resident else imgs[0]
+            if not resident and n != im.frames:
+                im.close()
+                imgs[0] = im = d.DeviceImage(d.CDF97_F32, w, h, n)
+            if not resident or rep == 0:
+                fill(im, k0s[ci])
+            L.check(L.c.dwtb200_sync())
+            if ci == 0:
+                barrier()
+            L.check(L.c.dwtb200_timer_start())
+            assert im.fwd2() == 11
+            f_ms += L.c.dwtb200_timer_stop_ms()
+            L.check(L.c.dwtb200_timer_start())
+            im.inv2(11)
+            i_ms += L.c.dwtb200_timer_stop_ms()
+        if rep:
+            tf += f_ms
+            ti += i_ms
+    tf, ti = gather_max([tf / reps * 1e-3, ti / reps * 1e-3], world, torch, dist)
+    # bit-exact check of a sample of frames of this rank against the oracle (first, a middle one, last)
+    checked, bad = [], 0
+    try:
+        from oracle.orc import Oracle
+        orc = Oracle()
+        im = imgs[0]
+        fill(im, k0s[0])
+        im.fwd2()
+        for f in sorted({0, im.frames // 2, im.frames - 1}):
+            a = orc.fill(np.zeros((h, w), np.float32), "s", rand=(k0s[0] + f) % 6)
+            orc.fwd2(a, "97", "s")
+            got = im.download(frame=f)
+            checked.append(k0s[0] + f)
+            bad += int(got.tobytes() != a.tobytes())
+        im.inv2(11)
+    except Exception as e:   # the oracle is the checker only; its absence must not break the measurement
+        checked = [f"oracle unavailable: {e}"]
+    bad = int(gather_max(float(bad), world, torch, dist))
+    # one chunk end to end: pinned host frames -> device, forward, coefficients -> host
+    e2e = None
+    try:
+        n = min(sizes[0], 64)
+        nb = n * w * h * 4
+        C = __import__("ctypes")
+        hp = L.c.dwtb200_host_alloc(nb)
+        arr = np.ndarray(shape=(n, h, w), dtype=np.float32, buffer=(C.c_uint8 * nb).from_address(hp))
+        sub = d.DeviceImage(d.CDF97_F32, w, h, n)
+        sub.fill(first % 6, 0, 6)
+        for f in range(n):
+            sub.download(arr[f], frame=f)
+        best = 1e30
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for f in range(n):
+                sub.upload(arr[f], frame=f)
+            sub.fwd2()
+            for f in range(n):
+                sub.download(arr[f], frame=f)
+            best = min(best, time.perf_counter() - t0)
+        sub.inv2(11)
+        sub.close()
+        L.c.dwtb200_host_free(hp)
+        best = gather_max(best, world, torch, dist)
+        e2e = {"frames_per_rank": n, "gpixel_s": world * n * w * h / best / 1e9, "ms": best * 1e3,
+               "what": "pinned host frames uploaded, forward transform of the chunk, coefficients downloaded (wall clock, max over ranks)"}
+    except Exception as e:
+        e2e = {"skipped": str(e)}
+    for im in imgs:
+        im.close()
+    pix = world * per_rank * w * h
+    return {"workload": f"{world * per_rank} frames of 2048x2048 float32 CDF 9/7, J=11, {per_rank} per GPU in {nchunk} chunk(s) of <= {max(sizes)} "
+                        f"frames ({'resident' if resident else 'one chunk resident at a time, refilled'}), frame k filled with rand = k % 6",
+            "fwd_gpixel_s": pix / tf / 1e9, "inv_gpixel_s": pix / ti / 1e9, "fwd_ms": tf * 1e3, "inv_ms": ti * 1e3,
+            "fwd_roofline_frac_per_gpu": b1 * per_rank / tf / 1e9 / peak, "inv_roofline_frac_per_gpu": b1 * per_rank / ti / 1e9 / peak,
+            "frames_checked_against_oracle": checked, "frames_differing": bad, "e2e_one_chunk": e2e}
+
+
+def strips_leg(L, d, torch, dist, rank, world, peak, barrier, size=65536, levels=0):
+    """BASELINE config 5a: ONE size x size CDF 9/7 float image as row strips over the ranks (dwtb200_strips_*: peer copies over NVLink,
+    device-side flags, no host synchronisation inside a call); forward and inverse, CUDA events, max over ranks; strong-scaling
+    efficiency against the single-GPU transform of the same image timed on the rank's own GPU in the same run; every rank's owned rows
+    compared bit for bit with that single-GPU result, and level 0 of rank 0's strip with the oracle on a row window (separability)."""
+    import uuid
+    obj = [uuid.uuid4().hex[:12] if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(obj, src=0)
+    s = d.DeviceStrips(d.CDF97_F32, size, size, rank, world, "dwtb200-bench-" + obj[0], levels)
+    s.connect()
+    wide = 1 if size > 16384 else 0
+    full = d.DeviceImage(d.CDF97_F32, size, size)
+    # the single-GPU transform of the whole picture (on every rank: it is also the checker of the rank's rows)
+    t1f = t1i = 1e30
+    J = 0
+    for _ in range(3):
+        full.fill(0, 0, 0, 0, wide)
+        L.check(L.c.dwtb200_sync())
+        L.check(L.c.dwtb200_timer_start())
+        J = full.fwd2()
+        t1f = min(t1f, L.c.dwtb200_timer_stop_ms())
+        L.check(L.c.dwtb200_timer_start())
+        full.inv2(J)
+        t1i = min(t1i, L.c.dwtb200_timer_stop_ms())
+    t1f, t1i = gather_max([t1f, t1i], world, torch, dist)
+    full.fill(0, 0, 0, 0, wide)
+    full.fwd2()
+    L.check(L.c.dwtb200_sync())
+    a0, m = 1024, 72                      # rank 0: input rows [a0, a0 + 2 m) for the oracle, output row pairs [k0, k1)
+    k0, k1 = a0 // 2 + 8, a0 // 2 + m - 8
+    win = got_l = got_h = None
+    tf = ti = 1e30
+    diff_f = diff_i = -1
+    peer_f = peer_i = 0
+    for rep in range(4):
+        s.fill(0, 0, wide)
+        s.sync()
+        if rep == 0 and rank == 0:
+            win = np.empty((2 * m, size), np.float32)
+            s.image.copy_rows(a0, 2 * m, win.ctypes.data, win.strides[0], False)
+            L.check(L.c.dwtb200_sync())
+        barrier()
+        L.check(L.c.dwtb200_timer_start())
+        assert s.fwd2() == J
+        ms = L.c.dwtb200_timer_stop_ms()
+        s.sync()
+        peer_f = s.last_peer_bytes
+        ms = gather_max(ms, world, torch, dist)
+        if rep:
+            tf = min(tf, ms)
+        else:
+            diff_f = s.compare_owned(full, True)
+            if rank == 0:   # rows k: [.. | HL_0], rows nly + k: [LH_0 | HH_0] of the strip's Mallat plane
+                nly_l = (s.plan.ext1 - s.plan.ext0 + 1) // 2
+                got_l, got_h = np.empty((k1 - k0, size), np.float32), np.empty((k1 - k0, size), np.float32)
+                s.image.copy_rows(k0, k1 - k0, got_l.ctypes.data, got_l.strides[0], False)
+                s.image.copy_rows(nly_l + k0, k1 - k0, got_h.ctypes.data, got_h.strides[0], False)
+                L.check(L.c.dwtb200_sync())
+        barrier()
+        L.check(L.c.dwtb200_timer_start())
+        s.inv2(J)
+        ms = L.c.dwtb200_timer_stop_ms()
+        s.sync()
+        peer_i = s.last_peer_bytes
+        ms = gather_max(ms, world, torch, dist)
+        if rep:
+            ti = min(ti, ms)
+        else:
+            full.inv2(J)
+            diff_i = s.compare_owned(full, False)
+            L.check(L.c.dwtb200_sync())
+    diffs = gather_max([float(diff_f), float(diff_i)], world, torch, dist)
+    peers = [float(peer_f), float(peer_i)]
+    if world > 1:
+        tt = torch.tensor(peers, device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        peers = tt.tolist()
+    oracle_rows = None
+    if rank == 0:
+        try:   # level 0 of the strip against the oracle's one-level transform of the row window (interior rows only)
+            from oracle.orc import Oracle
+            ref = win.copy()
+            Oracle().fwd2(ref, "97", "s", j_max=1)
+            nlx, i0, i1 = size // 2, k0 - a0 // 2, k1 - a0 // 2
+            bad = int((got_l[:, nlx:].view(np.uint32) != ref[i0:i1, nlx:].view(np.uint32)).sum())
+            bad += int((got_h.view(np.uint32) != ref[m + i0:m + i1].view(np.uint32)).sum())
+            oracle_rows = {"input_rows": [a0, a0 + 2 * m], "checked": f"HL, LH, HH rows {k0}..{k1 - 1} of level 0 at full width", "differing": bad}
+        except Exception as e:
+            oracle_rows = {"skipped": str(e)}
+    barrier()
+    full.close()
+    plan = [s.plan.own0, s.plan.own1, s.plan.ext0, s.plan.ext1]
+    Jd = s.Jd
+    s.close()
+    b = algorithmic_bytes(size, size, J, 4)
+    return {"workload": f"one {size}x{size} float32 CDF 9/7 image, J={J}, row strips over {world} GPUs, {Jd} levels distributed, the rest on rank 0",
+            "fwd_ms": tf, "inv_ms": ti, "fwd_gpixel_s": size * size / tf / 1e6, "inv_gpixel_s": size * size / ti / 1e6,
+            "single_gpu_fwd_ms": t1f, "single_gpu_inv_ms": t1i, "fwd_efficiency": t1f / (world * tf), "inv_efficiency": t1i / (world * ti),
+            "fwd_roofline_frac_per_gpu": b / world / (tf * 1e-3) / 1e9 / peak, "inv_roofline_frac_per_gpu": b / world / (ti * 1e-3) / 1e9 / peak,
+            "peer_bytes_fwd": peers[0], "peer_bytes_inv": peers[1], "rank0_rows": plan,
+            "owned_rows_differing_from_single_gpu": {"fwd": int(diffs[0]), "inv": int(diffs[1])}, "oracle_row_window": oracle_rows,
+            "transport": "cudaMemcpy2DAsync on CUDA-IPC peer mappings (NVLink P2P), device-side sequence flags, no host sync inside a call",
+            "timing": "CUDA events per rank from the call's first enqueued work to the rank's last, after a host barrier; max over ranks; best of 3"}
 
 
 def main():
@@ -499,6 +798,8 @@ def main():
     ap.add_argument("--images", type=int, default=4, help="independent 8192^2 images per sample type per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-large", action="store_true", help="skip the 32768^2 single-image leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the pcie / batch_2048 / strips legs")
+    ap.add_argument("--strips-size", type=int, default=65536, help="edge of the single image of the row-strip leg (N > 1)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 3 if args.impl == "reference" else 100

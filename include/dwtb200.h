@@ -121,7 +121,8 @@ void dwtb200_image_destroy(dwtb200_image *img);
 int dwtb200_image_upload(dwtb200_image *img, int frame, const void *host, int64_t stride_x, int64_t stride_y);
 int dwtb200_image_download(dwtb200_image *img, int frame, void *host, int64_t stride_x, int64_t stride_y);
 /* dwt_util_test_image_fill{,2}_{s,d,i} on the device (src/libdwt.c:1247-1385); frame k uses
- * rand = (rand_mod > 0 ? k % rand_mod : rand), cf. volume_fill_s (src/volume.c:41) */
+ * rand = (rand_mod > 0 ? (rand + k) % rand_mod : rand), cf. volume_fill_s (src/volume.c:41); with rand_mod > 0, `rand` is
+ * the global index of frame 0 when the batch is one shard of a larger one */
 int dwtb200_image_fill(dwtb200_image *img, int rand, int type, int rand_mod);
 /* the same with the pattern's row coordinate shifted by y_offset (a row strip of a larger image) and, with
  * wide != 0, the products evaluated in 64 bits: the extension of the patterns to images the reference cannot
@@ -214,6 +215,51 @@ int dwtb200_volume_inv3(dwtb200_volume *v);   /* cdf97_3i_ip_sep_horizontal_s */
 /* volume_perftest_fwd97op_s (src/volume-dwt.h:234, src/volume-dwt.c:2810) on the device: N runs of fill / forward (timed) /
  * inverse / compare; minimum forward seconds per voxel, number of failed round trips */
 int dwtb200_perf3(int size, int N, double *secs_per_voxel, int *errors);
+
+/* ---- ONE image as row strips over the GPUs of a box (BASELINE config 5a) ----------------------------
+ * Replaces nothing in the reference, which has no multi-device code and cannot address such an image (`y * stride_x` in int,
+ * src/inline.h:188); the transform is dwt_cdf97_2f_s / dwt_cdf97_2i_s and siblings (src/libdwt.c:12776-12924, 17040-17180) of
+ * the WHOLE picture, full depth, Mallat layout, bit-identical to the single-device result.
+ * One process per GPU.  Rank r owns rows [own0, own1) and holds the extended strip [ext0, ext1) (owned rows + halo) in an
+ * ordinary dwtb200_image (dwtb200_strips_image: fill / upload / download it like any image; local row = global row - ext0).
+ * The first levels_distributed levels run on every rank's strip; the halo rows and LL band move between the ranks as
+ * peer-to-peer copies over NVLink (CUDA IPC mappings) ordered by device-side flags -- the calls enqueue work and return, there is
+ * no host synchronisation inside them; rank 0 holds the remaining levels in its `top` image (the Mallat image of LL_Jd).
+ * The calls are collective: every rank makes the same sequence of dwtb200_strips_fwd2 / _inv2 calls. */
+typedef struct dwtb200_strips dwtb200_strips;
+typedef struct {
+    int halo;                 /* rows of level-0 input held beyond each end of the owned rows: HALO * 2^levels_distributed */
+    int own0, own1;           /* image rows this rank owns */
+    int ext0, ext1;           /* image rows it holds */
+    int ll_w, ll_h;           /* size of LL after the distributed levels (the top image) */
+    int ll_own0, ll_own1;     /* rows of that band this rank owns ... */
+    int ll_ext0, ll_ext1;     /* ... and holds */
+    int neighbours_only;      /* 1: every strip is at least as tall as the halo (required) */
+} dwtb200_strip_plan;
+/* geometry only (no device needed); halo_lines = lifting reach per level: 4 for CDF 9/7, 2 for CDF 5/3 */
+int dwtb200_strips_plan(int width, int height, int world, int levels_distributed, int halo_lines, int rank, dwtb200_strip_plan *out);
+/* rows of distributed level j in its output resolution: out[11] = { off, nly_global, nly_local, extL0, extL1, extH0, extH1,
+ * ownL0, ownL1, ownH0, ownH1 } (L: LL/HL rows, H: LH/HH rows; global row numbers; local row = global - off, H rows after nly_local) */
+int dwtb200_strips_band(int width, int height, int world, int levels_distributed, int halo_lines, int rank, int j, int *out);
+/* levels_distributed <= 0: chosen so that LL has at most 2048^2 samples.  `session`: a name unique to this strips object and
+ * common to its ranks (a POSIX shared-memory segment of that name carries the IPC handles); rank 0 must be created first when
+ * several ranks live in one process (single-GPU tests).  Returns NULL on failure (dwtb200_last_error). */
+dwtb200_strips *dwtb200_strips_create(int kind, int width, int height, int levels_distributed, int rank, int world, const char *session);
+int dwtb200_strips_connect(dwtb200_strips *s);   /* waits for every rank's create; implied by the first transform */
+void dwtb200_strips_destroy(dwtb200_strips *s);
+dwtb200_image *dwtb200_strips_image(dwtb200_strips *s);   /* the extended strip */
+dwtb200_image *dwtb200_strips_top(dwtb200_strips *s);     /* rank 0: Mallat image of LL_Jd; NULL elsewhere */
+int dwtb200_strips_levels(dwtb200_strips *s, int *j_total, int *j_distributed);
+int dwtb200_strips_get_plan(dwtb200_strips *s, dwtb200_strip_plan *out);
+int dwtb200_strips_fwd2(dwtb200_strips *s, int *j_max_ptr);   /* *j_max_ptr receives the depth (ceil_log2(min(width, height))) */
+int dwtb200_strips_inv2(dwtb200_strips *s, int j_max);        /* j_max: that depth, or -1 */
+int dwtb200_strips_sync(dwtb200_strips *s);   /* waits for this rank's queued work; fails if a wait for a peer timed out */
+unsigned long long dwtb200_strips_last_peer_bytes(dwtb200_strips *s);   /* bytes the last call moved between this rank and its peers */
+/* verification: differing samples (bit-wise) between the rows this rank owns and a single-device image of the whole picture on
+ * this device (mallat != 0: forward coefficients incl. rank 0's top; 0: image rows); -1 on error */
+int64_t dwtb200_strips_compare_owned(dwtb200_strips *s, dwtb200_image *full, int mallat);
+/* the owned rows written into a host image of the whole picture (stride_x bytes between rows) at their final positions */
+int dwtb200_strips_download_owned(dwtb200_strips *s, void *host_full, int64_t stride_x, int mallat);
 
 /* ---- device-event timing: replaces dwt_util_get_clock around transforms (src/libdwt.c:18701) ---- */
 int dwtb200_sync(void);                 /* wait for the library stream */

@@ -7,7 +7,7 @@ from oracle/ and has no CPU fallback -- importing works without a GPU (so the sy
 every compute call raises DwtError when no CUDA device is usable.
 """
 from .api import (  # noqa: F401
-    CDF97_F32, CDF97_F64, CDF53_I32, CDF53_F32, CDF53_F64, CDF97_I32, DwtError, DeviceImage, DeviceVolume, Library, lib,
+    CDF97_F32, CDF97_F64, CDF53_I32, CDF53_F32, CDF53_F64, CDF97_I32, DwtError, DeviceImage, DeviceStrips, DeviceVolume, Library, lib, strips_band, strips_plan,
     dwt_cdf97_2f_s, dwt_cdf97_2i_s, dwt_cdf97_2f_d, dwt_cdf97_2i_d, dwt_cdf53_2f_i, dwt_cdf53_2i_i,
     dwt_cdf53_2f_s, dwt_cdf53_2i_s, dwt_cdf53_2f_d, dwt_cdf53_2i_d, dwt_cdf97_2f_i, dwt_cdf97_2i_i,
     dwt_cdf97_2f_s2, dwt_cdf97_2i_s2, dwt_cdf97_2f_inplace_s, dwt_cdf97_2f_inplace_sep_s, dwt_cdf97_2f_inplace_sdl_s,

@@ -61,6 +61,14 @@ SYMBOLS = [
     ("dwtb200_volume_fill", _i, [_vp]), ("dwtb200_volume_fwd3", _i, [_vp]), ("dwtb200_volume_inv3", _i, [_vp]),
     ("dwtb200_sync", _i, []), ("dwtb200_timer_start", _i, []), ("dwtb200_timer_stop_ms", _dbl, []),
     ("dwtb200_stream", _vp, []), ("dwtb200_flush_l2", _i, [_sz]),
+    # one image as row strips over the GPUs of a box
+    ("dwtb200_strips_plan", _i, [_i, _i, _i, _i, _i, _i, _vp]), ("dwtb200_strips_band", _i, [_i, _i, _i, _i, _i, _i, _i, _ip]),
+    ("dwtb200_strips_create", _vp, [_i, _i, _i, _i, _i, _i, C.c_char_p]), ("dwtb200_strips_connect", _i, [_vp]),
+    ("dwtb200_strips_destroy", None, [_vp]), ("dwtb200_strips_image", _vp, [_vp]), ("dwtb200_strips_top", _vp, [_vp]),
+    ("dwtb200_strips_levels", _i, [_vp, _ip, _ip]), ("dwtb200_strips_get_plan", _i, [_vp, _vp]),
+    ("dwtb200_strips_fwd2", _i, [_vp, _ip]), ("dwtb200_strips_inv2", _i, [_vp, _i]), ("dwtb200_strips_sync", _i, [_vp]),
+    ("dwtb200_strips_last_peer_bytes", C.c_ulonglong, [_vp]), ("dwtb200_strips_compare_owned", _i64, [_vp, _vp, _i]),
+    ("dwtb200_strips_download_owned", _i, [_vp, _vp, _i64, _i]),
 ]
 
 
@@ -381,6 +389,101 @@ class DeviceImage:
     @property
     def last_path(self):
         return self.L.c.dwtb200_image_last_path(self.h)
+
+
+class StripPlanC(C.Structure):
+    """dwtb200_strip_plan (include/dwtb200.h)."""
+    _fields_ = [(n, C.c_int) for n in ("halo", "own0", "own1", "ext0", "ext1", "ll_w", "ll_h", "ll_own0", "ll_own1", "ll_ext0", "ll_ext1",
+                                       "neighbours_only")]
+
+
+def strips_plan(width, height, world, levels_distributed, halo_lines, rank):
+    p = StripPlanC()
+    L = lib()
+    L.check(L.c.dwtb200_strips_plan(width, height, world, levels_distributed, halo_lines, rank, C.byref(p)))
+    return p
+
+
+def strips_band(width, height, world, levels_distributed, halo_lines, rank, j):
+    out = (C.c_int * 11)()
+    L = lib()
+    L.check(L.c.dwtb200_strips_band(width, height, world, levels_distributed, halo_lines, rank, j, out))
+    return dict(zip(("off", "nly_g", "nly_l", "extL0", "extL1", "extH0", "extH1", "ownL0", "ownL1", "ownH0", "ownH1"), out))
+
+
+class _Borrowed(DeviceImage):
+    """A dwtb200_image owned by another object (the strip / top image of a DeviceStrips)."""
+
+    def __init__(self, handle, kind, size_x, size_y):
+        self.L = lib()
+        self.kind, self.size_x, self.size_y, self.frames = kind, size_x, size_y, 1
+        self.h = handle
+
+    def close(self):
+        self.h = None
+
+
+class DeviceStrips:
+    """ONE image as row strips over the GPUs of a box (dwtb200_strips_*): this process is `rank` of `world`.
+    `session` must be the same string on every rank and unique to this object."""
+
+    def __init__(self, kind, width, height, rank, world, session, levels_distributed=0):
+        self.L = lib()
+        self.L.init()
+        self.kind, self.width, self.height, self.rank, self.world = kind, width, height, rank, world
+        self.h = self.L.c.dwtb200_strips_create(kind, width, height, levels_distributed, rank, world, session.encode())
+        if not self.h:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+        self.plan = StripPlanC()
+        self.L.check(self.L.c.dwtb200_strips_get_plan(self.h, C.byref(self.plan)))
+        jt, jd = C.c_int(), C.c_int()
+        self.L.check(self.L.c.dwtb200_strips_levels(self.h, C.byref(jt), C.byref(jd)))
+        self.J, self.Jd = jt.value, jd.value
+        self.image = _Borrowed(self.L.c.dwtb200_strips_image(self.h), kind, width, self.plan.ext1 - self.plan.ext0)
+        t = self.L.c.dwtb200_strips_top(self.h)
+        self.top = _Borrowed(t, kind, self.plan.ll_w, self.plan.ll_h) if t else None
+
+    def close(self):
+        if self.h:
+            self.L.c.dwtb200_strips_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def connect(self):
+        self.L.check(self.L.c.dwtb200_strips_connect(self.h))
+
+    def fill(self, rand=0, type_=0, wide=0):
+        """the test pattern of the whole picture on the rows this rank holds"""
+        self.image.fill(rand, type_, 0, y_offset=self.plan.ext0, wide=wide)
+
+    def fwd2(self):
+        j = C.c_int(-1)
+        self.L.check(self.L.c.dwtb200_strips_fwd2(self.h, C.byref(j)))
+        return j.value
+
+    def inv2(self, j_max=-1):
+        self.L.check(self.L.c.dwtb200_strips_inv2(self.h, j_max))
+
+    def sync(self):
+        self.L.check(self.L.c.dwtb200_strips_sync(self.h))
+
+    @property
+    def last_peer_bytes(self):
+        return int(self.L.c.dwtb200_strips_last_peer_bytes(self.h))
+
+    def compare_owned(self, full, mallat):
+        r = self.L.c.dwtb200_strips_compare_owned(self.h, full.h, 1 if mallat else 0)
+        if r < 0:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+        return r
+
+    def download_owned(self, host_full, mallat):
+        self.L.check(self.L.c.dwtb200_strips_download_owned(self.h, host_full.ctypes.data, host_full.strides[0], 1 if mallat else 0))
 
 
 class DeviceVolume:

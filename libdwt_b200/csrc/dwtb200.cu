@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "../../include/dwtb200.h"
+#include "internal.h"
 #include "kernels.h"
 #include "lifting.cuh"
 
@@ -180,6 +181,34 @@ void stage_release()
     cudaEventRecord(g.stage_ev, g.st);
 }
 }  // namespace
+
+namespace dwtb200 {
+ImageView image_view(const dwtb200_image *im)
+{
+    ImageView v;
+    v.plane[0] = im->plane[0];
+    v.plane[1] = im->plane[1];
+    v.cur = im->cur;
+    v.pitch = im->pitch;
+    v.frame = im->frame;
+    v.es = im->es;
+    v.ox = im->ox;
+    v.oy = im->oy;
+    v.frames = im->frames;
+    v.kind = im->kind;
+    v.st = im->st;
+    return v;
+}
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g.err, sizeof g.err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+std::recursive_mutex &api_mutex() { return g_api_mutex; }
+}  // namespace dwtb200
 
 extern "C" {
 

@@ -74,7 +74,7 @@ k_fill(T *buf, int64_t pitch, int64_t frame, int nx, int ny, int rnd, int type, 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= nx || y >= ny) return;
-    const int r = mod > 0 ? (int)(blockIdx.z % mod) : rnd;
+    const int r = mod > 0 ? (int)((blockIdx.z + (unsigned)rnd) % mod) : rnd;   // frame k of a batch that starts at global frame `rnd`
     buf[(int64_t)blockIdx.z * frame + (int64_t)y * pitch + x] =
         wide ? pattern_wide<T>(x, y + y_offset, r, type) : pattern<T>(x, y + y_offset, r, type);
 }

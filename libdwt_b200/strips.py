@@ -93,12 +93,12 @@ class NumpyEngine:
 # oracle-backed engine) and by the single-GPU emulation test (with the device engine).  The multi-process
 # driver below does the same steps with the exchanges going through torch.distributed.
 # ======================================================================================================
-def forward_strips_local(image, world, levels_distributed, engine, j_max=-1):
+def forward_strips_local(image, world, levels_distributed, engine, j_max=-1, halo_lines=4):
     """Returns the Mallat-layout forward transform of `image` computed strip-wise by `world` emulated ranks."""
     H, W = image.shape
     J = _full_depth(W, H) if j_max < 0 else min(j_max, _full_depth(W, H))
     Jd = min(levels_distributed, J)
-    plan = StripPlan(W, H, world, Jd)
+    plan = StripPlan(W, H, world, Jd, halo_lines)
     out = np.empty_like(image)
     ll = np.empty((ceil_div_pow2(H, Jd), ceil_div_pow2(W, Jd)), dtype=image.dtype)
     for r in range(world):
@@ -116,10 +116,10 @@ def forward_strips_local(image, world, levels_distributed, engine, j_max=-1):
     return out, J
 
 
-def inverse_strips_local(coeffs, world, levels_distributed, engine, J):
+def inverse_strips_local(coeffs, world, levels_distributed, engine, J, halo_lines=4):
     H, W = coeffs.shape
     Jd = min(levels_distributed, J)
-    plan = StripPlan(W, H, world, Jd)
+    plan = StripPlan(W, H, world, Jd, halo_lines)
     h_d, w_d = ceil_div_pow2(H, Jd), ceil_div_pow2(W, Jd)
     ll = np.ascontiguousarray(coeffs[:h_d, :w_d])
     if J > Jd:

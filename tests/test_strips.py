@@ -39,6 +39,46 @@ def test_strip_scheme_is_bit_exact(oracle, kind):
                 assert back.tobytes() == ref.tobytes(), (W, H, G, Jd)
 
 
+def test_halo_of_two_rows_per_level_is_enough_for_cdf53(oracle):
+    """The C ABI (csrc/strips.cu) holds HALO * 2^Jd rows beyond the owned ones with HALO = the lifting reach: 2 for CDF 5/3."""
+    from libdwt_b200 import strips
+    for (w, t) in (("53", "i"), ("53", "s")):
+        eng = oracle_engine(oracle, w, t)
+        for (W, H, G, Jd) in ((256, 512, 2, 3), (300, 1000, 3, 2), (64, 2048, 8, 3), (517, 777, 2, 1)):
+            img = oracle.fill(np.zeros((H, W), DT[t]), t)
+            want = img.copy()
+            J = oracle.fwd2(want, w, t)
+            got, _ = strips.forward_strips_local(img, G, Jd, eng, halo_lines=2)
+            assert got.tobytes() == want.tobytes(), (w, t, W, H, G, Jd)
+            back = strips.inverse_strips_local(want, G, Jd, eng, J, halo_lines=2)
+            ref = want.copy()
+            oracle.inv2(ref, w, t, j_max=J)
+            assert back.tobytes() == ref.tobytes(), (w, t, W, H, G, Jd)
+
+
+def test_c_abi_plan_equals_the_python_model():
+    """dwtb200_strips_plan / dwtb200_strips_band (host arithmetic of csrc/strips.cu, no device needed) against StripPlan."""
+    import libdwt_b200 as d
+    from libdwt_b200.strips import StripPlan
+    cases = [(65536, 65536, 8, 5, 4), (65536, 65536, 8, 4, 4), (8192, 8192, 2, 2, 4), (300, 1000, 3, 3, 4), (517, 777, 2, 1, 2),
+             (64, 2048, 8, 3, 2), (7919, 6007, 4, 3, 4), (4096, 4097, 4, 4, 4), (130, 777, 3, 2, 4), (1000, 37, 1, 2, 4)]
+    for (W, H, G, Jd, hl) in cases:
+        p = StripPlan(W, H, G, Jd, hl)
+        for r in range(G):
+            c = d.strips_plan(W, H, G, Jd, hl, r)
+            assert (c.own0, c.own1) == p.owned(r) and (c.ext0, c.ext1) == p.extended(r) and c.halo == p.halo, (W, H, G, Jd, r)
+            own, ext, off = p.ll_rows(r)
+            assert (c.ll_own0, c.ll_own1) == own and (c.ll_ext0, c.ll_ext1) == ext and c.ll_ext0 == off
+            assert (c.ll_w, c.ll_h) == (-(-W >> Jd), -(-H >> Jd))
+            nonempty = all(b > a for a, b in (p.owned(q) for q in range(G)))
+            assert bool(c.neighbours_only) == (p.neighbours_only() and nonempty or G == 1 and nonempty)
+            for j in range(Jd):
+                b, m = d.strips_band(W, H, G, Jd, hl, r, j), p.bands(r, j)
+                assert (b["off"], b["nly_g"], b["nly_l"]) == (m["off"], m["nly_g"], m["nly_l"])
+                assert (b["extL0"], b["extL1"]) == m["extL"] and (b["extH0"], b["extH1"]) == m["extH"]
+                assert (b["ownL0"], b["ownL1"]) == m["ownL"] and (b["ownH0"], b["ownH1"]) == m["ownH"]
+
+
 def test_plan_geometry():
     from libdwt_b200.strips import StripPlan
     p = StripPlan(65536, 65536, 8, 4)
