@@ -266,6 +266,16 @@ int dwtb200_sync(void);                 /* wait for the library stream */
 int dwtb200_timer_start(void);          /* record an event on the library stream */
 double dwtb200_timer_stop_ms(void);     /* record, synchronise, elapsed milliseconds (< 0 on error) */
 void *dwtb200_stream(void);             /* cudaStream_t of the library stream */
+/* the same for the calls made on ONE image: both events are recorded on the image's own stream (the one its kernels are
+ * launched on), so nothing but that image's work lies between them */
+int dwtb200_image_timer_start(dwtb200_image *img);
+double dwtb200_image_timer_stop_ms(dwtb200_image *img);
+/* a series of marks recorded on the image's stream WITHOUT synchronising (the host runs ahead, so no host latency falls between two
+ * marks); _read waits for the last mark, stores the milliseconds between consecutive marks in ms[0 .. ) and returns their number
+ * (< 0: error); dwtb200_image_wait orders `img`'s later work after everything queued so far on `other` (no host wait) */
+int dwtb200_image_timer_mark(dwtb200_image *img);
+int dwtb200_image_timer_read(dwtb200_image *img, double *ms, int capacity);
+int dwtb200_image_wait(dwtb200_image *img, dwtb200_image *other);
 /* write `bytes` of device scratch so the 126 MB L2 holds none of the previous step's data */
 int dwtb200_flush_l2(size_t bytes);
 

@@ -61,6 +61,8 @@ SYMBOLS = [
     ("dwtb200_volume_fill", _i, [_vp]), ("dwtb200_volume_fwd3", _i, [_vp]), ("dwtb200_volume_inv3", _i, [_vp]),
     ("dwtb200_sync", _i, []), ("dwtb200_timer_start", _i, []), ("dwtb200_timer_stop_ms", _dbl, []),
     ("dwtb200_stream", _vp, []), ("dwtb200_flush_l2", _i, [_sz]),
+    ("dwtb200_image_timer_start", _i, [_vp]), ("dwtb200_image_timer_stop_ms", _dbl, [_vp]),
+    ("dwtb200_image_timer_mark", _i, [_vp]), ("dwtb200_image_timer_read", _i, [_vp, C.POINTER(_dbl), _i]), ("dwtb200_image_wait", _i, [_vp, _vp]),
     # one image as row strips over the GPUs of a box
     ("dwtb200_strips_plan", _i, [_i, _i, _i, _i, _i, _i, _vp]), ("dwtb200_strips_band", _i, [_i, _i, _i, _i, _i, _i, _i, _ip]),
     ("dwtb200_strips_create", _vp, [_i, _i, _i, _i, _i, _i, C.c_char_p]), ("dwtb200_strips_connect", _i, [_vp]),
@@ -378,6 +380,25 @@ class DeviceImage:
         if r < 0:
             raise DwtError(self.L.c.dwtb200_last_error().decode())
         return r
+
+    def timer_start(self):
+        self.L.check(self.L.c.dwtb200_image_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        return self.L.c.dwtb200_image_timer_stop_ms(self.h)
+
+    def mark(self):
+        self.L.check(self.L.c.dwtb200_image_timer_mark(self.h))
+
+    def read_marks(self, capacity=4096):
+        buf = (C.c_double * capacity)()
+        n = self.L.c.dwtb200_image_timer_read(self.h, buf, capacity)
+        if n < 0:
+            raise DwtError(self.L.c.dwtb200_last_error().decode())
+        return list(buf[:n])
+
+    def wait_for(self, other):
+        self.L.check(self.L.c.dwtb200_image_wait(self.h, other.h))
 
     def copy_from(self, other):
         self.L.check(self.L.c.dwtb200_image_copy(self.h, other.h))

@@ -31,6 +31,12 @@ __device__ __forceinline__ void chain_wait(const Chain &c, uint32_t gen, int fra
     const uint32_t *f = c.in + (size_t)frame * c.in_nblocks + block;
     while ((int32_t)(ld_acquire_gpu(f) - target) < 0) __nanosleep(40);
 }
+// the same question without waiting
+__device__ __forceinline__ bool chain_test(const Chain &c, uint32_t gen, int frame, int block)
+{
+    const uint32_t target = (gen + 1u) * (uint32_t)c.in_need;
+    return (int32_t)(ld_acquire_gpu(c.in + (size_t)frame * c.in_nblocks + block) - target) >= 0;
+}
 // one thread, after a CTA-wide barrier that follows the CTA's stores
 __device__ __forceinline__ void chain_signal(const Chain &c, int frame, int block)
 {
@@ -63,6 +69,28 @@ struct ChainWindow {
             lo = b;
         }
         asm volatile("fence.proxy.async;" ::: "memory");   // the data is read next by the bulk-copy (async) proxy
+    }
+    // need_row without waiting: false when a block the row needs is not complete yet (what was verified so far is kept)
+    __device__ __forceinline__ bool try_row(const Chain &c, uint32_t gen, int frame, int row)
+    {
+        const int b = chain_block(c, row);
+        if (b >= lo && b <= hi) return true;
+        if (hi < 0) {
+            if (!chain_test(c, gen, frame, b)) return false;
+            lo = hi = b;
+        } else if (b > hi) {
+            for (int x = hi + 1; x <= b; x++) {
+                if (!chain_test(c, gen, frame, x)) return false;
+                hi = x;
+            }
+        } else {
+            for (int x = lo - 1; x >= b; x--) {
+                if (!chain_test(c, gen, frame, x)) return false;
+                lo = x;
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        return true;
     }
 };
 

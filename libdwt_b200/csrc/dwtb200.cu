@@ -75,6 +75,7 @@ struct Ctx {
     int pfd = 1;
     int pipeline = 1;   // pipelined host path for large dense images
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
+    int ring_v2 = 1;    // the ring levels take the 256-column kernels (kernels_ring2.cu) where they apply; scoped off for the interleaved layout
     int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // strip-length search range of the ring kernels (0: defaults)
     int64_t pyr_max_in = (int64_t)512 * 512;   // only levels with at most this many input samples per frame are fused
     int vol3 = 1;       // forward 3-D: one pass over the volume where the tile kernel applies (kernels_vol.cu, k_vol3_fwd)
@@ -127,6 +128,9 @@ int ensure_stage(size_t bytes)
 struct dwtb200_image {
     cudaStream_t st = nullptr;   // independent images overlap: the small levels of one run in the shadow of another's big ones
     cudaEvent_t ev = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // dwtb200_image_timer_*: events on the image's own stream
+    std::vector<cudaEvent_t> marks;           // dwtb200_image_timer_mark
+    size_t nmarks = 0;
     int kind = 0, ox = 0, oy = 0, frames = 0;
     size_t es = 4;
     int64_t pitch = 0, frame = 0;   // elements
@@ -245,6 +249,7 @@ int dwtb200_init(int device)
     g.sm_count = prop.multiProcessorCount;
     CK(preload_stream());
     CK(preload_ring());
+    CK(preload_ring2());
     CK(preload_inplace());
     CK(preload_pyr());
     CK(preload_tail());
@@ -415,6 +420,9 @@ void dwtb200_image_destroy(dwtb200_image *im)
     if (im->st) cudaStreamSynchronize(im->st);
     g.live.erase(im);
     if (im->ev) cudaEventDestroy(im->ev);
+    if (im->t0) cudaEventDestroy(im->t0);
+    if (im->t1) cudaEventDestroy(im->t1);
+    for (cudaEvent_t e : im->marks) cudaEventDestroy(e);
     if (im->st) cudaStreamDestroy(im->st);
     for (auto &kv : im->graphs) {
         cudaGraphExecDestroy(kv.second.exec);
@@ -670,13 +678,27 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.narrow = g.narrow;
     p.dbg = g.dbg;
     p.pfd = inverse ? 1 : g.pfd;
-    const int outw = stream_out_width(im->kind, p.narrow);
+    // second-generation ring kernels (256-column warp windows): every forward level, inverse levels of the rows-first wavelets
+    const int vec = im->es == 8 ? 2 : (p.narrow ? 2 : 4);   // elements per subband store of a lane
+    p.sub_aligned = (p.nLx % vec) == 0;
+    // (an inverse level whose HL / HH column origin is not 16-byte aligned falls back to the register kernels and their geometry)
+    const bool ring_here = !p.narrow && (inverse ? ((g.ring & 2) && p.sub_aligned) : (g.ring & 1));
+    const int forced = (g.ring >> 4) & 7;   // DWTB200_TUNE_RING bits 4-6 force a shape
+    const bool v2 = ring_here && g.ring_v2 && (forced == 0 || forced == RING_CFG_V2) && (!inverse || ring2_inverse_ok(im->kind)) &&
+                    ring2_width_ok(im->kind, W);
+    const int outw = v2 ? ring2_out_width(im->kind) : stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
+    if (v2) {
+        p.cfg = RING_CFG_V2;
+        const int cw = ring_cta_warps(p.cfg), nb = (p.ncg + cw - 1) / cw;
+        p.bw = (p.ncg + nb - 1) / nb;
+        p.nbands = (p.ncg + p.bw - 1) / p.bw;
+    } else
     {   // ring kernels: bands of at most ring_cta_warps() column groups, as equal as possible
         // CTA shape: 7 consumer warps x 2 CTAs per SM, unless the row splits into bands of exactly 5 column groups (2048-
         // or 1080p-wide frames) AND the batch is large enough for >= 2 waves of the smaller CTAs: then 5 x 3 keeps 15 instead
         // of 10 consumer warps per SM busy (2048^2 x 64: 419 -> 445 Gpixel/s; a 4-frame level of 2048^2 is better off with 7 x 2)
-        p.cfg = (g.ring >> 4) & 7;   // DWTB200_TUNE_RING bits 4-6 force a shape
+        p.cfg = forced == RING_CFG_V2 ? 0 : forced;
         if (p.cfg == 0) {
             const int nb7 = (p.ncg + 6) / 7, bw7 = (p.ncg + nb7 - 1) / nb7;   // bands of the default shape: 5 of 7 warps busy?
             const int nb5 = (p.ncg + 4) / 5, bw5 = (p.ncg + nb5 - 1) / nb5;
@@ -703,14 +725,30 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
             const int cfg = p.cfg;
             const int64_t slots = (int64_t)g.sm_count * ring_ctas_per_sm(cfg);
             const int ns = kind_lifting_steps(im->kind), warm = inverse ? ns : ns / 2 + (ns == 4 ? 1 : 0);
-            const int lo = g.ring_pps_min > 0 ? g.ring_pps_min : (ns == 4 ? 12 : 8), hi = g.ring_pps_max > 0 ? g.ring_pps_max : 40;
+            int lo = g.ring_pps_min > 0 ? g.ring_pps_min : (ns == 4 ? 12 : 8), hi = g.ring_pps_max > 0 ? g.ring_pps_max : 40;
+            // Level 0 is not fed by a predecessor through the chain, its own ramp and ragged end are paid in full: measured on one
+            // 8192^2 float image (profiles/single_r2_pps.txt), strips of 14 / 18 / 24 pairs (4.95 / 3.85 / 2.9 waves) take 100.3 /
+            // 100.4 / 101.7 us, the 35 pairs (2.0 waves) the model below used to pick 109.6 us, 16 / 22 / 30 pairs (4.3 / 3.2 / 2.3
+            // waves) 105 - 108 us.  Fitted: the re-read of the warm-up rows costs a quarter of its bytes (reads only, half of them
+            // L2 hits), an incomplete last wave 30 % of its idle slots (the running CTAs get the bandwidth), and few waves a ragged
+            // end of 0.36 / waves^2.  The levels behind level 0 run at the pace of their predecessor and keep the old model.
+            const bool head = j == 0 && g.ring_waves != 99;
             double best = 1e30;
             pps = lo;
+            // a level that cannot fill one wave of CTAs even with the shortest regular strips is latency-bound: its time is the
+            // (warm-up + pps) iterations one CTA walks through, so it gets the shortest strips that still fit one wave
+            if (!head && g.ring_pps_min == 0 && (int64_t)p.nbands * ((units + lo - 1) / lo) * im->frames <= slots) {
+                int c = lo;
+                while (c > 4 && (int64_t)p.nbands * ((units + (c - 1) - 1) / (c - 1)) * im->frames <= slots) c--;
+                lo = hi = c;
+            }
             for (int c = lo; c <= hi; c++) {
                 const int64_t n = (int64_t)p.nbands * ((units + c - 1) / c) * im->frames;
                 const int64_t waves = (n + slots - 1) / slots;
                 const double eff = (double)n / (double)(waves * slots);
-                const double cost = (1.0 + 0.5 * warm / c) / eff + 0.002 * c;
+                const double wv = (double)n / (double)slots;
+                const double cost = head ? (1.0 + 0.25 * warm / c) * (1.0 + 0.3 * (1.0 / eff - 1.0)) * (1.0 + 0.36 / (wv * wv))
+                                         : (1.0 + 0.5 * warm / c) / eff + 0.002 * c;
                 if (cost < best - 1e-9) {
                     best = cost;
                     pps = c;
@@ -727,9 +765,6 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     }
     p.pps = pps;
     p.nstrips = (units + pps - 1) / pps;
-    const int vec = im->es == 8 ? 2 : (p.narrow ? 2 : 4);   // elements per subband store of a lane
-    p.sub_aligned = (p.nLx % vec) == 0;
-
 }
 
 // parameters of forward level j reading `in` (LL_{j-1} or the source plane); returns where LL_j goes
@@ -1306,6 +1341,13 @@ constexpr int IP_STD_MIN = 32;            // a level with a side below this is e
 constexpr int IP_WHOLE_MAX = 256 * 256;   // samples (all frames) up to which a level is evaluated by k_ip_phase alone
 constexpr int IP_TOP = 8, IP_RIGHT = 6;   // frame whose sweep order differs from rows-then-columns (7 / 8 rows, 5 columns)
 
+// the interleaved layout is served by the first-generation ring kernels: their geometry must be the one level_geometry computes
+struct RingV2Off {
+    int prev;
+    RingV2Off() : prev(g.ring_v2) { g.ring_v2 = 0; }
+    ~RingV2Off() { g.ring_v2 = prev; }
+};
+
 // one level of the 9/7 family: the ordinary level kernel, then the exact schedule over the top and right frame
 int ip_level(dwtb200_image *im, bool inverse, const LevelParams &lp)
 {
@@ -1511,6 +1553,7 @@ int inplace_transform(dwtb200_image *im, bool inverse, int J)
 {
     if (im->kind != DWTB200_CDF97_F32 && im->kind != DWTB200_CDF53_F32)
         return fail(DWTB200_EINVAL, "in-place family: CDF 9/7 float and CDF 5/3 float only (kind %d)", im->kind);
+    RingV2Off v2off;
     im->last_launches = 0;
     if (J <= 0) return DWTB200_OK;
     DensePlan pl53;
@@ -2391,6 +2434,70 @@ double dwtb200_timer_stop_ms(void)
     return (double)ms;
 }
 void *dwtb200_stream(void) { return (void *)g.st0; }
+
+// device time of the calls made on ONE image between start and stop: CUDA events recorded on the image's own stream (the stream
+// its kernels are launched on), no cross-stream joins in the timed region
+int dwtb200_image_timer_start(dwtb200_image *im)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im) return fail(DWTB200_EINVAL, "image_timer_start: null image");
+    if (!im->t0) {
+        CK(cudaEventCreate(&im->t0));
+        CK(cudaEventCreate(&im->t1));
+    }
+    CK(cudaEventRecord(im->t0, im->st));
+    return DWTB200_OK;
+}
+// A series of marks on the image's stream, recorded without synchronising: the host runs ahead of the device, so the interval
+// between two marks around a call is the call's device time with no host latency in it.  dwtb200_image_timer_read synchronises and
+// returns the intervals between consecutive marks (n marks -> n - 1 intervals), then forgets the marks.
+int dwtb200_image_timer_mark(dwtb200_image *im)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im) return fail(DWTB200_EINVAL, "image_timer_mark: null image");
+    if (im->nmarks == im->marks.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        im->marks.push_back(e);
+    }
+    CK(cudaEventRecord(im->marks[im->nmarks++], im->st));
+    return DWTB200_OK;
+}
+int dwtb200_image_timer_read(dwtb200_image *im, double *ms, int capacity)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im || !ms) return fail(DWTB200_EINVAL, "image_timer_read: null argument");
+    int n = 0;
+    if (im->nmarks) CK(cudaEventSynchronize(im->marks[im->nmarks - 1]));
+    for (size_t i = 0; i + 1 < im->nmarks && n < capacity; i++) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, im->marks[i], im->marks[i + 1]));
+        ms[n++] = (double)t;
+    }
+    im->nmarks = 0;
+    return n;
+}
+// everything queued later on `im` runs after everything queued so far on `other` (device-side ordering, no host wait)
+int dwtb200_image_wait(dwtb200_image *im, dwtb200_image *other)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im || !other) return fail(DWTB200_EINVAL, "image_wait: null image");
+    wait_for_image(im->st, other);
+    return DWTB200_OK;
+}
+double dwtb200_image_timer_stop_ms(dwtb200_image *im)
+{
+    API_LOCK();
+    if (g.dev < 0 || !im || !im->t0) return -1.0;
+    if (cudaEventRecord(im->t1, im->st) != cudaSuccess || cudaEventSynchronize(im->t1) != cudaSuccess) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, im->t0, im->t1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 int dwtb200_flush_l2(size_t bytes)
 {

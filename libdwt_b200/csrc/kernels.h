@@ -67,6 +67,15 @@ void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t s
 cudaError_t preload_ring();
 void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
 void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st);
+// second generation (kernels_ring2.cu, cfg 4): 256-column windows, 8 consumer warps, producer folded into warp 0; inverse for the
+// rows-first (float / double) wavelets only
+cudaError_t preload_ring2();
+void launch_fwd_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st);
+void launch_inv_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st);
+bool ring2_inverse_ok(int kind);
+bool ring2_width_ok(int kind, int W);
+int ring2_out_width(int kind);
+constexpr int RING_CFG_V2 = 4;
 bool ring_interleaved_ok(int kind);   // p.il != nullptr is supported for this kind ...
 bool ring_interleaved_cfg_ok(int cfg);   // ... and this CTA shape
 int ring_warps_per_sm(int cfg);

@@ -23,11 +23,11 @@
 // /root/reference/src/libdwt.c lines each pass replaces).
 #include <type_traits>
 #include "chain.cuh"
+#include "ring_common.cuh"
 #include "stream_common.cuh"
 
 namespace dwtb200 {
 
-constexpr int RING_SLOTS = 6;    // row pairs in flight per CTA
 // CTA shapes (consumer warps per CTA, CTAs per SM).  The register file gives 128 registers per thread to
 // 16 warps per SM, 96 to 20: with 8 + 1 warps twice per SM ptxas has to spill the subband pointers into
 // the loop (measured: 104 us, long-scoreboard stalls on the LDLs), so the consumers get 7 warps.
@@ -43,93 +43,6 @@ template <int CW_, int NCTA_> struct RingCfg {
     static constexpr int SLOTB_IL = 5 * (SLOTB / 4);
     static constexpr int DATA_IL = (RING_SLOTS * SLOTB_IL + 127) / 128 * 128;
     static constexpr int SMEM_IL = DATA_IL + 2 * RING_SLOTS * 8;
-};
-
-// ---- mbarrier / bulk-copy primitives -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-template <class T, int N> __device__ __forceinline__ void lds_vec(uint32_t addr, T *v)
-{
-    static_assert(N * sizeof(T) == 32 || N * sizeof(T) == 16, "lane width");
-#pragma unroll
-    for (int i = 0; i < (int)(N * sizeof(T)) / 16; i++) {
-        int4 r;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr + 16 * i));
-        *reinterpret_cast<int4 *>(reinterpret_cast<char *>(v) + 16 * i) = r;
-    }
-}
-template <class T> __device__ __forceinline__ T lds_one(uint32_t addr)
-{
-    T v;
-    if constexpr (sizeof(T) == 4) {
-        uint32_t r;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
-        v = *reinterpret_cast<T *>(&r);
-    } else {
-        unsigned long long r;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr));
-        v = *reinterpret_cast<T *>(&r);
-    }
-    return v;
-}
-
-struct RingState {   // position in a consumer's ring, advanced identically by producer and consumer
-    int slot = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void next()
-    {
-        if (++slot == RING_SLOTS) {
-            slot = 0;
-            phase ^= 1;
-        }
-    }
 };
 
 // =====================================================================================================
@@ -529,7 +442,7 @@ constexpr int RING_NCFG = 4;
 template <class WV> constexpr bool ring_il() { return std::is_same<WV, W97F>::value || std::is_same<WV, W53F>::value; }
 bool ring_interleaved_ok(int kind) { return kind == K_CDF97_F32 || kind == K_CDF53_F32; }
 // CTA shapes whose five-segment inverse ring still fits the SM's shared memory NCTA times (all but 8 x 2)
-bool ring_interleaved_cfg_ok(int cfg) { return cfg != 2; }
+bool ring_interleaved_cfg_ok(int cfg) { return cfg != 2 && cfg != RING_CFG_V2; }
 template <class F> static void dispatch_cfg(int cfg, F &&f)
 {
     if (cfg == 1) f(RingCfg<15, 1>{});
@@ -561,6 +474,7 @@ int ring_warps_per_sm(int cfg) { return ring_cta_warps(cfg) * ring_ctas_per_sm(c
 
 void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st)
 {
+    if (cfg == RING_CFG_V2 && !p.il) return launch_fwd_ring2(kind, p, frames, st);
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
         constexpr int V = 32 / (int)sizeof(typename WV::T);
@@ -580,6 +494,7 @@ void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
 
 void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st)
 {
+    if (cfg == RING_CFG_V2 && !p.il && ring2_inverse_ok(kind)) return launch_inv_ring2(kind, p, frames, st);
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
         constexpr int V = 32 / (int)sizeof(typename WV::T);
@@ -596,7 +511,7 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         });
     });
 }
-int ring_cta_warps(int cfg) { return cfg == 1 ? 15 : cfg == 2 ? 8 : cfg == 3 ? 5 : 7; }
+int ring_cta_warps(int cfg) { return cfg == 1 ? 15 : (cfg == 2 || cfg == RING_CFG_V2) ? 8 : cfg == 3 ? 5 : 7; }
 int ring_ctas_per_sm(int cfg) { return cfg == 1 ? 1 : cfg == 3 ? 3 : 2; }
 
 }  // namespace dwtb200

@@ -104,6 +104,8 @@ FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-
             "persistent+tinytail": (BIG, 16, BIG), "stream>persistent": (256 * 256, 2720, 256 * 256),
             "regstream-only": (0, 0, 0, 0), "regstream+bigtail": (0, 16384, 0, 0), "ringfwd-reginv": (0, 1024, 0, 1),
             "ring15x1": (0, 1024, 0, 3 | (1 << 4)), "ring5x3": (0, 1024, 0, 3 | (3 << 4)),
+            # first-generation ring kernels (240-column windows, producer warp) forced: the default is the 256-column generation
+            "ring7x2-gen1": (0, 1024, 0, 3 | (5 << 4)), "ring-gen2-forced": (0, 0, 0, 3 | (4 << 4)),
             # the same mixes without the dataflow chain between the kernels of a pyramid (DWTB200_TUNE_CHAIN = 0)
             "nochain-default": (1024 * 1024, 1024, 0, 3, 0), "nochain-stream": (0, 0, 0, 3, 0), "nochain-tile": (BIG, 16, 0, 3, 0),
             "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1),
@@ -157,6 +159,42 @@ def test_every_kernel_family_gives_the_same_bits(dev, oracle, kind, family):
                 if not (bits(got, t) == bits(want, t)).all():
                     fails.append(f"batch frame {k} inverse: " + describe_mismatch(got, want, t))
             img.close()
+    finally:
+        set_tuning(L, DEFAULT_TUNING)
+    report(fails)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=KIDS)
+def test_ring_gen2_on_whole_window_widths(dev, oracle, kind):
+    """kernels_ring2.cu takes rows that are a whole number of 256-column (double: 128-column) warp windows: one window, several windows
+    of one band, more than one band (> 8 windows), few and many rows, with every level forced onto the streaming kernels."""
+    w, t = kind
+    L = dev.lib()
+    set_tuning(L, (0, 0, 0))
+    fails = []
+    try:
+        for (ox, oy) in ((256, 37), (128, 128), (512, 300), (768, 130), (1024, 77), (2304, 64), (2560, 33), (4096, 40)):
+            for (j, d1) in ((-1, 0), (1, 0)):
+                fails += both(dev, oracle, w, t, ox, oy, j, d1)
+        img = dev.DeviceImage(dev.kind_of(w, t), 1024, 200, 3)   # a batch: frames in grid.y
+        img.fill(0, 0, 6)
+        J = img.fwd2()
+        for k in range(3):
+            want = oracle.fill(np.zeros((200, 1024), DT[t]), t, rand=k % 6)
+            oracle.fwd2(want, w, t)
+            got = img.download(frame=k)
+            if not (bits(got, t) == bits(want, t)).all():
+                fails.append(f"batch frame {k} forward: " + describe_mismatch(got, want, t))
+        img.inv2(J)
+        for k in range(3):
+            want = oracle.fill(np.zeros((200, 1024), DT[t]), t, rand=k % 6)
+            got = img.download(frame=k)
+            ref = want.copy()
+            oracle.fwd2(ref, w, t)
+            oracle.inv2(ref, w, t, j_max=J)
+            if not (bits(got, t) == bits(ref, t)).all():
+                fails.append(f"batch frame {k} inverse: " + describe_mismatch(got, ref, t))
+        img.close()
     finally:
         set_tuning(L, DEFAULT_TUNING)
     report(fails)
