@@ -43,6 +43,11 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
     const int tid = threadIdx.x;
     const int TAIL_THREADS = blockDim.x;
 
+    // Lines shorter than TAIL_FAST_MIN are evaluated pair by pair from a mirrored 2 * HALO + 2 window: folding every tap index
+    // (lifting.cuh: reflect, a loop when the line is shorter than the window) made each of the last levels cost ~1.5 us of
+    // dependent integer work on a handful of threads.  The folded indices of a level come from a table instead, built once per
+    // level by as many threads as it has entries: tap q of pair k is tab[2 k + q] = reflect(2 k + q - HALO, n).
+    __shared__ short tabx[TAIL_FAST_MIN + 2 * WV::HALO + 2], taby[TAIL_FAST_MIN + 2 * WV::HALO + 2];
     int w = cdiv_pow2(p.W0, p.j0), h = cdiv_pow2(p.H0, p.j0);
     for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[(t / w) * tail_pitch(w) + (t % w)] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
     T *in = bufA, *other = bufB;
@@ -51,6 +56,11 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
     for (int j = p.j0; j < p.j1; j++) {
         const int nlx = (w + 1) >> 1, nhx = w >> 1, nly = (h + 1) >> 1, nhy = h >> 1;
         const int pw = tail_pitch(w), pn = tail_pitch(nlx);   // pitches of this level's band and of the next one
+        if ((w < TAIL_FAST_MIN && w >= 2) || (h < TAIL_FAST_MIN && h >= 2)) {
+            if (w < TAIL_FAST_MIN && w >= 2 && tid < w + 2 * WV::HALO + 2) tabx[tid] = (short)reflect(tid - WV::HALO, w);
+            if (h < TAIL_FAST_MIN && h >= 2 && tid >= 64 && tid - 64 < h + 2 * WV::HALO + 2) taby[tid - 64] = (short)reflect(tid - 64 - WV::HALO, h);
+            __syncthreads();
+        }
         // ---- rows: in -> other, row y = [L (nlx) | H (nhx)] ----
         T *rows = in;
         if (!(WV::GUARD && w <= 1)) {
@@ -87,7 +97,7 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                     const T *line = in + y * pw;
                     T win[2 * WV::HALO + 2];
 #pragma unroll
-                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = line[reflect(2 * k - WV::HALO + i, w)];
+                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = line[tabx[2 * k + i]];
                     T L, H;
                     window_fwd<WV>(win, L, H);
                     rows[y * pw + k] = L;
@@ -129,7 +139,7 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                 const int k = t / w, x = t % w;
                 T win[2 * WV::HALO + 2];
 #pragma unroll
-                for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = rows[reflect(2 * k - WV::HALO + i, h) * pw + x];
+                for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = rows[taby[2 * k + i] * pw + x];
                 T L, H;
                 window_fwd<WV>(win, L, H);
                 if (x < nlx) next[k * pn + x] = L;
@@ -186,6 +196,7 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
     const int tid = threadIdx.x;
     const int TAIL_THREADS = blockDim.x;
     const int w0 = cdiv_pow2(p.W0, p.j0), pm = tail_pitch(w0);
+    __shared__ short itabx[TAIL_FAST_MIN + 2 * WV::HALO + 2], itaby[TAIL_FAST_MIN + 2 * WV::HALO + 2];
     if (mal) {
         const int h0 = cdiv_pow2(p.H0, p.j0);
         for (int t = tid; t < w0 * h0; t += TAIL_THREADS) mal[(t / w0) * pm + (t % w0)] = ld(src + (int64_t)(t / w0) * p.src_pitch + (t % w0));
@@ -209,6 +220,18 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
             return (y < nly && x < nlx) ? in[y * pl + x] : (mal ? mal[y * pm + x] : ld(src + (int64_t)y * p.src_pitch + x));
         };
         const bool do_rows = !(WV::GUARD && w <= 1), do_cols = !(WV::GUARD && h <= 1);
+        // short lines: the Mallat position of every (mirrored) tap from a table, see fwd_tail_body
+        if ((w < TAIL_FAST_MIN && w >= 2) || (h < TAIL_FAST_MIN && h >= 2)) {
+            if (w < TAIL_FAST_MIN && w >= 2 && tid < w + 2 * WV::HALO + 2) {
+                const int c = reflect(tid - WV::HALO, w);
+                itabx[tid] = (short)((c & 1) ? nlx + (c >> 1) : (c >> 1));
+            }
+            if (h < TAIL_FAST_MIN && h >= 2 && tid >= 64 && tid - 64 < h + 2 * WV::HALO + 2) {
+                const int c = reflect(tid - 64 - WV::HALO, h);
+                itaby[tid - 64] = (short)((c & 1) ? nly + (c >> 1) : (c >> 1));
+            }
+            __syncthreads();
+        }
         if constexpr (!WV::INV_COLS_FIRST) {
             // rows: M -> tmp (h x w, rows still in Mallat order)
             if (do_rows && w >= TAIL_FAST_MIN) {
@@ -228,10 +251,7 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                     const int y = t / nlx, k = t % nlx;
                     T win[2 * WV::HALO + 2];
 #pragma unroll
-                    for (int i = 0; i < 2 * WV::HALO + 2; i++) {
-                        const int c = reflect(2 * k - WV::HALO + i, w);
-                        win[i] = M(y, (c & 1) ? nlx + (c >> 1) : (c >> 1));
-                    }
+                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = M(y, itabx[2 * k + i]);
                     T E, O;
                     window_inv<WV>(win, E, O);
                     tmp[y * pw + 2 * k] = E;
@@ -271,10 +291,7 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                 if (do_cols && h >= 2) {
                     T win[2 * WV::HALO + 2];
 #pragma unroll
-                    for (int i = 0; i < 2 * WV::HALO + 2; i++) {
-                        const int c = reflect(2 * k - WV::HALO + i, h);
-                        win[i] = tmp[((c & 1) ? nly + (c >> 1) : (c >> 1)) * pw + x];
-                    }
+                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = tmp[itaby[2 * k + i] * pw + x];
                     window_inv<WV>(win, E, O);
                 } else {
                     E = do_cols ? one_inv<WV>(tmp[x]) : tmp[x];   // h == 1
@@ -308,10 +325,7 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                 if (h >= 2) {
                     T win[2 * WV::HALO + 2];
 #pragma unroll
-                    for (int i = 0; i < 2 * WV::HALO + 2; i++) {
-                        const int c = reflect(2 * k - WV::HALO + i, h);
-                        win[i] = M((c & 1) ? nly + (c >> 1) : (c >> 1), x);
-                    }
+                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = M(itaby[2 * k + i], x);
                     T E, O;
                     window_inv<WV>(win, E, O);
                     tmp[(2 * k) * pw + x] = E;
@@ -347,10 +361,7 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                 if (w >= 2) {
                     T win[2 * WV::HALO + 2];
 #pragma unroll
-                    for (int i = 0; i < 2 * WV::HALO + 2; i++) {
-                        const int c = reflect(2 * k - WV::HALO + i, w);
-                        win[i] = tmp[y * pw + ((c & 1) ? nlx + (c >> 1) : (c >> 1))];
-                    }
+                    for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = tmp[y * pw + itabx[2 * k + i]];
                     window_inv<WV>(win, E, O);
                 } else {
                     E = one_inv<WV>(tmp[y * pw]);
