@@ -56,7 +56,9 @@ int dwtb200_device_count(void);
 int dwtb200_device(void);          /* device in use, -1 before init */
 
 /* ---- pinned host images: dwt_util_alloc_image / dwt_util_free_image (src/libdwt.c:1437, 1482) ---- */
-void *dwtb200_host_alloc(size_t bytes);   /* page-locked, 16-byte aligned like memalign(16, ...) */
+/* page-locked, page-aligned; on a multi-socket host the pages are bound to the NUMA node of the GPU in use (DWTB200_NUMA=0: off) */
+void *dwtb200_host_alloc(size_t bytes);
+int dwtb200_host_numa_node(void);         /* that node; -1: not bound (single node, unknown, or switched off) */
 void dwtb200_host_free(void *ptr);
 
 /* ---- level arithmetic shared with the reference drivers (src/libdwt.c:12807-12810, inline.h:443-460) ---- */
@@ -158,6 +160,13 @@ int dwtb200_image_subband_moments(dwtb200_image *img, int frame, int size_i_big_
  * accumulated in double on the device (the reference sums sequentially in float), only the feature vector crosses PCIe. */
 enum { DWTB200_FEAT_WPS = 0, DWTB200_FEAT_MEAN = 1, DWTB200_FEAT_VAR = 2, DWTB200_FEAT_STDEV = 3, DWTB200_FEAT_MAXNORM = 4, DWTB200_FEAT_NORM = 5 };
 int dwtb200_image_features(dwtb200_image *img, int frame, int size_i_big_x, int size_i_big_y, int j_max, int feature, float *fv, int *count);
+/* dwt_util_conv_show_{s,d,i} (src/libdwt.h; src/libdwt.c:21075, 21120, 21020) on device-resident planes: the current plane of every
+ * frame of `dst` receives log(1 + |c| * 100) / 10 (float, double; logarithm in double as the reference's log_i_s) or |c| (int) of
+ * the top-left size_i_big_x x size_i_big_y samples of `src`; src == dst is allowed */
+int dwtb200_image_conv_show(dwtb200_image *src, dwtb200_image *dst, int size_i_big_x, int size_i_big_y);
+/* dwt_util_save_to_pgm_s / _d (src/libdwt.c:19794, 19877) for a device-resident frame: grey values computed on the device (one byte
+ * per sample crosses PCIe instead of the plane), the same "P2" text file written by the host */
+int dwtb200_image_save_pgm(dwtb200_image *img, int frame, const char *filename, double max_value, int size_i_big_x, int size_i_big_y);
 /* bit-exact comparison of the current planes of two images on the device: number of differing samples */
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b);
 /* max |a-b| over the current planes (float/double kinds), cf. dwt_util_compare_s (src/libdwt.c:1593) */

@@ -135,6 +135,14 @@ void cdf97_3f_op_wrapper_s(struct volume_t *src, struct volume_t *dst, int appro
  * CPU schedule of the same transform); seconds per voxel of the forward transform on a device-resident volume */
 int volume_perftest_fwd97op_s(int size, int opt_stride, int approach, int N, double *secs, long unsigned *faults);
 
+/* src/volume.h:29, 81, 34 (src/volume.c:10, 194): strides per dwt_util_get_stride(opt_stride); page-locked host memory, so the
+ * transfers of the 3-D entry points above run at PCIe speed */
+struct volume_t *volume_alloc_realiably(size_t pix_size, int size_x, int size_y, int size_z, int opt_stride);
+struct volume_t *volume_alloc_realiably_locked(size_t pix_size, int size_x, int size_y, int size_z, int opt_stride);
+void volume_free(struct volume_t *volume);
+/* src/volume-dwt.h:246 (src/volume-dwt.c:2898): the perf test over a range of cube sizes, results into data/perftest/ */
+int volume_measure_fwd97op_s(int size_min, int size_max, int size_step, int N, int opt_stride, int approach);
+
 /* device-event timing around the transforms (replaces dwt_util_get_clock in benchmarks, src/libdwt.c:18701):
  * milliseconds the device spent in the last transform call, excluding host<->device copies */
 double dwt_b200_last_transform_ms(void);

@@ -26,7 +26,7 @@ _ip = C.POINTER(C.c_int)
 SYMBOLS = [
     ("dwtb200_init", _i, [_i]), ("dwtb200_finish", None, []), ("dwtb200_last_error", C.c_char_p, []),
     ("dwtb200_device_count", _i, []), ("dwtb200_device", _i, []),
-    ("dwtb200_host_alloc", _vp, [_sz]), ("dwtb200_host_free", None, [_vp]),
+    ("dwtb200_host_alloc", _vp, [_sz]), ("dwtb200_host_free", None, [_vp]), ("dwtb200_host_numa_node", _i, []),
     ("dwtb200_ceil_log2", _i, [_i]), ("dwtb200_clamp_j", _i, [_i, _i, _i, _i]),
     ("dwtb200_fwd2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _ip, _i, _i]),
     ("dwtb200_inv2_host", _i, [_i, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _i]),
@@ -51,6 +51,7 @@ SYMBOLS = [
     ("dwtb200_image_features", _i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _ip]),
     ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
     ("dwtb200_image_copy", _i, [_vp, _vp]),
+    ("dwtb200_image_conv_show", _i, [_vp, _vp, _i, _i]), ("dwtb200_image_save_pgm", _i, [_vp, _i, C.c_char_p, _dbl, _i, _i]),
     ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
     ("dwtb200_force_generic", None, [_i]), ("dwtb200_set_strip_rows", None, [_i]),
     ("dwtb200_set_tuning", _i, [_i, C.c_longlong]),
@@ -399,6 +400,15 @@ class DeviceImage:
 
     def wait_for(self, other):
         self.L.check(self.L.c.dwtb200_image_wait(self.h, other.h))
+
+    def conv_show(self, dst=None, inner=None):
+        """dwt_util_conv_show_* of the current plane into `dst` (default: in place)."""
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        self.L.check(self.L.c.dwtb200_image_conv_show(self.h, (dst or self).h, ix, iy))
+
+    def save_pgm(self, filename, max_value, frame=0, inner=None):
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        self.L.check(self.L.c.dwtb200_image_save_pgm(self.h, frame, filename.encode(), max_value, ix, iy))
 
     def copy_from(self, other):
         self.L.check(self.L.c.dwtb200_image_copy(self.h, other.h))

@@ -29,9 +29,15 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <string>
 #include <tuple>
 #include <algorithm>
 #include <vector>
+
+#include <cctype>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "../../include/dwtb200.h"
 #include "internal.h"
@@ -141,6 +147,7 @@ struct dwtb200_image {
     uint32_t *sync = nullptr;         // chain counters of un-captured launch sequences (captured graphs own theirs)
     size_t sync_words = 0;
     int last_launches = 0, last_path = 0;
+    int kind_class() const { return dwtb200::kind_elem_class(kind); }
     typedef std::tuple<int, int, int, int, int, int, int, int, int> Key;
     struct Entry {
         cudaGraphExec_t exec;
@@ -297,12 +304,68 @@ int dwtb200_device(void) { return g.dev; }
         }                                                \
     } while (0)
 
+// Page-locked host memory on the NUMA node of the GPU.  cudaHostAlloc places the pages wherever the calling thread happens to run;
+// with one process per GPU on a two-socket host half the ranks then move every byte across the socket interconnect and the eight
+// ranks' copies pile up on one memory controller (round 1: aggregate H2D + D2H saturated at 100-130 GB/s whatever the number of
+// GPUs).  Here the block is mmap'ed, bound to the node the GPU's PCIe root port hangs off (sysfs numa_node, mbind MPOL_PREFERRED)
+// and then registered with the driver.  DWTB200_NUMA=0, a single-node host or a refused mbind fall back to cudaHostAlloc.
+namespace {
+std::map<void *, size_t> g_numa_blocks;   // blocks obtained through mmap + cudaHostRegister
+int gpu_numa_node()
+{
+    static int node = -2;
+    if (node != -2) return node;
+    node = -1;
+    const char *e = getenv("DWTB200_NUMA");
+    if (e && !atoi(e)) return node;
+    char bdf[32] = "";
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, g.dev) != cudaSuccess) {
+        cudaGetLastError();
+        return node;
+    }
+    for (char *c = bdf; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    if (FILE *f = fopen(path, "r")) {
+        int n = -1;
+        if (fscanf(f, "%d", &n) == 1) node = n;
+        fclose(f);
+    }
+    if (node >= 0 && access("/sys/devices/system/node/node1", F_OK) != 0) node = -1;   // one node: nothing to choose
+    return node;
+}
+}  // namespace
+
+int dwtb200_host_numa_node(void)
+{
+    API_LOCK();
+    if (g.dev < 0 && dwtb200_init(-1)) return -1;
+    return gpu_numa_node();
+}
+
 void *dwtb200_host_alloc(size_t bytes)
 {
     API_LOCK();
     if (g.dev < 0 && dwtb200_init(-1)) return nullptr;
+    if (!bytes) bytes = 1;
+    const int node = gpu_numa_node();
+    if (node >= 0 && node < 1024) {
+        const size_t len = (bytes + 4095) & ~(size_t)4095;
+        void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask[16] = {0};
+            mask[node / 64] = 1ul << (node % 64);
+            const long rc = syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, mask, 1025ul, 0u);
+            if (rc == 0 && cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                g_numa_blocks[p] = len;
+                return p;
+            }
+            cudaGetLastError();
+            munmap(p, len);
+        }
+    }
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
         fail(DWTB200_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -312,6 +375,13 @@ void dwtb200_host_free(void *ptr)
 {
     API_LOCK();
     if (!ptr) return;
+    auto it = g_numa_blocks.find(ptr);
+    if (it != g_numa_blocks.end()) {
+        cudaHostUnregister(ptr);
+        munmap(ptr, it->second);
+        g_numa_blocks.erase(it);
+        return;
+    }
     // the compat layer interposes dwt_util_free_image process-wide: a pointer that did not come from dwtb200_host_alloc
     // (memalign in the reference's own allocator) goes back to free(), and no CUDA error is left pending
     if (cudaFreeHost(ptr) != cudaSuccess) {
@@ -1690,6 +1760,59 @@ int dwtb200_image_subband_moments(dwtb200_image *im, int frame, int ix, int iy, 
     if (sum_sq) *sum_sq = h[1];
     if (max_abs) *max_abs = h[2];
     return DWTB200_OK;
+}
+
+// dwt_util_conv_show_{s,d,i} (src/libdwt.c:21075, 21120, 21020) on device-resident planes: frame `frame` of src -> frame 0.. of dst
+int dwtb200_image_conv_show(dwtb200_image *src, dwtb200_image *dst, int ix, int iy)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!src || !dst || src->kind_class() != dst->kind_class() || src->frames != dst->frames || ix < 0 || iy < 0 || ix > src->ox || iy > src->oy ||
+        ix > dst->ox || iy > dst->oy)
+        return fail(DWTB200_EINVAL, "image_conv_show: images must hold the same sample type and cover %d x %d", ix, iy);
+    ImageScope scope(dst);
+    wait_for_image(g.st, src);
+    for (int f = 0; f < src->frames; f++)
+        launch_conv_show(kind_elem_class(src->kind), frame_ptr(src, src->cur, f), src->pitch, frame_ptr(dst, dst->cur, f), dst->pitch, ix, iy, g.st);
+    CK(cudaGetLastError());
+    wait_for_image(src->st, dst);
+    return DWTB200_OK;
+}
+
+// dwt_util_save_to_pgm_s / _d (src/libdwt.c:19794, 19877): the grey values are computed on the device, one byte per sample is copied
+// to the host, the text file ("P2", one value per line) is written there
+int dwtb200_image_save_pgm(dwtb200_image *im, int frame, const char *filename, double max_value, int ix, int iy)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im || !filename || frame < 0 || frame >= im->frames || ix < 0 || iy < 0 || ix > im->ox || iy > im->oy || max_value == 0.0 ||
+        kind_elem_class(im->kind) == 0)
+        return fail(DWTB200_EINVAL, "image_save_pgm: float or double image, a frame, a file name and a nonzero maximum");
+    ImageScope scope(im);
+    const size_t n = (size_t)ix * (size_t)iy;
+    unsigned char *d = nullptr;
+    std::vector<unsigned char> h(n ? n : 1);
+    if (n) {
+        CK(cudaMalloc((void **)&d, n));
+        launch_pgm_quant(kind_elem_class(im->kind), frame_ptr(im, im->cur, frame), im->pitch, d, ix, iy, max_value, g.st);
+        cudaMemcpyAsync(h.data(), d, n, cudaMemcpyDeviceToHost, g.st);
+        const cudaError_t e = cudaStreamSynchronize(g.st);
+        cudaFree(d);
+        if (e != cudaSuccess) return fail(DWTB200_ECUDA, "image_save_pgm: %s", cudaGetErrorString(e));
+    }
+    FILE *file = fopen(filename, "w");
+    if (!file) return fail(DWTB200_EINVAL, "image_save_pgm: cannot open %s", filename);
+    fprintf(file, "P2\n%i %i\n%i\n", ix, iy, 255);
+    std::string out;
+    out.reserve(n * 4);
+    char buf[8];
+    for (size_t i = 0; i < n; i++) {
+        const int len = snprintf(buf, sizeof buf, "%i\n", (int)h[i]);
+        out.append(buf, (size_t)len);
+    }
+    const bool ok = fwrite(out.data(), 1, out.size(), file) == out.size();
+    fclose(file);
+    return ok ? DWTB200_OK : fail(DWTB200_EINVAL, "image_save_pgm: error writing %s", filename);
 }
 
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)

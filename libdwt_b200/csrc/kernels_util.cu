@@ -174,6 +174,59 @@ void launch_compare(int es, const void *a, const void *b, int64_t pitch, int64_t
     else k_compare<int32_t><<<g, blk, 0, st>>>((const int32_t *)a, (const int32_t *)b, pitch, frame, nx, ny, out);
 }
 
+// ---- visualisation of a device-resident plane without bringing the coefficients to the host -----------------------------
+// dwt_util_conv_show_{s,d,i} (src/libdwt.c:21075, 21120, 21020): float / double: log(1 + |c| * 100) / 10 -- the reference takes
+// the logarithm in double (log_i_s, :21010) and rounds it to the sample type before the division --, a non-finite result
+// becomes 0; int: |c|.
+template <class T> __global__ void __launch_bounds__(256) k_conv_show(const T *src, int64_t sp, T *dst, int64_t dp, int nx, int ny)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const T c = src[(int64_t)y * sp + x];
+    T r;
+    if constexpr (sizeof(T) == 8) {
+        r = __ddiv_rn(log(__dadd_rn(1.0, __dmul_rn(fabs((double)c), 100.0))), 10.0);
+        if (!isfinite((double)r)) r = 0;
+    } else if constexpr (T(1) / T(2) > T(0)) {
+        const float t = (float)log((double)__fadd_rn(1.f, __fmul_rn(fabsf((float)c), 100.f)));
+        r = __fdiv_rn(t, 10.f);
+        if (!isfinite((float)r)) r = 0;
+    } else {
+        r = c < 0 ? (T)(0u - (uint32_t)c) : c;   // abs(); INT_MIN stays INT_MIN as in C
+    }
+    dst[(int64_t)y * dp + x] = r;
+}
+void launch_conv_show(int elem_class, const void *src, int64_t sp, void *dst, int64_t dp, int nx, int ny, cudaStream_t st)
+{
+    if (nx <= 0 || ny <= 0) return;
+    const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
+    if (elem_class == 2) k_conv_show<double><<<g, b, 0, st>>>((const double *)src, sp, (double *)dst, dp, nx, ny);
+    else if (elem_class == 1) k_conv_show<float><<<g, b, 0, st>>>((const float *)src, sp, (float *)dst, dp, nx, ny);
+    else k_conv_show<int32_t><<<g, b, 0, st>>>((const int32_t *)src, sp, (int32_t *)dst, dp, nx, ny);
+}
+// the grey value dwt_util_save_to_pgm_s writes for a sample (src/libdwt.c:19794-19866): (int)(255 * px / max_value) in float,
+// 255 above max_value, 0 below zero and for NaN; one byte per sample is all that crosses PCIe
+template <class T> __global__ void __launch_bounds__(256) k_pgm_quant(const T *src, int64_t sp, unsigned char *dst, int nx, int ny, T maxv)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    const T px = src[(int64_t)y * sp + x];
+    int val;
+    if constexpr (sizeof(T) == 8) val = (int)__ddiv_rn(__dmul_rn(255.0, px), maxv);
+    else val = (int)__fdiv_rn(__fmul_rn(255.f, px), maxv);
+    if (px != px) val = 0;
+    if (px > maxv) val = 255;
+    if (px < T(0)) val = 0;
+    dst[(int64_t)y * nx + x] = (unsigned char)min(max(val, 0), 255);
+}
+void launch_pgm_quant(int elem_class, const void *src, int64_t sp, unsigned char *dst, int nx, int ny, double maxv, cudaStream_t st)
+{
+    if (nx <= 0 || ny <= 0) return;
+    const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
+    if (elem_class == 2) k_pgm_quant<double><<<g, b, 0, st>>>((const double *)src, sp, dst, nx, ny, maxv);
+    else k_pgm_quant<float><<<g, b, 0, st>>>((const float *)src, sp, dst, nx, ny, (float)maxv);
+}
+
 // ---- moments of a rectangle (a subband of the Mallat plane): sum, sum of squares, max |x|, in double ----
 // what dwt_util_band_wps_s / _var_s / _norm_s style feature reductions need (src/libdwt.c:23086-23786) without bringing the
 // coefficients back to the host

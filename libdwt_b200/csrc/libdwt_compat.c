@@ -4,6 +4,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/dwtb200.h"
 #include "../../include/libdwt_compat.h"
@@ -215,6 +216,111 @@ int volume_perftest_fwd97op_s(int size, int opt_stride, int approach, int N, dou
     if (rc) die("volume_perftest_fwd97op_s", rc);
     if (faults) *faults = 0;
     return errors;
+}
+
+/* ---- volumes in page-locked host memory: volume_alloc_realiably / volume_alloc_realiably_locked / volume_free
+ * (src/volume.c:10, 194, 34).  Strides per dwt_util_get_stride (src/libdwt.c:20688-20728): 0 packed, 1 next prime, 2 prime << 6,
+ * 3 one cache line past a page multiple, 4 multiple of 64, 5, 6 odd, 7 odd << 6.  The reference mlock()s the block; here it is
+ * cudaHostAlloc'ed, so the slice-by-slice transfers of cdf97_3f_op_sep_horizontal_s run at PCIe speed instead of through a staging copy. */
+static int is_prime_(int n)
+{
+    if (n < 2) return 0;
+    if (n % 2 == 0) return n == 2;
+    for (int q = 3; (long long)q * q <= n; q += 2)
+        if (n % q == 0) return 0;
+    return 1;
+}
+static int next_prime_(int n)
+{
+    if (n <= 2) return 2;
+    n |= 1;
+    while (!is_prime_(n)) n += 2;
+    return n;
+}
+static int ceil_log2_(int x)
+{
+    int j = 0;
+    while ((1LL << j) < x) j++;
+    return j;
+}
+static int get_stride_(int min_stride, int opt)
+{
+    const int a64 = (min_stride + 63) & ~63, a4096 = (min_stride + 4095) & ~4095;
+    switch (opt) {
+    case 1: return next_prime_(min_stride);
+    case 2: return next_prime_(a64 >> 6) << 6;
+    case 3: return ((a4096 >> 6) + 1) << 6;
+    case 4: return a64;
+    case 5: return a4096 + (1 << ceil_log2_(min_stride));
+    case 6: return min_stride | 1;
+    case 7: return ((a64 >> 6) | 1) << 6;
+    default: return min_stride;
+    }
+}
+struct volume_t *volume_alloc_realiably_locked(size_t pix_size, int size_x, int size_y, int size_z, int opt_stride)
+{
+    struct volume_t *v = (struct volume_t *)malloc(sizeof *v);
+    if (!v) die("volume_alloc_realiably_locked", DWTB200_ENOMEM);
+    v->size_x = size_x;
+    v->size_y = size_y;
+    v->size_z = size_z;
+    v->stride_x = pix_size;
+    v->stride_y = (size_t)get_stride_((int)(v->stride_x * (size_t)size_x), opt_stride);
+    v->stride_z = (size_t)get_stride_((int)(v->stride_y * (size_t)size_y), opt_stride);
+    v->data = dwtb200_host_alloc(v->stride_z * (size_t)size_z);
+    if (!v->data) die("volume_alloc_realiably_locked", DWTB200_ENOMEM);
+    return v;
+}
+struct volume_t *volume_alloc_realiably(size_t pix_size, int size_x, int size_y, int size_z, int opt_stride)
+{
+    return volume_alloc_realiably_locked(pix_size, size_x, size_y, size_z, opt_stride);
+}
+void volume_free(struct volume_t *volume)
+{
+    if (!volume) return;
+    dwtb200_host_free(volume->data);
+    free(volume);
+}
+
+/* volume_measure_fwd97op_s (src/volume-dwt.c:2898): volume_perftest_fwd97op_s over cube edges size_min, size_grow(size) ... below
+ * size_max (growth factor 1.13, rounded up to a multiple of size_step: :2884), one "voxels <TAB> seconds per voxel" line per size into
+ * data/perftest/time-stride=S-approach=A.txt and the page-fault twin (always 0 here: the volumes live in HBM) */
+int volume_measure_fwd97op_s(int size_min, int size_max, int size_step, int N, int opt_stride, int approach)
+{
+    char path[4096];
+    snprintf(path, sizeof path, "data/perftest/time-stride=%i-approach=%i.txt", opt_stride, approach);
+    FILE *file_time = fopen(path, "w");
+    if (!file_time) {
+        fprintf(stderr, "ERROR: unable to open file: %s\n", path);
+        abort();
+    }
+    snprintf(path, sizeof path, "data/perftest/faults-stride=%i-approach=%i.txt", opt_stride, approach);
+    FILE *file_faults = fopen(path, "w");
+    if (!file_faults) {
+        fprintf(stderr, "ERROR: unable to open file: %s\n", path);
+        abort();
+    }
+    fprintf(file_time, "# voxels secs/pel\n");
+    fprintf(file_faults, "# voxels page_faults\n");
+    int total_errors = 0;
+    for (int size = size_min; size < size_max;) {
+        double secs = 0;
+        long unsigned faults = 0;
+        const int errors = volume_perftest_fwd97op_s(size, opt_stride, approach, N, &secs, &faults);
+        const int voxels = size * size * size;
+        fprintf(stderr, "perftest: size=%4i opt_stride=%i approach=%2i (N=%2i): time=%f [nsecs/pel]; errors=%i; faults=%lu\n", size, opt_stride,
+                approach, N, secs * 1e9, errors, faults);
+        fprintf(file_time, "%i\t%.20f\n", voxels, secs);
+        fprintf(file_faults, "%i\t%lu\n", voxels, faults);
+        total_errors += errors;
+        size = (int)(size * 1.13f);   /* size_grow */
+        size += 1;
+        size += size_step - 1;
+        size &= ~(size_step - 1);
+    }
+    fclose(file_time);
+    fclose(file_faults);
+    return total_errors;
 }
 
 double dwt_b200_last_transform_ms(void) { return dwtb200_last_transform_ms(); }

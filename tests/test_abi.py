@@ -57,10 +57,11 @@ def test_compat_library_exports_the_reference_symbols():
     import ctypes
     src = open(os.path.join(ROOT, "include", "libdwt_compat.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = sorted(set(re.findall(r"\b((?:dwt_|cdf97_3)[a-z0-9_]+)\s*\(", src)))
+    names = sorted(set(re.findall(r"\b((?:dwt_|cdf97_3|volume_)[a-z0-9_]+)\s*\(", src)))
     assert {"dwt_cdf97_2f_s", "dwt_cdf97_2i_s", "dwt_cdf97_2f_d", "dwt_cdf97_2i_d", "dwt_cdf53_2f_i", "dwt_cdf53_2i_i",
             "dwt_util_alloc_image", "dwt_util_free_image", "cdf97_3f_op_sep_horizontal_s",
-            "cdf97_3i_ip_sep_horizontal_s"} <= set(names)
+            "cdf97_3i_ip_sep_horizontal_s", "volume_alloc_realiably_locked", "volume_free", "volume_measure_fwd97op_s",
+            "volume_perftest_fwd97op_s"} <= set(names)
     so = ctypes.CDLL(os.path.join(ROOT, "libdwt_b200", "libdwt_compat.so"))
     for n in names:
         assert hasattr(so, n), n
