@@ -254,7 +254,10 @@ int dwtb200_strips_band(int width, int height, int world, int levels_distributed
  * common to its ranks (a POSIX shared-memory segment of that name carries the IPC handles); rank 0 must be created first when
  * several ranks live in one process (single-GPU tests).  Returns NULL on failure (dwtb200_last_error). */
 dwtb200_strips *dwtb200_strips_create(int kind, int width, int height, int levels_distributed, int rank, int world, const char *session);
-int dwtb200_strips_connect(dwtb200_strips *s);   /* waits for every rank's create; implied by the first transform */
+/* waits for every rank's create and maps their planes.  Called explicitly (before the strip holds data: it runs warm-up transforms)
+ * it also lets level 0 of the forward transform read the halo rows straight from the neighbours' planes over NVLink instead of
+ * copying them first (DWTB200_STRIPS_DIRECT=0: off); the first transform implies a plain connect without that */
+int dwtb200_strips_connect(dwtb200_strips *s);
 void dwtb200_strips_destroy(dwtb200_strips *s);
 dwtb200_image *dwtb200_strips_image(dwtb200_strips *s);   /* the extended strip */
 dwtb200_image *dwtb200_strips_top(dwtb200_strips *s);     /* rank 0: Mallat image of LL_Jd; NULL elsewhere */

@@ -135,6 +135,10 @@ struct dwtb200_image {
     cudaStream_t st = nullptr;   // independent images overlap: the small levels of one run in the shadow of another's big ones
     cudaEvent_t ev = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // dwtb200_image_timer_*: events on the image's own stream
+    // row strips (strips.cu): where level 0 of a forward transform reads the rows it does not own, per plane (see LevelParams)
+    const void *up[2] = {nullptr, nullptr}, *dn[2] = {nullptr, nullptr};
+    int up_end = 0, dn_begin = 0;
+    int64_t up_row0 = 0, dn_row0 = 0;
     std::vector<cudaEvent_t> marks;           // dwtb200_image_timer_mark
     size_t nmarks = 0;
     int kind = 0, ox = 0, oy = 0, frames = 0;
@@ -219,6 +223,27 @@ int set_error(int code, const char *fmt, ...)
     return code;
 }
 std::recursive_mutex &api_mutex() { return g_api_mutex; }
+}  // namespace dwtb200
+namespace dwtb200 {
+bool image_level0_is_ring(dwtb200_image *im, int J);   // defined below, next to the planner
+void image_set_row_sources(dwtb200_image *im, const void *const up[2], const void *const dn[2], int up_end, int dn_begin, int64_t up_row0, int64_t dn_row0)
+{
+    for (int i = 0; i < 2; i++) {
+        im->up[i] = up ? up[i] : nullptr;
+        im->dn[i] = dn ? dn[i] : nullptr;
+    }
+    im->up_end = up_end;
+    im->dn_begin = dn_begin;
+    im->up_row0 = up_row0;
+    im->dn_row0 = dn_row0;
+    // the cached graphs hold the kernel parameters of the old sources
+    if (im->st) cudaStreamSynchronize(im->st);
+    for (auto &kv : im->graphs) {
+        cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.sync) cudaFree(kv.second.sync);
+    }
+    im->graphs.clear();
+}
 }  // namespace dwtb200
 
 extern "C" {
@@ -837,6 +862,16 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.nstrips = (units + pps - 1) / pps;
 }
 
+}  // namespace
+// true when level 0 of a dense forward transform of `im` is served by a bulk-copy ring kernel (the kernels that can take rows from
+// neighbour planes, LevelParams::src_up / src_dn)
+extern "C++" bool dwtb200::image_level0_is_ring(dwtb200_image *im, int J)
+{
+    if (J < 1 || g.force_generic || !(g.ring & 1) || g.narrow || !g.use_graph) return false;
+    const DensePlan pl = dense_plan(im, J);
+    return pl.jt > 0 && pl.type[0] == PLAN_STREAM && pl.pyr_len[0] == 0;
+}
+namespace {
 // parameters of forward level j reading `in` (LL_{j-1} or the source plane); returns where LL_j goes
 Band fwd_level_params(const dwtb200_image *im, int j, int J, const Band &in, char *dst_plane, LevelParams &p)
 {
@@ -855,6 +890,14 @@ Band fwd_level_params(const dwtb200_image *im, int j, int J, const Band &in, cha
     p.hh = dst_plane + ((size_t)ody * im->pitch + odx) * im->es;
     p.sub_pitch = im->pitch;
     p.sub_frame = im->frame;
+    if (j == 0 && (im->up[im->cur] || im->dn[im->cur])) {
+        p.src_up = im->up[im->cur];
+        p.src_dn = im->dn[im->cur];
+        p.up_end = im->up[im->cur] ? im->up_end : 0;
+        p.dn_begin = im->dn[im->cur] ? im->dn_begin : 0;
+        p.up_row0 = im->up_row0;
+        p.dn_row0 = im->dn_row0;
+    }
     return out;
 }
 

@@ -60,7 +60,20 @@ struct LevelParams {
     // = L, odd = H in both directions) and LL additionally to `ll`; inverse reads HL, LH, HH from `il` and LL from `ll`
     void *il;
     int64_t il_pitch, il_frame;
+    // row strips over several GPUs (strips.cu), forward ring kernels only, one frame: input rows [0, up_end) are read from `src_up`
+    // (row r lives at row r + up_row0 there) and rows >= dn_begin (0: none) from `src_dn` (row r - dn_begin + dn_row0) -- the
+    // neighbour ranks' planes, peer-mapped -- with the pitch of `src`.  The bulk copies of the ring producer fetch them over NVLink.
+    const void *src_up, *src_dn;
+    int up_end, dn_begin;
+    int64_t up_row0, dn_row0;
 };
+// the plane and row a forward ring producer reads input row r (already mirrored into [0, H)) from
+template <class T> __device__ __forceinline__ const T *level_src_row(const LevelParams &p, const T *local, int r)
+{
+    if (r < p.up_end) return (const T *)p.src_up + ((int64_t)r + p.up_row0) * p.src_pitch;
+    if (p.dn_begin && r >= p.dn_begin) return (const T *)p.src_dn + ((int64_t)(r - p.dn_begin) + p.dn_row0) * p.src_pitch;
+    return local + (int64_t)r * p.src_pitch;
+}
 void launch_fwd_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_level(int kind, const LevelParams &p, int frames, cudaStream_t st);
 // the same level with its input staged through a shared-memory ring by the bulk-copy engine (kernels_ring.cu)

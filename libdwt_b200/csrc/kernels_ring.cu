@@ -83,7 +83,7 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
         if (lane != 0) return;
         const int c0 = max(xs0, 0), c1 = (int)min((int64_t)xs0 + nact * OUTW + 2 * VPL, p.src_pitch);   // clipped to the plane
         const uint32_t bytes = (uint32_t)(c1 - c0) * ES;
-        const T *src = (const T *)p.src + (int64_t)blockIdx.y * p.src_frame + c0;
+        const T *src = (const T *)p.src + (int64_t)blockIdx.y * p.src_frame;
         const uint32_t dst0 = ring0 + (c0 - xs0) * ES;
         const int nitems = m1 - m0 + 2;   // one single row, then one row pair per iteration
         RingState rs;
@@ -96,7 +96,7 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
                 const int r = reflect(2 * m0, H);
                 if (dep) win.need_row(p.chain, gen, blockIdx.y, r);
                 mbar_expect_tx(fb, bytes);
-                bulk_g2s(d + CFG::ROWB, src + (int64_t)r * p.src_pitch, bytes, fb);
+                bulk_g2s(d + CFG::ROWB, level_src_row(p, src, r) + c0, bytes, fb);
             } else {
                 const int m = m0 + q - 1;
                 const int ra = reflect(2 * m + 1, H), rb = reflect(2 * m + 2, H);
@@ -105,8 +105,8 @@ template <class WV, int VPL, class CFG, bool IL = false> __global__ void __launc
                     win.need_row(p.chain, gen, blockIdx.y, rb);
                 }
                 mbar_expect_tx(fb, 2 * bytes);
-                bulk_g2s(d, src + (int64_t)ra * p.src_pitch, bytes, fb);
-                bulk_g2s(d + CFG::ROWB, src + (int64_t)rb * p.src_pitch, bytes, fb);
+                bulk_g2s(d, level_src_row(p, src, ra) + c0, bytes, fb);
+                bulk_g2s(d + CFG::ROWB, level_src_row(p, src, rb) + c0, bytes, fb);
             }
             rs.next();
         }

@@ -252,15 +252,15 @@ template <class WV> __global__ void __launch_bounds__(R2<typename WV::T>::THREAD
         }
         const int c0 = max(xs0, 0), c1 = (int)min((int64_t)xs0 + stw, p.src_pitch);   // clipped to the plane
         const uint32_t bytes = (uint32_t)(c1 - c0) * ES;
-        const T *src = (const T *)p.src + (int64_t)blockIdx.y * p.src_frame + c0;
+        const T *src = (const T *)p.src + (int64_t)blockIdx.y * p.src_frame;
         const uint32_t d = ring0 + (c0 - xs0) * ES + slot * C::SLOTB, fb = full + 8 * slot;
         if (q == 0) {
             mbar_expect_tx(fb, bytes);
-            bulk_g2s(d + C::ROWB, src + (int64_t)ra * p.src_pitch, bytes, fb);
+            bulk_g2s(d + C::ROWB, level_src_row(p, src, ra) + c0, bytes, fb);
         } else {
             mbar_expect_tx(fb, 2 * bytes);
-            bulk_g2s(d, src + (int64_t)ra * p.src_pitch, bytes, fb);
-            bulk_g2s(d + C::ROWB, src + (int64_t)rb * p.src_pitch, bytes, fb);
+            bulk_g2s(d, level_src_row(p, src, ra) + c0, bytes, fb);
+            bulk_g2s(d + C::ROWB, level_src_row(p, src, rb) + c0, bytes, fb);
         }
         return true;
     };

@@ -105,6 +105,40 @@ __global__ void k_wait(FlagList f, uint32_t seq, uint32_t *error, unsigned long 
     __threadfence_system();
 }
 
+// Several rectangles copied by ONE launch (the inverse needs two per distributed level and neighbour: ten cudaMemcpy2DAsync calls
+// per side kept the host busy for longer than the copies take).  The source is peer memory read over NVLink; 16-byte accesses
+// where rows start and end on 16-byte boundaries.
+constexpr int MAX_RECTS = 2 * 16;
+struct RectList {
+    int n, total_rows;
+    struct R {
+        char *dst;
+        const char *src;
+        int64_t dpitch, spitch;
+        int rows, row_bytes, row0;   // row0: index of the rectangle's first row among all rows of the list
+    } r[MAX_RECTS];
+};
+__global__ void __launch_bounds__(256) k_pull_rects(const RectList L)
+{
+    const int row = blockIdx.x;
+    int i = 0;
+    while (i + 1 < L.n && row >= L.r[i + 1].row0) i++;
+    const RectList::R &q = L.r[i];
+    const int y = row - q.row0;
+    char *d = q.dst + (int64_t)y * q.dpitch;
+    const char *s_ = q.src + (int64_t)y * q.spitch;
+    const int nb = q.row_bytes;
+    if ((((uintptr_t)d | (uintptr_t)s_ | (uintptr_t)nb) & 15) == 0) {
+        const int4 *s4 = reinterpret_cast<const int4 *>(s_);
+        int4 *d4 = reinterpret_cast<int4 *>(d);
+        for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < nb / 16; k += gridDim.y * blockDim.x) d4[k] = s4[k];
+    } else {
+        const int *s1 = reinterpret_cast<const int *>(s_);
+        int *d1 = reinterpret_cast<int *>(d);
+        for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < nb / 4; k += gridDim.y * blockDim.x) d1[k] = s1[k];
+    }
+}
+
 // bit-wise comparison of two rectangles with their own pitches: out[0] += number of differing samples
 template <class U> __global__ void __launch_bounds__(256) k_cmp_rect(const U *a, int64_t pa, const U *b, int64_t pb, int nx, int ny,
                                                                      unsigned long long *out)
@@ -210,6 +244,7 @@ struct dwtb200_strips {
     std::string shm_name;
     Shm *shm = nullptr;
     bool connected = false;
+    bool direct = false;    // forward: level 0 reads the halo rows straight from the neighbours' planes (no halo copy)
     char *peer_plane[MAXR][2] = {};
     Ctrl *peer_ctrl[MAXR] = {};
     char *peer_top[2] = {nullptr, nullptr};
@@ -334,7 +369,7 @@ int open_handle(dwtb200_strips *s, const cudaIpcMemHandle_t &h, void **out)
     return 0;
 }
 
-int connect(dwtb200_strips *s)
+int connect(dwtb200_strips *s, bool may_warm = false)
 {
     if (s->connected) return 0;
     const int mypid = (int)getpid();
@@ -374,6 +409,33 @@ int connect(dwtb200_strips *s)
         if (p == 0) s->top_pitch = r.top_pitch_bytes;
     }
     s->connected = true;
+    // Forward level 0 can fetch the halo rows itself: its ring producer's bulk copies read them from the neighbours' planes over
+    // NVLink while the rest of the strip streams from local HBM, instead of a copy phase (two 33 MB pulls per rank at 65536^2 x 8,
+    // ~90 us of a 1.2 ms call) in front of the transform.  Only when level 0 is a ring level, and only from an explicit
+    // dwtb200_strips_connect(): the graphs must be captured again with the neighbours' pointers in the kernel parameters, and
+    // capturing transforms the planes (the caller's data would be lost inside an implicit connect).
+    const char *e = getenv("DWTB200_STRIPS_DIRECT");
+    const int r = s->rank, G = s->world;
+    const ImageView lv = image_view(s->local);
+    const int64_t mypitch = lv.pitch * (int64_t)lv.es;
+    if (may_warm && G > 1 && !(e && !atoi(e)) && image_level0_is_ring(s->local, s->Jd) && (r == 0 || s->peer_pitch[r - 1] == mypitch) &&
+        (r == G - 1 || s->peer_pitch[r + 1] == mypitch)) {
+        const dwtb200_strip_plan &pl = s->plan[r];
+        const void *up[2] = {nullptr, nullptr}, *dn[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; i++) {
+            if (r > 0) up[i] = s->peer_plane[r - 1][i];
+            if (r < G - 1) dn[i] = s->peer_plane[r + 1][i];
+        }
+        image_set_row_sources(s->local, up, dn, r > 0 ? pl.own0 - pl.ext0 : 0, r < G - 1 ? pl.own1 - pl.ext0 : 0,
+                              r > 0 ? pl.ext0 - s->plan[r - 1].ext0 : 0, r < G - 1 ? pl.own1 - s->plan[r + 1].ext0 : 0);
+        bool ok = true;
+        int j = s->Jd;
+        for (int i = 0; ok && i < 2; i++) ok = dwtb200_image_fwd2(s->local, s->W, pl.ext1 - pl.ext0, &j, 0, 0) == 0;
+        for (int i = 0; ok && i < 2; i++) ok = dwtb200_image_inv2(s->local, s->W, pl.ext1 - pl.ext0, s->Jd, 0, 0) == 0;
+        ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+        if (!ok) return DWTB200_ECUDA;
+        s->direct = true;
+    }
     return 0;
 }
 
@@ -433,6 +495,7 @@ dwtb200_strips *dwtb200_strips_create(int kind, int width, int height, int level
     {   // load the protocol kernels now: a lazy module load behind a spinning wait kernel could block
         cudaFuncAttributes a;
         if (cudaFuncGetAttributes(&a, k_signal) != cudaSuccess || cudaFuncGetAttributes(&a, k_wait) != cudaSuccess ||
+            cudaFuncGetAttributes(&a, k_pull_rects) != cudaSuccess ||
             cudaFuncGetAttributes(&a, k_cmp_rect<uint32_t>) != cudaSuccess || cudaFuncGetAttributes(&a, k_cmp_rect<uint64_t>) != cudaSuccess) {
             set_error(DWTB200_ECUDA, "strips_create: %s", cudaGetErrorString(cudaGetLastError()));
             return nullptr;
@@ -504,7 +567,7 @@ int dwtb200_strips_connect(dwtb200_strips *s)
 {
     std::lock_guard<std::recursive_mutex> lock(api_mutex());
     if (!s) return set_error(DWTB200_EINVAL, "strips_connect: null");
-    return connect(s);
+    return connect(s, true);
 }
 
 void dwtb200_strips_destroy(dwtb200_strips *s)
@@ -581,9 +644,19 @@ int dwtb200_strips_fwd2(dwtb200_strips *s, int *j_max_ptr)
         rc = signal_list(T, f, seq);
         if (rc) return rc;
     }
+    if (s->direct) {
+        // level 0 reads the halo rows from the neighbours' planes itself: just wait until their strips hold this call's data
+        FlagList f;
+        f.n = 0;
+        if (r > 0) f.p[f.n++] = &s->ctrl->nb_ready[0];
+        if (r < G - 1) f.p[f.n++] = &s->ctrl->nb_ready[1];
+        rc = wait_list(s, L, f, seq);
+        if (rc) return rc;
+        s->nvlink_bytes += (unsigned long long)((pl.own0 - pl.ext0) + (pl.ext1 - pl.own1)) * (unsigned long long)s->W * s->es;
+    }
     // halo rows of the level-0 input, pulled from the owned rows of the two neighbours on a stream each
     CKS(cudaEventRecord(s->ev[0], L));
-    if (r > 0) {
+    if (!s->direct && r > 0) {
         const dwtb200_strip_plan &nb = s->plan[r - 1];
         CKS(cudaStreamWaitEvent(s->up, s->ev[0], 0));
         rc = wait_one(s, s->up, &s->ctrl->nb_ready[0], seq);
@@ -594,7 +667,7 @@ int dwtb200_strips_fwd2(dwtb200_strips *s, int *j_max_ptr)
         CKS(cudaEventRecord(s->ev[1], s->up));
         CKS(cudaStreamWaitEvent(L, s->ev[1], 0));
     }
-    if (r < G - 1) {
+    if (!s->direct && r < G - 1) {
         const dwtb200_strip_plan &nb = s->plan[r + 1];
         CKS(cudaStreamWaitEvent(s->dn, s->ev[0], 0));
         rc = wait_one(s, s->dn, &s->ctrl->nb_ready[1], seq);
@@ -609,6 +682,10 @@ int dwtb200_strips_fwd2(dwtb200_strips *s, int *j_max_ptr)
     int jd = s->Jd;
     rc = dwtb200_image_fwd2(s->local, s->W, pl.ext1 - pl.ext0, &jd, 0, 0);
     if (rc) return rc;
+    if (s->direct) {   // the neighbours' rows have been read
+        rc = signal(L, {r > 0 ? &s->peer_ctrl[r - 1]->done_by[r] : nullptr, r < G - 1 ? &s->peer_ctrl[r + 1]->done_by[r] : nullptr}, seq);
+        if (rc) return rc;
+    }
     s->local_cur ^= 1;
     lv = image_view(s->local);
     // owned rows of LL_Jd -> rank 0's top image
@@ -690,6 +767,9 @@ int dwtb200_strips_inv2(dwtb200_strips *s, int j_max)
         CKS(cudaStreamWaitEvent(st, s->ev[0], 0));
         rc = wait_one(s, st, &s->ctrl->nb_ready[side], seq);
         if (rc) return rc;
+        RectList list;
+        list.n = list.total_rows = 0;
+        int widest = 0;
         for (int j = 0; j < s->Jd; j++) {
             int me[11], ot[11];
             band_of(s, r, j, me);
@@ -699,12 +779,30 @@ int dwtb200_strips_inv2(dwtb200_strips *s, int j_max)
             for (int type = 0; type < 2; type++) {
                 const int e0 = me[3 + 2 * type], e1 = me[4 + 2 * type], o0 = ot[7 + 2 * type], o1 = ot[8 + 2 * type];
                 const int g0 = std::max(o0, e0), g1 = std::min(o1, e1);
-                if (g1 <= g0) continue;
+                const int c0 = type ? 0 : nlx;
+                if (g1 <= g0 || w <= c0) continue;
                 const int base_me = type ? me[2] : 0, base_ot = type ? ot[2] : 0;
-                rc = copy_rect(s, st, plane, pitch, base_me + g0 - me[0], s->peer_plane[nb][cur], s->peer_pitch[nb], base_ot + g0 - ot[0], g1 - g0,
-                               type ? 0 : nlx, w, true);
-                if (rc) return rc;
+                if (list.n == MAX_RECTS) {   // (more than 16 distributed levels: cannot happen below 2^20 rows per rank, kept for safety)
+                    k_pull_rects<<<dim3(list.total_rows, std::max(1, std::min(16, widest / 16384))), 256, 0, st>>>(list);
+                    list.n = list.total_rows = 0;
+                }
+                RectList::R &q = list.r[list.n++];
+                q.dst = plane + (size_t)(base_me + g0 - me[0]) * pitch + (size_t)c0 * s->es;
+                q.src = s->peer_plane[nb][cur] + (size_t)(base_ot + g0 - ot[0]) * s->peer_pitch[nb] + (size_t)c0 * s->es;
+                q.dpitch = pitch;
+                q.spitch = s->peer_pitch[nb];
+                q.rows = g1 - g0;
+                q.row_bytes = (int)((size_t)(w - c0) * s->es);
+                q.row0 = list.total_rows;
+                list.total_rows += q.rows;
+                widest = std::max(widest, q.row_bytes);
+                s->nvlink_bytes += (unsigned long long)q.rows * (unsigned long long)q.row_bytes;
             }
+        }
+        if (list.total_rows > 0) {
+            const dim3 grid(list.total_rows, std::max(1, std::min(16, widest / 16384)));
+            k_pull_rects<<<grid, 256, 0, st>>>(list);
+            CKS(cudaGetLastError());
         }
         rc = signal(st, {&s->peer_ctrl[nb]->done_by[r]}, seq);
         if (rc) return rc;
