@@ -4,7 +4,7 @@ ARCH  = -gencode arch=compute_100a,code=sm_100a
 # DEBUG_KEYS=1 compiles the measurement-only tuning keys 96-99 and the no-store / no-arithmetic branches of k_fwd_level in
 NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v $(if $(DEBUG_KEYS),-DDWTB200_DEBUG_KEYS)
 CSRC = libdwt_b200/csrc
-OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_ring.o $(CSRC)/kernels_ring2.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_tile.o $(CSRC)/kernels_pyr.o $(CSRC)/kernels_inplace.o $(CSRC)/kernels_vol.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/strips.o $(CSRC)/dwtb200.o
+OBJS = $(CSRC)/kernels_stream.o $(CSRC)/kernels_ring.o $(CSRC)/kernels_ring2.o $(CSRC)/kernels_tail.o $(CSRC)/kernels_tile.o $(CSRC)/kernels_inplace.o $(CSRC)/kernels_vol.o $(CSRC)/kernels_generic.o $(CSRC)/kernels_util.o $(CSRC)/strips.o $(CSRC)/dwtb200.o
 
 all: libdwt_b200/libdwtb200.so libdwt_b200/libdwt_compat.so oracle examples
 

@@ -300,7 +300,7 @@ def run_ours(args):
     assert im.last_launches == 1
     bytes0 = 2 * 4 * PIX * M
     im.fill(0, 0, 6)
-    roof = {"bound": "hbm", "kernel": f"k_fwd_ring<W97F,8,RingCfg<7,2>> (level 0 of dwt_cdf97_2f_s, {M} frames of 8192x8192 per launch)",
+    roof = {"bound": "hbm", "kernel": f"k_fwd_ring2<W97F> (level 0 of dwt_cdf97_2f_s, {M} frames of 8192x8192 per launch)",
             "achieved": bytes0 / t_fwd0 / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "frac": bytes0 / t_fwd0 / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes0,
             "us_per_launch": t_fwd0 * 1e6,
@@ -309,7 +309,7 @@ def run_ours(args):
     if os.path.exists(tr):
         try:
             tj = json.load(open(tr))
-            roof["traffic"] = tj["k_fwd_ring_w97f_level0_dram_bytes_per_launch_4_frames"] * M / 4
+            roof["traffic"] = tj["k_fwd_ring2_w97f_level0_dram_bytes_per_launch_4_frames"] * M / 4
             roof["traffic_source"] = tj["source"]
         except Exception:
             pass

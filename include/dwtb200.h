@@ -197,8 +197,7 @@ void dwtb200_set_strip_rows(int rows);
  *                          large batches of 2048-wide frames; 1 = 15 x 1, 2 = 8 x 2, 3 = 5 x 3, 5 = 7 x 2)
  *   DWTB200_TUNE_VOL3      1 (default): the forward 3-D transform of volumes of at least 128 x 32 x 16 runs in ONE pass (k_vol3_fwd);
  *                          0: always x + y per slice, then z (two passes)
- *   DWTB200_TUNE_PYR       T > 0: runs of tile levels are fused: one launch carries T x T tiles of the last level's LL band
- *                          through up to three levels in shared memory (0 = one tile launch per level)
+ *   DWTB200_TUNE_PYR       accepted and ignored (the fused tile-pyramid kernels of round 1 were never faster and are gone)
  *   DWTB200_TUNE_CHAIN     1: the kernels of a pyramid are launched with programmatic stream serialization and wait for
  *                          their input row block by row block on completion counters, so consecutive levels overlap (1) */
 enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MAX = 2, DWTB200_TUNE_PDL = 3, DWTB200_TUNE_NARROW = 4,

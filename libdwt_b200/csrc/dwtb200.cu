@@ -83,9 +83,7 @@ struct Ctx {
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
     int ring_v2 = 1;    // the ring levels take the 256-column kernels (kernels_ring2.cu) where they apply; scoped off for the interleaved layout
     int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // strip-length search range of the ring kernels (0: defaults)
-    int64_t pyr_max_in = (int64_t)512 * 512;   // only levels with at most this many input samples per frame are fused
     int vol3 = 1;       // forward 3-D: one pass over the volume where the tile kernel applies (kernels_vol.cu, k_vol3_fwd)
-    int pyr = 0;        // > 0: runs of tile levels are fused, tiles of this edge carried through up to 3 levels (kernels_pyr.cu)
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
@@ -283,7 +281,6 @@ int dwtb200_init(int device)
     CK(preload_ring());
     CK(preload_ring2());
     CK(preload_inplace());
-    CK(preload_pyr());
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
@@ -439,10 +436,9 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
-    case DWTB200_TUNE_PYR: g.pyr = (int)value; break;
+    case DWTB200_TUNE_PYR: break;   // the fused tile-pyramid kernels were removed in round 2 (never faster than one tile launch per level)
     case DWTB200_TUNE_VOL3: g.vol3 = value != 0; break;
 #ifdef DWTB200_DEBUG_KEYS   // measurement-only knobs (profiles/scripts): not part of the release ABI
-    case 96: g.pyr_max_in = value; break;
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
     case 99: g.dbg = (int)value; break;   // see kernels.h
@@ -696,13 +692,12 @@ struct Band {   // where an LL band lives
 //   TILE    kernels_tile.cu     one launch per level, small tiles (only when the persistent kernel is off)
 //   MID     kernels_tile.cu     L2-resident levels: ALL of them plus the tail in ONE cooperative launch
 //   TAIL    kernels_tail.cu     every remaining level once the LL band fits one CTA's shared memory
-enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2, PLAN_PYR = 3 };   // PLAN_PYR: first level of a fused group (pyr_len levels)
+enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2 };
 struct DensePlan {
     int jt;                 // first level of the tail (== J: no tail); -1: the dense kernels cannot take this pyramid
     int jm;                 // first level of the persistent launch (== jt when it holds no tile level)
     bool tail_in_mid;       // the tail runs inside the persistent launch
     int type[40];
-    int pyr_len[40];
 };
 
 DensePlan dense_plan(const dwtb200_image *im, int J)
@@ -734,20 +729,6 @@ DensePlan dense_plan(const dwtb200_image *im, int J)
         }
     }
     pl.tail_in_mid = mid_on && pl.jt < J && pl.jm < pl.jt;
-    // runs of tile levels become fused groups (forward only so far; the inverse keeps one tile launch per level)
-    for (int j = 0; j < 40; j++) pl.pyr_len[j] = 0;
-    if (g.pyr > 0) {
-        const int maxf = pyr_max_levels(im->kind);
-        for (int j = 0; j < pl.jt;) {
-            int f = 0;
-            while (j + f < pl.jt && f < maxf && pl.type[j + f] == PLAN_TILE &&
-                   (int64_t)cdiv_pow2(im->ox, j + f) * cdiv_pow2(im->oy, j + f) <= g.pyr_max_in &&
-                   std::min(cdiv_pow2(im->ox, j + f), cdiv_pow2(im->oy, j + f)) >= pyr_min_side())
-                f++;
-            if (f >= 2) pl.pyr_len[j] = f;
-            j += f > 0 ? f : 1;
-        }
-    }
     return pl;
 }
 
@@ -869,7 +850,7 @@ extern "C++" bool dwtb200::image_level0_is_ring(dwtb200_image *im, int J)
 {
     if (J < 1 || g.force_generic || !(g.ring & 1) || g.narrow || !g.use_graph) return false;
     const DensePlan pl = dense_plan(im, J);
-    return pl.jt > 0 && pl.type[0] == PLAN_STREAM && pl.pyr_len[0] == 0;
+    return pl.jt > 0 && pl.type[0] == PLAN_STREAM;
 }
 namespace {
 // parameters of forward level j reading `in` (LL_{j-1} or the source plane); returns where LL_j goes
@@ -935,9 +916,7 @@ void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
 
 // ---- the dense path as a list of launches, linked into a chain (struct Chain, kernels.h) ----------------
 struct Launch {
-    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, PYR_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
-    Band pin, pout;   // PYR_*: input / output band of the group
-    int pj0 = 0, pF = 0;
+    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
     LevelParams lp;
     TailParams tp;
     MidParams mp;
@@ -1027,10 +1006,6 @@ int issue(dwtb200_image *im, std::vector<Launch> &ls)
         case Launch::TILE_F: launch_fwd_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_F: launch_fwd_tail(im->kind, l.tp, im->frames, g.st); break;
         case Launch::MID_F: e = launch_fwd_mid(im->kind, l.mp, g.st); break;
-        case Launch::PYR_F:
-            launch_fwd_pyr(im->kind, l.pin.p, l.pin.pitch, l.pin.frame, l.pout.p, l.pout.pitch, l.pout.frame, im->plane[im->cur ^ 1],
-                           im->pitch, im->frame, im->ox, im->oy, l.pj0, l.pF, im->frames, g.pyr, g.st);
-            break;
         case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, l.lp.cfg, g.st); break;
         case Launch::REG_I: launch_inv_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_I: launch_inv_tile(im->kind, l.lp, im->frames, g.st); break;
@@ -1086,18 +1061,6 @@ void plan_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart, s
                 mp.tail = tail_params(pl.jt, in);
             }
             return;
-        }
-        if (pl.pyr_len[j] >= 2) {   // levels j .. j+F-1 in one launch
-            const int F = pl.pyr_len[j];
-            L.type = Launch::PYR_F;
-            memset(&L.lp, 0, sizeof L.lp);
-            L.pin = in;
-            L.pout = (j + F == J) ? Band{dst_plane, im->pitch, im->frame} : ll_band(im, j + F - 1);
-            L.pj0 = j;
-            L.pF = F;
-            in = L.pout;
-            j += F - 1;
-            continue;
         }
         in = fwd_level_params(im, j, J, in, dst_plane, L.lp);
         plan_level(im, L, false, pl.type[j]);
@@ -1567,8 +1530,6 @@ bool ip_53_fast(const dwtb200_image *im, bool inverse, int J, DensePlan &pl)
     if (lp.narrow || !(g.ring & (inverse ? 2 : 1)) || !ring_interleaved_ok(im->kind) || !ring_interleaved_cfg_ok(lp.cfg)) return false;
     pl = dense_plan(im, J);
     if (pl.jt < 1 || pl.jm < pl.jt) return false;   // degenerate pyramid, or the persistent mid-level launch is switched on
-    for (int j = 0; j < pl.jt; j++)
-        if (pl.pyr_len[j]) return false;
     return true;
 }
 int ip_run53(dwtb200_image *im, bool inverse, int J, const DensePlan &pl)
@@ -2125,6 +2086,7 @@ int host_transform(bool inverse, int kind, void *ptr, int64_t sx, int64_t sy, in
 }  // namespace
 
 double dwtb200_last_transform_ms(void) { return (double)g_last_ms; }
+static void release_host_volume();
 void dwtb200_release_host_cache(void)
 {
     API_LOCK();
@@ -2144,6 +2106,7 @@ void dwtb200_release_host_cache(void)
         if (g_host_img[k]) dwtb200_image_destroy(g_host_img[k]);
         g_host_img[k] = nullptr;
     }
+    release_host_volume();
 }
 
 int dwtb200_fwd2_host(int kind, void *ptr, int64_t sx, int64_t sy, int ox, int oy, int ix, int iy, int *j_max_ptr,
@@ -2498,29 +2461,42 @@ int dwtb200_volume_inv3(dwtb200_volume *v)
     return volume_axes(v, 1);
 }
 
+// the device volume of the *_host calls is kept between calls of the same shape (two planes of the volume's size: allocating and
+// freeing 8.6 GB per call of a 1024^3 volume cost more than the transform and a good part of the copies); dwtb200_release_host_cache frees it
+static dwtb200_volume *g_host_vol = nullptr;
+static void release_host_volume()
+{
+    if (g_host_vol) dwtb200_volume_destroy(g_host_vol);
+    g_host_vol = nullptr;
+}
+static dwtb200_volume *host_volume(int nx, int ny, int nz)
+{
+    if (g_host_vol && g_host_vol->nx == nx && g_host_vol->ny == ny && g_host_vol->nz == nz) return g_host_vol;
+    if (g_host_vol) dwtb200_volume_destroy(g_host_vol);
+    g_host_vol = dwtb200_volume_create(nx, ny, nz);
+    return g_host_vol;
+}
 int dwtb200_fwd3_host(const void *src, size_t ssx, size_t ssy, size_t ssz, void *dst, size_t dsx, size_t dsy, size_t dsz,
                       int nx, int ny, int nz)
 {
     API_LOCK();
     NEED_DEV();
-    dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
+    dwtb200_volume *v = host_volume(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
     int r = dwtb200_volume_upload(v, src, ssx, ssy, ssz);
     if (!r) r = dwtb200_volume_fwd3(v);
     if (!r) r = dwtb200_volume_download(v, dst, dsx, dsy, dsz);
-    dwtb200_volume_destroy(v);
     return r;
 }
 int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny, int nz)
 {
     API_LOCK();
     NEED_DEV();
-    dwtb200_volume *v = dwtb200_volume_create(nx, ny, nz);
+    dwtb200_volume *v = host_volume(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
     int r = dwtb200_volume_upload(v, vol, sx, sy, sz);
     if (!r) r = dwtb200_volume_inv3(v);
     if (!r) r = dwtb200_volume_download(v, vol, sx, sy, sz);
-    dwtb200_volume_destroy(v);
     return r;
 }
 

@@ -102,14 +102,6 @@ dim3 tile_grid_of(int kind, const LevelParams &p, int frames);
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 
-// fused tile-pyramid kernels (kernels_pyr.cu): up to pyr_max_levels() consecutive levels in one launch, tiles carried
-// through them in shared memory
-cudaError_t preload_pyr();
-int pyr_max_levels(int kind);
-int pyr_min_side();
-void launch_fwd_pyr(int kind, const void *in, int64_t in_pitch, int64_t in_frame, void *out, int64_t out_pitch, int64_t out_frame,
-                    void *plane, int64_t plane_pitch, int64_t plane_frame, int W0, int H0, int j0, int F, int frames, int T, cudaStream_t st);
-
 // persistent mid-pyramid kernels (kernels_tile.cu): the levels lv[0..nlev) in execution order plus the
 // frames' tails in ONE cooperative launch
 constexpr int MID_MAX_LEVELS = 12;

@@ -108,10 +108,7 @@ FAMILIES = {"stream+bigtail": (0, 16384, 0), "tile+tail": (BIG, 1024, 0), "tile-
             "ring7x2-gen1": (0, 1024, 0, 3 | (5 << 4)), "ring-gen2-forced": (0, 0, 0, 3 | (4 << 4)),
             # the same mixes without the dataflow chain between the kernels of a pyramid (DWTB200_TUNE_CHAIN = 0)
             "nochain-default": (1024 * 1024, 1024, 0, 3, 0), "nochain-stream": (0, 0, 0, 3, 0), "nochain-tile": (BIG, 16, 0, 3, 0),
-            "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1),
-            # runs of tile levels fused into one launch (DWTB200_TUNE_PYR = tile edge), with and without a tail / ring levels
-            "pyr8": (BIG, 1024, 0, 3, 1, 8), "pyr8-tinytail": (BIG, 16, 0, 3, 1, 8), "pyr4-notail": (BIG, 0, 0, 3, 1, 4),
-            "pyr16+ring": (128 * 128, 256, 0, 3, 1, 16), "pyr8-default": (1024 * 1024, 1024, 0, 3, 1, 8)}
+            "chain-tile+bigtail": (BIG, 4096, 0, 3, 1), "chain-ring+tile": (64 * 64, 256, 0, 3, 1)}
 DEFAULT_TUNING = (1024 * 1024, 4096, 0, 3, 1, 0)
 
 
