@@ -42,6 +42,9 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
     T *dst = (T *)p.dst + (int64_t)frame * p.dst_frame;
     const int tid = threadIdx.x;
     const int TAIL_THREADS = blockDim.x;
+    // tasks are indexed (tx, ty) = (lane, warp) by nested strided loops: a flat index split by / and % of a run-time size costs an
+    // integer division (a ~150-cycle dependent chain) per task in passes that have only a few hundred cycles of work
+    const int tx = tid & 31, ty = tid >> 5, nty = TAIL_THREADS >> 5;
 
     // Lines shorter than TAIL_FAST_MIN are evaluated pair by pair from a mirrored 2 * HALO + 2 window: folding every tap index
     // (lifting.cuh: reflect, a loop when the line is shorter than the window) made each of the last levels cost ~1.5 us of
@@ -49,7 +52,8 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
     // level by as many threads as it has entries: tap q of pair k is tab[2 k + q] = reflect(2 k + q - HALO, n).
     __shared__ short tabx[TAIL_FAST_MIN + 2 * WV::HALO + 2], taby[TAIL_FAST_MIN + 2 * WV::HALO + 2];
     int w = cdiv_pow2(p.W0, p.j0), h = cdiv_pow2(p.H0, p.j0);
-    for (int t = tid; t < w * h; t += TAIL_THREADS) bufA[(t / w) * tail_pitch(w) + (t % w)] = ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
+    for (int y = ty; y < h; y += nty)
+        for (int x = tx; x < w; x += 32) bufA[y * tail_pitch(w) + x] = ld(src + (int64_t)y * p.src_pitch + x);
     T *in = bufA, *other = bufB;
     __syncthreads();
 
@@ -70,8 +74,14 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                 // is shifted back so that it ends with the line (recomputes a few pairs, same values)
                 constexpr int P = TAIL_P, NT = 2 * P + 2 * WV::HALO;
                 const int ng = (nlx + P - 1) / P;
-                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
-                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                for (int wt = ty; wt < ng * ((h + 31) >> 5); wt += nty) {   // a warp per (group of pairs, block of 32 lines): no division per task
+                    int g = 0, yb = wt;
+                    while (yb >= ((h + 31) >> 5)) {
+                        yb -= (h + 31) >> 5;
+                        g++;
+                    }
+                    const int y = (yb << 5) + tx;   // consecutive threads walk down a column of windows
+                    if (y >= h) continue;
                     int k = g * P;
                     if (k + P > nlx) k = nlx - P;
                     const T *line = in + y * pw;
@@ -92,8 +102,8 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                     }
                 }
             } else if (w >= 2) {
-                for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
-                    const int y = t / nlx, k = t % nlx;
+                for (int y = ty; y < h; y += nty)
+                for (int k = tx; k < nlx; k += 32) {
                     const T *line = in + y * pw;
                     T win[2 * WV::HALO + 2];
 #pragma unroll
@@ -113,8 +123,14 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
         if (!(WV::GUARD && h <= 1) && h >= TAIL_FAST_MIN) {
             constexpr int P = TAIL_P, NT = 2 * P + 2 * WV::HALO;
             const int ng = (nly + P - 1) / P;
-            for (int t = tid; t < ng * w; t += TAIL_THREADS) {
-                const int g = t / w, x = t - g * w;
+            for (int wt = ty; wt < ng * ((w + 31) >> 5); wt += nty) {
+                int g = 0, xb = wt;
+                while (xb >= ((w + 31) >> 5)) {
+                    xb -= (w + 31) >> 5;
+                    g++;
+                }
+                const int x = (xb << 5) + tx;
+                if (x >= w) continue;
                 int k = g * P;
                 if (k + P > nly) k = nly - P;
                 T win[NT], L[P], H[P];
@@ -135,8 +151,8 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                 }
             }
         } else if (!(WV::GUARD && h <= 1) && h >= 2) {
-            for (int t = tid; t < nly * w; t += TAIL_THREADS) {
-                const int k = t / w, x = t % w;
+            for (int k = ty; k < nly; k += nty)
+            for (int x = tx; x < w; x += 32) {
                 T win[2 * WV::HALO + 2];
 #pragma unroll
                 for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = rows[taby[2 * k + i] * pw + x];
@@ -147,8 +163,8 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
                 if (k < nhy) dst[(int64_t)(nly + k) * p.dst_pitch + x] = H;
             }
         } else {   // h == 1 (or guarded): the single row passes through
-            for (int t = tid; t < h * w; t += TAIL_THREADS) {
-                const int y = t / w, x = t % w;
+            for (int y = ty; y < h; y += nty)
+            for (int x = tx; x < w; x += 32) {
                 T v = rows[y * pw + x];
                 if (!(WV::GUARD && h <= 1)) v = one_fwd<WV>(v);
                 if (x < nlx) next[y * pn + x] = v;
@@ -161,7 +177,8 @@ template <class WV, class LD> __device__ __forceinline__ void fwd_tail_body(cons
         w = nlx;
         h = nly;
     }
-    for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[(t / w) * tail_pitch(w) + (t % w)];
+    for (int y = ty; y < h; y += nty)
+        for (int x = tx; x < w; x += 32) dst[(int64_t)y * p.dst_pitch + x] = in[y * tail_pitch(w) + x];
 }
 
 // P output pairs k .. k+P-1 of one inverse line of n samples: tap(c) returns interleaved coefficient c, emit(q, E, O)
@@ -195,18 +212,22 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
     T *dst = (T *)p.dst + (int64_t)frame * p.dst_frame;
     const int tid = threadIdx.x;
     const int TAIL_THREADS = blockDim.x;
+    // tasks are indexed (tx, ty) = (lane, warp) by nested strided loops: a flat index split by / and % of a run-time size costs an
+    // integer division (a ~150-cycle dependent chain) per task in passes that have only a few hundred cycles of work
+    const int tx = tid & 31, ty = tid >> 5, nty = TAIL_THREADS >> 5;
     const int w0 = cdiv_pow2(p.W0, p.j0), pm = tail_pitch(w0);
     __shared__ short itabx[TAIL_FAST_MIN + 2 * WV::HALO + 2], itaby[TAIL_FAST_MIN + 2 * WV::HALO + 2];
     if (mal) {
         const int h0 = cdiv_pow2(p.H0, p.j0);
-        for (int t = tid; t < w0 * h0; t += TAIL_THREADS) mal[(t / w0) * pm + (t % w0)] = ld(src + (int64_t)(t / w0) * p.src_pitch + (t % w0));
+        for (int y = ty; y < h0; y += nty)
+            for (int x = tx; x < w0; x += 32) mal[y * pm + x] = ld(src + (int64_t)y * p.src_pitch + x);
         __syncthreads();
     }
 
     {   // coarsest LL band
         const int w = cdiv_pow2(p.W0, p.j1), h = cdiv_pow2(p.H0, p.j1);
-        for (int t = tid; t < w * h; t += TAIL_THREADS)
-            bufA[(t / w) * tail_pitch(w) + (t % w)] = mal ? mal[(t / w) * pm + (t % w)] : ld(src + (int64_t)(t / w) * p.src_pitch + (t % w));
+        for (int y = ty; y < h; y += nty)
+            for (int x = tx; x < w; x += 32) bufA[y * tail_pitch(w) + x] = mal ? mal[y * pm + x] : ld(src + (int64_t)y * p.src_pitch + x);
     }
     T *in = bufA, *tmp = bufB;
     __syncthreads();
@@ -236,8 +257,14 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
             // rows: M -> tmp (h x w, rows still in Mallat order)
             if (do_rows && w >= TAIL_FAST_MIN) {
                 const int ng = (nlx + TAIL_P - 1) / TAIL_P;
-                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
-                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                for (int wt = ty; wt < ng * ((h + 31) >> 5); wt += nty) {   // a warp per (group of pairs, block of 32 lines): no division per task
+                    int g = 0, yb = wt;
+                    while (yb >= ((h + 31) >> 5)) {
+                        yb -= (h + 31) >> 5;
+                        g++;
+                    }
+                    const int y = (yb << 5) + tx;   // consecutive threads walk down a column of windows
+                    if (y >= h) continue;
                     const int k = (g + 1) * TAIL_P > nlx ? nlx - TAIL_P : g * TAIL_P;
                     inv_group<WV, TAIL_P>(
                         k, w, [&](int c) { return M(y, (c & 1) ? nlx + (c >> 1) : (c >> 1)); },
@@ -247,8 +274,8 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                         });
                 }
             } else if (do_rows && w >= 2) {
-                for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
-                    const int y = t / nlx, k = t % nlx;
+                for (int y = ty; y < h; y += nty)
+                for (int k = tx; k < nlx; k += 32) {
                     T win[2 * WV::HALO + 2];
 #pragma unroll
                     for (int i = 0; i < 2 * WV::HALO + 2; i++) win[i] = M(y, itabx[2 * k + i]);
@@ -258,9 +285,10 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                     if (2 * k + 1 < w) tmp[y * pw + 2 * k + 1] = O;
                 }
             } else {
-                for (int t = tid; t < h * w; t += TAIL_THREADS) {
-                    const T v = M(t / w, t % w);
-                    tmp[(t / w) * pw + (t % w)] = do_rows ? one_inv<WV>(v) : v;
+                for (int y = ty; y < h; y += nty)
+                for (int x = tx; x < w; x += 32) {
+                    const T v = M(y, x);
+                    tmp[y * pw + x] = do_rows ? one_inv<WV>(v) : v;
                 }
             }
             __syncthreads();
@@ -269,8 +297,14 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
             const bool last = (j - 1 == p.j0);
             if (do_cols && h >= TAIL_FAST_MIN) {
                 const int ng = (nly + TAIL_P - 1) / TAIL_P;
-                for (int t = tid; t < ng * w; t += TAIL_THREADS) {
-                    const int g = t / w, x = t - g * w;
+                for (int wt = ty; wt < ng * ((w + 31) >> 5); wt += nty) {
+                    int g = 0, xb = wt;
+                    while (xb >= ((w + 31) >> 5)) {
+                        xb -= (w + 31) >> 5;
+                        g++;
+                    }
+                    const int x = (xb << 5) + tx;
+                    if (x >= w) continue;
                     const int k = (g + 1) * TAIL_P > nly ? nly - TAIL_P : g * TAIL_P;
                     inv_group<WV, TAIL_P>(
                         k, h, [&](int c) { return tmp[((c & 1) ? nly + (c >> 1) : (c >> 1)) * pw + x]; },
@@ -285,8 +319,8 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                         });
                 }
             } else
-            for (int t = tid; t < nly * w; t += TAIL_THREADS) {
-                const int k = t / w, x = t % w;
+            for (int k = ty; k < nly; k += nty)
+            for (int x = tx; x < w; x += 32) {
                 T E, O = T(0);
                 if (do_cols && h >= 2) {
                     T win[2 * WV::HALO + 2];
@@ -309,8 +343,14 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
             // columns first (int 5/3): M -> tmp (rows de-interleaved, columns still in Mallat order)
             if (h >= TAIL_FAST_MIN) {
                 const int ng = (nly + TAIL_P - 1) / TAIL_P;
-                for (int t = tid; t < ng * w; t += TAIL_THREADS) {
-                    const int g = t / w, x = t - g * w;
+                for (int wt = ty; wt < ng * ((w + 31) >> 5); wt += nty) {
+                    int g = 0, xb = wt;
+                    while (xb >= ((w + 31) >> 5)) {
+                        xb -= (w + 31) >> 5;
+                        g++;
+                    }
+                    const int x = (xb << 5) + tx;
+                    if (x >= w) continue;
                     const int k = (g + 1) * TAIL_P > nly ? nly - TAIL_P : g * TAIL_P;
                     inv_group<WV, TAIL_P>(
                         k, h, [&](int c) { return M((c & 1) ? nly + (c >> 1) : (c >> 1), x); },
@@ -320,8 +360,8 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                         });
                 }
             } else
-            for (int t = tid; t < nly * w; t += TAIL_THREADS) {
-                const int k = t / w, x = t % w;
+            for (int k = ty; k < nly; k += nty)
+            for (int x = tx; x < w; x += 32) {
                 if (h >= 2) {
                     T win[2 * WV::HALO + 2];
 #pragma unroll
@@ -339,8 +379,14 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
             const bool last = (j - 1 == p.j0);
             if (w >= TAIL_FAST_MIN) {
                 const int ng = (nlx + TAIL_P - 1) / TAIL_P;
-                for (int t = tid; t < h * ng; t += TAIL_THREADS) {
-                    const int g = t / h, y = t - g * h;   // consecutive threads walk down a column of windows
+                for (int wt = ty; wt < ng * ((h + 31) >> 5); wt += nty) {   // a warp per (group of pairs, block of 32 lines): no division per task
+                    int g = 0, yb = wt;
+                    while (yb >= ((h + 31) >> 5)) {
+                        yb -= (h + 31) >> 5;
+                        g++;
+                    }
+                    const int y = (yb << 5) + tx;   // consecutive threads walk down a column of windows
+                    if (y >= h) continue;
                     const int k = (g + 1) * TAIL_P > nlx ? nlx - TAIL_P : g * TAIL_P;
                     inv_group<WV, TAIL_P>(
                         k, w, [&](int c) { return tmp[y * pw + ((c & 1) ? nlx + (c >> 1) : (c >> 1))]; },
@@ -355,8 +401,8 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
                         });
                 }
             } else
-            for (int t = tid; t < h * nlx; t += TAIL_THREADS) {
-                const int y = t / nlx, k = t % nlx;
+            for (int y = ty; y < h; y += nty)
+            for (int k = tx; k < nlx; k += 32) {
                 T E, O = T(0);
                 if (w >= 2) {
                     T win[2 * WV::HALO + 2];
@@ -379,7 +425,8 @@ __device__ __forceinline__ void inv_tail_body(const TailParams &p, int frame, ty
     }
     if (p.j1 == p.j0) {   // nothing to do: pass the band through
         const int w = cdiv_pow2(p.W0, p.j0), h = cdiv_pow2(p.H0, p.j0);
-        for (int t = tid; t < w * h; t += TAIL_THREADS) dst[(int64_t)(t / w) * p.dst_pitch + (t % w)] = in[(t / w) * tail_pitch(w) + (t % w)];
+        for (int y = ty; y < h; y += nty)
+            for (int x = tx; x < w; x += 32) dst[(int64_t)y * p.dst_pitch + x] = in[y * tail_pitch(w) + x];
     }
 }
 
