@@ -185,9 +185,7 @@ void dwtb200_set_strip_rows(int rows);
  *                          levels the streaming kernels (2048*2048)
  *   DWTB200_TUNE_TAIL_MAX  the single-launch tail starts at the first level with <= value samples per
  *                          frame (64*64; 0 disables the tail)
- *   DWTB200_TUNE_MID_MAX   levels with <= value samples over all frames (and <= TILE_MAX) are fused, together
- *                          with the tail, into ONE persistent cooperative launch (0 = off: a grid-wide
- *                          barrier measured ~5 us on B200, no better than a dependent launch)
+ *   DWTB200_TUNE_MID_MAX   accepted and ignored (the persistent mid-level kernels of round 1 were never faster and are gone)
  *   DWTB200_TUNE_PDL       1: kernels of a pyramid are chained by programmatic dependent launch (0: measured no gain)
  *   DWTB200_TUNE_NARROW    1: streaming kernels hold 16 instead of 32 bytes per lane: twice the warps per SM (0)
  *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips and download for large dense images (1)

@@ -73,8 +73,6 @@ struct Ctx {
     // kernels instead of the streaming ones; the tail kernel starts at the first level with at most
     // tail_max samples per frame
     int64_t tile_max = (int64_t)1024 * 1024;
-    int64_t mid_max = 0;   // levels this small (and <= tile_max) share ONE persistent cooperative launch; 0 = off
-    int mid_ctas_per_sm = 4;
     int tail_max = 64 * 64;
     int narrow = 0;
     int dbg = 0;
@@ -284,7 +282,7 @@ int dwtb200_init(int device)
     CK(preload_tail());
     CK(preload_generic());
     CK(preload_util());
-    CK(preload_tile(g.sm_count, g.mid_ctas_per_sm));
+    CK(preload_tile());
     CK(cudaStreamCreateWithFlags(&g.st0, cudaStreamNonBlocking));
     g.st = g.st0;
     CK(cudaEventCreate(&g.e0));
@@ -432,7 +430,7 @@ int dwtb200_set_tuning(int key, long long value)
     API_LOCK();
     switch (key) {
     case DWTB200_TUNE_TILE_MAX: g.tile_max = value; break;
-    case DWTB200_TUNE_MID_MAX: g.mid_max = value; break;
+    case DWTB200_TUNE_MID_MAX: break;   // the persistent mid-level kernels were removed in round 2 (never faster than one launch per level)
     case DWTB200_TUNE_PIPELINE: g.pipeline = value != 0; break;
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
@@ -689,22 +687,18 @@ struct Band {   // where an LL band lives
 // ---- kernel selection for the dense path -----------------------------------------------------------
 // Level j (input w_j x h_j, all frames) is handled by
 //   STREAM  kernels_stream.cu   big, HBM-bound levels: one launch per level
-//   TILE    kernels_tile.cu     one launch per level, small tiles (only when the persistent kernel is off)
-//   MID     kernels_tile.cu     L2-resident levels: ALL of them plus the tail in ONE cooperative launch
+//   TILE    kernels_tile.cu     one launch per level, small tiles
 //   TAIL    kernels_tail.cu     every remaining level once the LL band fits one CTA's shared memory
-enum { PLAN_STREAM = 0, PLAN_TILE = 1, PLAN_MID = 2 };
+enum { PLAN_STREAM = 0, PLAN_TILE = 1 };
 struct DensePlan {
     int jt;                 // first level of the tail (== J: no tail); -1: the dense kernels cannot take this pyramid
-    int jm;                 // first level of the persistent launch (== jt when it holds no tile level)
-    bool tail_in_mid;       // the tail runs inside the persistent launch
     int type[40];
 };
 
 DensePlan dense_plan(const dwtb200_image *im, int J)
 {
     DensePlan pl;
-    const bool mid_on = g.mid_max > 0;
-    int cap = mid_on ? mid_tail_max_elems(im->kind) : tail_max_elems(im->kind);
+    int cap = tail_max_elems(im->kind);
     if (g.tail_max < cap) cap = g.tail_max;
     pl.jt = J;
     for (int j = 0; j < J; j++) {
@@ -718,17 +712,10 @@ DensePlan dense_plan(const dwtb200_image *im, int J)
             return pl;
         }
     }
-    pl.jm = pl.jt;
     for (int j = 0; j < pl.jt; j++) {
         const int64_t n = (int64_t)cdiv_pow2(im->ox, j) * cdiv_pow2(im->oy, j) * im->frames;
-        if (mid_on && n <= g.mid_max && n <= g.tile_max && pl.jt - j <= MID_MAX_LEVELS) {
-            pl.type[j] = PLAN_MID;
-            if (j < pl.jm) pl.jm = j;
-        } else {
-            pl.type[j] = n <= g.tile_max ? PLAN_TILE : PLAN_STREAM;
-        }
+        pl.type[j] = n <= g.tile_max ? PLAN_TILE : PLAN_STREAM;
     }
-    pl.tail_in_mid = mid_on && pl.jt < J && pl.jm < pl.jt;
     return pl;
 }
 
@@ -916,10 +903,9 @@ void stream_inv(int kind, const LevelParams &p, int frames, cudaStream_t st)
 
 // ---- the dense path as a list of launches, linked into a chain (struct Chain, kernels.h) ----------------
 struct Launch {
-    enum { RING_F, REG_F, TILE_F, TAIL_F, MID_F, RING_I, REG_I, TILE_I, TAIL_I, MID_I } type;
+    enum { RING_F, REG_F, TILE_F, TAIL_F, RING_I, REG_I, TILE_I, TAIL_I } type;
     LevelParams lp;
     TailParams tp;
-    MidParams mp;
     bool chainable = false;
     // how consumers find the row block of an LL row this launch produces
     int out_nblocks = 0, out_div = 1, out_bias = 0, out_need = 0;
@@ -1005,12 +991,10 @@ int issue(dwtb200_image *im, std::vector<Launch> &ls)
         case Launch::REG_F: launch_fwd_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_F: launch_fwd_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_F: launch_fwd_tail(im->kind, l.tp, im->frames, g.st); break;
-        case Launch::MID_F: e = launch_fwd_mid(im->kind, l.mp, g.st); break;
         case Launch::RING_I: launch_inv_ring(im->kind, l.lp, im->frames, l.lp.cfg, g.st); break;
         case Launch::REG_I: launch_inv_level(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TILE_I: launch_inv_tile(im->kind, l.lp, im->frames, g.st); break;
         case Launch::TAIL_I: launch_inv_tail(im->kind, l.tp, im->frames, g.st); break;
-        case Launch::MID_I: e = launch_inv_mid(im->kind, l.mp, g.st); break;
         }
         if (e != cudaSuccess) return fail(DWTB200_ECUDA, "cooperative launch: %s", cudaGetErrorString(e));
         g.launches++;
@@ -1049,19 +1033,6 @@ void plan_fwd_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstart, s
             L.total = im->frames;
             return;
         }
-        if (pl.type[j] == PLAN_MID) {   // levels j .. jt-1 and the tail in one cooperative launch
-            L.type = Launch::MID_F;
-            MidParams &mp = L.mp;
-            memset(&mp, 0, sizeof mp);
-            mp.frames = im->frames;
-            mp.tail_elems = mid_tail_buf_elems(im->kind);
-            for (; j < pl.jt; j++) in = fwd_level_params(im, j, J, in, dst_plane, mp.lv[mp.nlev++]);
-            if (pl.jt < J) {
-                mp.has_tail = 1;
-                mp.tail = tail_params(pl.jt, in);
-            }
-            return;
-        }
         in = fwd_level_params(im, j, J, in, dst_plane, L.lp);
         plan_level(im, L, false, pl.type[j]);
     }
@@ -1089,21 +1060,7 @@ void plan_inv_dense(dwtb200_image *im, int J, const DensePlan &pl, int jstop, st
         return t;
     };
     int jtop = jt < J ? jt : J;   // levels jtop-1 .. 0 remain after the tail
-    if (pl.jm < jt) {             // tail (if any) and levels jt-1 .. jm in one cooperative launch
-        ls.emplace_back();
-        Launch &L = ls.back();
-        L.type = Launch::MID_I;
-        MidParams &mp = L.mp;
-        memset(&mp, 0, sizeof mp);
-        mp.frames = im->frames;
-        mp.tail_elems = mid_tail_buf_elems(im->kind);
-        if (jt < J) {
-            mp.has_tail = 1;
-            mp.tail = tail_params();
-        }
-        for (int j = jt - 1; j >= pl.jm; j--) inv_level_params(im, j, J, src_plane, dst_plane, mp.lv[mp.nlev++]);
-        jtop = pl.jm;
-    } else if (jt < J) {
+    if (jt < J) {
         ls.emplace_back();
         Launch &L = ls.back();
         L.type = Launch::TAIL_I;
@@ -1529,7 +1486,7 @@ bool ip_53_fast(const dwtb200_image *im, bool inverse, int J, DensePlan &pl)
     level_geometry(im, 0, inverse, lp);
     if (lp.narrow || !(g.ring & (inverse ? 2 : 1)) || !ring_interleaved_ok(im->kind) || !ring_interleaved_cfg_ok(lp.cfg)) return false;
     pl = dense_plan(im, J);
-    if (pl.jt < 1 || pl.jm < pl.jt) return false;   // degenerate pyramid, or the persistent mid-level launch is switched on
+    if (pl.jt < 1) return false;   // degenerate pyramid
     return true;
 }
 int ip_run53(dwtb200_image *im, bool inverse, int J, const DensePlan &pl)
@@ -1920,7 +1877,7 @@ bool pipeline_applies(const dwtb200_image *im, int64_t sx, int64_t sy, int ix, i
     if (!g.pipeline || g.force_generic || im->frames != 1 || sy != (int64_t)im->es || ix != im->ox || iy != im->oy || J < 2) return false;
     if ((int64_t)im->ox * im->oy * (int64_t)im->es < ((int64_t)32 << 20) || sx < (int64_t)im->ox * (int64_t)im->es) return false;
     pl = dense_plan(im, J);
-    return pl.jt > 1 && pl.type[0] == PLAN_STREAM && pl.jm > 0;
+    return pl.jt > 1 && pl.type[0] == PLAN_STREAM;
 }
 
 int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int J, const DensePlan &pl)

@@ -13,7 +13,7 @@ cudaError_t preload_stream();
 cudaError_t preload_tail();
 cudaError_t preload_generic();
 cudaError_t preload_util();
-cudaError_t preload_tile(int sm_count, int mid_ctas_per_sm);
+cudaError_t preload_tile();
 
 // ---- dataflow links between the kernels of one transform (chain.cuh) ---------------------------------
 // The kernels of a pyramid are launched back to back with programmatic stream serialization: a kernel may
@@ -102,9 +102,6 @@ dim3 tile_grid_of(int kind, const LevelParams &p, int frames);
 void launch_fwd_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st);
 
-// persistent mid-pyramid kernels (kernels_tile.cu): the levels lv[0..nlev) in execution order plus the
-// frames' tails in ONE cooperative launch
-constexpr int MID_MAX_LEVELS = 12;
 // ---- tail kernels: all remaining coarse levels of a plane inside one CTA's shared memory -----------
 struct TailParams {
     const void *src;   // fwd: LL input of level j0 (w0 x h0); inv: Mallat plane holding the subbands
@@ -117,17 +114,6 @@ struct TailParams {
 void launch_fwd_tail(int kind, const TailParams &p, int frames, cudaStream_t st);
 void launch_inv_tail(int kind, const TailParams &p, int frames, cudaStream_t st);
 int tail_max_elems(int kind);
-
-struct MidParams {
-    LevelParams lv[MID_MAX_LEVELS];
-    TailParams tail;
-    int nlev, has_tail, frames;
-    int tail_elems;   // elements per tail buffer (>= the tail's first LL band)
-};
-cudaError_t launch_fwd_mid(int kind, const MidParams &mp, cudaStream_t st);
-cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st);
-int mid_tail_max_elems(int kind);
-int mid_tail_buf_elems(int kind);
 
 // ---- interleaved in-place family (kernels_inplace.cu) --------------------------------------------------------
 cudaError_t preload_inplace();

@@ -13,8 +13,6 @@
 // 17098-17154 / 18178-18195 inverse): every sample sees "row lifting + scale, then column lifting +
 // scale" (int inverse: columns first) with whole-sample mirrored borders, so the result is
 // bit-identical to the reference whichever kernel family handles a level.
-#include <cooperative_groups.h>
-
 #include "chain.cuh"
 #include "tail_body.cuh"
 
@@ -255,67 +253,6 @@ template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_tile(c
     }
 }
 
-// ---- persistent kernels: every level from the first L2-resident one to the end of the pyramid in ONE
-// cooperative launch.  A dependent kernel launch costs ~5 us on B200 however small the kernel, and the
-// last ~10 levels of an 8192^2 pyramid together hold 1.6 % of the samples: here they cost one launch,
-// with a grid-wide barrier (a few hundred ns) between levels instead.  CTAs loop over the tiles of a
-// level, synchronise, go on to the next level; the frames' tails run on one CTA each at the end (forward)
-// or the beginning (inverse).  Inputs written earlier in the same launch are read with ld.global.cg.
-template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_fwd_mid(const __grid_constant__ MidParams mp)
-{
-    using T = typename WV::T;
-    using C = TileCfg<WV>;
-    __shared__ __align__(16) TileSmem<WV> sm;
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    for (int l = 0; l < mp.nlev; l++) {
-        const LevelParams &p = mp.lv[l];
-        const int tx = (p.W + C::TW - 1) / C::TW, ty = (p.H + C::TH - 1) / C::TH;
-        const int ntiles = tx * ty * mp.frames;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const int bz = t / (tx * ty), r = t % (tx * ty);
-            if (l == 0) fwd_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdNc());   // input written by an earlier launch
-            else fwd_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdCg());
-            __syncthreads();
-        }
-        if (l + 1 < mp.nlev || mp.has_tail) grid.sync();
-    }
-    if (mp.has_tail) {
-        T *bufA = reinterpret_cast<T *>(&sm), *bufB = bufA + mp.tail_elems;
-        for (int f = blockIdx.x; f < mp.frames; f += gridDim.x) {
-            if (mp.nlev) fwd_tail_body<WV>(mp.tail, f, bufA, bufB, LdCg());
-            else fwd_tail_body<WV>(mp.tail, f, bufA, bufB, LdNc());
-            __syncthreads();
-        }
-    }
-}
-template <class WV> __global__ void __launch_bounds__(TILE_THREADS) k_inv_mid(const __grid_constant__ MidParams mp)
-{
-    using T = typename WV::T;
-    using C = TileCfg<WV>;
-    __shared__ __align__(16) TileSmem<WV> sm;
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    if (mp.has_tail) {
-        T *bufA = reinterpret_cast<T *>(&sm), *bufB = bufA + mp.tail_elems;
-        for (int f = blockIdx.x; f < mp.frames; f += gridDim.x) {
-            inv_tail_body<WV>(mp.tail, f, bufA, bufB, LdNc());
-            __syncthreads();
-        }
-        if (mp.nlev) grid.sync();
-    }
-    for (int l = 0; l < mp.nlev; l++) {   // lv[] is in execution order: coarsest level first
-        const LevelParams &p = mp.lv[l];
-        const int tx = (p.W + C::TW - 1) / C::TW, ty = (p.H + C::TH - 1) / C::TH;
-        const int ntiles = tx * ty * mp.frames;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const int bz = t / (tx * ty), r = t % (tx * ty);
-            // the subbands come from an earlier launch, the LL band from this one: one loader for both
-            inv_tile_body<WV>(p, r % tx, r / tx, bz, sm, LdCg());
-            __syncthreads();
-        }
-        if (l + 1 < mp.nlev) grid.sync();
-    }
-}
-
 // ---- launchers -------------------------------------------------------------------------------
 template <class WV> static dim3 tile_grid(const LevelParams &p, int frames)
 {
@@ -344,90 +281,19 @@ void launch_inv_tile(int kind, const LevelParams &p, int frames, cudaStream_t st
     });
 }
 
-int mid_tail_buf_elems(int kind)   // stride between the tail's two shared-memory buffers inside the tile staging area
-{
-    int n = 0;
-    dispatch_kind(kind, [&](auto wv) {
-        using WV = decltype(wv);
-        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T)));
-    });
-    return n;
-}
-int mid_tail_max_elems(int kind)
-{
-    // the tail's two LL buffers alias the tile staging area of the persistent kernel
-    int n = 0;
-    dispatch_kind(kind, [&](auto wv) {
-        using WV = decltype(wv);
-        n = (int)(sizeof(TileSmem<WV>) / (2 * sizeof(typename WV::T))) / 17 * 16;   // room for the odd row pitch (tail_pitch)
-    });
-    return n;
-}
-
-static int g_mid_ctas_per_sm[2][K_COUNT];   // [inverse][kind], filled by preload_tile()
-static int g_sm_count = 0;
-
-template <class K> static cudaError_t launch_coop(K kern, const MidParams &mp, int ctas_per_sm, int work, cudaStream_t st)
-{
-    int grid = ctas_per_sm * g_sm_count;
-    if (grid > work) grid = work;
-    if (grid < 1) grid = 1;
-    void *args[] = {(void *)&mp};
-    return cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(TILE_THREADS), args, 0, st);
-}
-template <class WV> static int mid_work(const MidParams &mp)
-{
-    using C = TileCfg<WV>;
-    int work = mp.frames;
-    for (int l = 0; l < mp.nlev; l++) {
-        const int n = ((mp.lv[l].W + C::TW - 1) / C::TW) * ((mp.lv[l].H + C::TH - 1) / C::TH) * mp.frames;
-        if (n > work) work = n;
-    }
-    return work;
-}
-cudaError_t launch_fwd_mid(int kind, const MidParams &mp, cudaStream_t st)
-{
-    cudaError_t e = cudaSuccess;
-    dispatch_kind(kind, [&](auto wv) {
-        using WV = decltype(wv);
-        e = launch_coop(k_fwd_mid<WV>, mp, g_mid_ctas_per_sm[0][kind], mid_work<WV>(mp), st);
-    });
-    return e;
-}
-cudaError_t launch_inv_mid(int kind, const MidParams &mp, cudaStream_t st)
-{
-    cudaError_t e = cudaSuccess;
-    dispatch_kind(kind, [&](auto wv) {
-        using WV = decltype(wv);
-        e = launch_coop(k_inv_mid<WV>, mp, g_mid_ctas_per_sm[1][kind], mid_work<WV>(mp), st);
-    });
-    return e;
-}
-
 template <class K> static cudaError_t touch(K kern)
 {
     cudaFuncAttributes a;
     return cudaFuncGetAttributes(&a, kern);
 }
-template <class K> static cudaError_t occupancy(K kern, int &out, int cap)
+cudaError_t preload_tile()
 {
-    cudaError_t e = touch(kern);
-    int n = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TILE_THREADS, 0);
-    out = n < cap ? n : cap;
-    return e;
-}
-cudaError_t preload_tile(int sm_count, int mid_ctas_per_sm)
-{
-    g_sm_count = sm_count;
     cudaError_t e = cudaSuccess;
     for (int kind = 0; kind < K_COUNT; kind++)
         dispatch_kind(kind, [&](auto wv) {
             using WV = decltype(wv);
             if (e == cudaSuccess) e = touch(k_fwd_tile<WV>);
             if (e == cudaSuccess) e = touch(k_inv_tile<WV>);
-            if (e == cudaSuccess) e = occupancy(k_fwd_mid<WV>, g_mid_ctas_per_sm[0][kind], mid_ctas_per_sm);
-            if (e == cudaSuccess) e = occupancy(k_inv_mid<WV>, g_mid_ctas_per_sm[1][kind], mid_ctas_per_sm);
         });
     return e;
 }

@@ -1,6 +1,5 @@
 // tail_body.cuh -- all remaining coarse levels of ONE frame inside one CTA's shared memory.
-// Device bodies shared by the stand-alone tail kernels (kernels_tail.cu) and the persistent
-// mid-pyramid kernels (kernels_tile.cu).  Semantics: see kernels_tail.cu.
+// Device bodies of the tail kernels (kernels_tail.cu).  Semantics: see kernels_tail.cu.
 #pragma once
 #include "kernels.h"
 #include "lifting.cuh"
