@@ -65,3 +65,18 @@ def test_compat_library_exports_the_reference_symbols():
     so = ctypes.CDLL(os.path.join(ROOT, "libdwt_b200", "libdwt_compat.so"))
     for n in names:
         assert hasattr(so, n), n
+
+
+def test_strips_fail_loudly_without_gpu_and_validate_arguments():
+    import ctypes as C
+    import libdwt_b200 as d
+    L = d.lib()
+    p = d.api.StripPlanC()
+    assert L.c.dwtb200_strips_plan(0, 100, 2, 1, 4, 0, C.byref(p)) == -3          # DWTB200_EINVAL
+    assert L.c.dwtb200_strips_plan(100, 100, 2, 1, 4, 2, C.byref(p)) == -3        # rank out of range
+    assert L.c.dwtb200_strips_plan(100, 100, 17, 1, 4, 0, C.byref(p)) == -3       # more ranks than a box has GPUs
+    assert L.c.dwtb200_strips_plan(64, 64, 8, 3, 4, 0, C.byref(p)) == 0 and p.neighbours_only == 0   # strips shorter than the halo
+    if L.c.dwtb200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    assert not L.c.dwtb200_strips_create(d.CDF97_F32, 4096, 4096, 0, 0, 1, b"dwtb200-abi-test")
+    assert b"CUDA" in L.c.dwtb200_last_error() or b"device" in L.c.dwtb200_last_error()

@@ -408,6 +408,38 @@ def test_properties_at_full_size(dev):
     f.close(); k.close()
 
 
+def test_concurrent_host_calls_are_serialised(dev, oracle):
+    """The reference is not re-entrant; this library keeps global state too, but every entry point takes one process-wide lock
+    (include/dwtb200.h): host threads calling the reference-named transforms at the same time must all get the right bits."""
+    import threading
+    cases = [("97", "s", 517, 301), ("53", "i", 300, 200), ("97", "s", 640, 480), ("97", "d", 129, 127)]
+    want, imgs = [], []
+    for (w, t, ox, oy) in cases:
+        a = oracle.fill(np.zeros((oy, ox), DT[t]), t)
+        imgs.append(a.copy())
+        oracle.fwd2(a, w, t)
+        want.append(a)
+    errs = []
+
+    def work(i):
+        w, t, ox, oy = cases[i]
+        try:
+            for _ in range(6):
+                b = imgs[i].copy()
+                J = dev.fwd2(b, w, t)
+                if not (bits(b, t) == bits(want[i], t)).all():
+                    errs.append(f"thread {i}: forward differs")
+                dev.inv2(b, w, t, j_max=J)
+        except Exception as e:   # noqa: BLE001
+            errs.append(f"thread {i}: {e}")
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+
+
 # ---- 3-D ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(16, 16, 16), (33, 20, 9), (64, 48, 40), (5, 5, 5), (100, 37, 21), (520, 300, 70), (256, 257, 131)],
                          ids=lambda s: "x".join(map(str, s)))
