@@ -746,13 +746,14 @@ void level_geometry(const dwtb200_image *im, int j, bool inverse, LevelParams &p
     p.sub_aligned = (p.nLx % vec) == 0;
     // (an inverse level whose HL / HH column origin is not 16-byte aligned falls back to the register kernels and their geometry)
     const bool ring_here = !p.narrow && (inverse ? ((g.ring & 2) && p.sub_aligned) : (g.ring & 1));
-    const int forced = (g.ring >> 4) & 7;   // DWTB200_TUNE_RING bits 4-6 force a shape
+    int forced = (g.ring >> 4) & 7;   // DWTB200_TUNE_RING bits 4-6 force a shape
+    if (forced > 5) forced = 0;
     const bool v2 = ring_here && g.ring_v2 && (forced == 0 || forced == RING_CFG_V2) && (!inverse || ring2_inverse_ok(im->kind)) &&
                     ring2_width_ok(im->kind, W);
     const int outw = v2 ? ring2_out_width(im->kind) : stream_out_width(im->kind, p.narrow);
     p.ncg = (W + outw - 1) / outw;
     if (v2) {
-        p.cfg = RING_CFG_V2;
+        p.cfg = ring2_cfg_for(p.ncg);   // 8 warps per CTA, or 4 / 2 / 1 for rows of at most 4 / 2 / 1 windows
         const int cw = ring_cta_warps(p.cfg), nb = (p.ncg + cw - 1) / cw;
         p.bw = (p.ncg + nb - 1) / nb;
         p.nbands = (p.ncg + p.bw - 1) / p.bw;

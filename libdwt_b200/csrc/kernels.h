@@ -83,8 +83,11 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
 // second generation (kernels_ring2.cu, cfg 4): 256-column windows, 8 consumer warps, producer folded into warp 0; inverse for the
 // rows-first (float / double) wavelets only
 cudaError_t preload_ring2();
-void launch_fwd_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st);
-void launch_inv_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st);
+void launch_fwd_ring2(int kind, const LevelParams &p, int frames, int cta_warps, cudaStream_t st);
+void launch_inv_ring2(int kind, const LevelParams &p, int frames, int cta_warps, cudaStream_t st);
+int ring2_cfg_for(int ncg);      // cfg number of the CTA shape for a row of ncg windows: 8, 4, 2 or 1 warps per CTA (16 warps per SM each)
+int ring2_cfg_warps(int cfg);
+bool ring2_cfg(int cfg);
 bool ring2_inverse_ok(int kind);
 bool ring2_width_ok(int kind, int W);
 int ring2_out_width(int kind);

@@ -442,7 +442,7 @@ constexpr int RING_NCFG = 4;
 template <class WV> constexpr bool ring_il() { return std::is_same<WV, W97F>::value || std::is_same<WV, W53F>::value; }
 bool ring_interleaved_ok(int kind) { return kind == K_CDF97_F32 || kind == K_CDF53_F32; }
 // CTA shapes whose five-segment inverse ring still fits the SM's shared memory NCTA times (all but 8 x 2)
-bool ring_interleaved_cfg_ok(int cfg) { return cfg != 2 && cfg != RING_CFG_V2; }
+bool ring_interleaved_cfg_ok(int cfg) { return cfg != 2 && !ring2_cfg(cfg); }
 template <class F> static void dispatch_cfg(int cfg, F &&f)
 {
     if (cfg == 1) f(RingCfg<15, 1>{});
@@ -474,7 +474,7 @@ int ring_warps_per_sm(int cfg) { return ring_cta_warps(cfg) * ring_ctas_per_sm(c
 
 void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st)
 {
-    if (cfg == RING_CFG_V2 && !p.il) return launch_fwd_ring2(kind, p, frames, st);
+    if (ring2_cfg(cfg) && !p.il) return launch_fwd_ring2(kind, p, frames, ring2_cfg_warps(cfg), st);
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
         constexpr int V = 32 / (int)sizeof(typename WV::T);
@@ -494,7 +494,7 @@ void launch_fwd_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
 
 void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaStream_t st)
 {
-    if (cfg == RING_CFG_V2 && !p.il && ring2_inverse_ok(kind)) return launch_inv_ring2(kind, p, frames, st);
+    if (ring2_cfg(cfg) && !p.il && ring2_inverse_ok(kind)) return launch_inv_ring2(kind, p, frames, ring2_cfg_warps(cfg), st);
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
         constexpr int V = 32 / (int)sizeof(typename WV::T);
@@ -511,7 +511,7 @@ void launch_inv_ring(int kind, const LevelParams &p, int frames, int cfg, cudaSt
         });
     });
 }
-int ring_cta_warps(int cfg) { return cfg == 1 ? 15 : (cfg == 2 || cfg == RING_CFG_V2) ? 8 : cfg == 3 ? 5 : 7; }
-int ring_ctas_per_sm(int cfg) { return cfg == 1 ? 1 : cfg == 3 ? 3 : 2; }
+int ring_cta_warps(int cfg) { return ring2_cfg(cfg) ? ring2_cfg_warps(cfg) : cfg == 1 ? 15 : cfg == 2 ? 8 : cfg == 3 ? 5 : 7; }
+int ring_ctas_per_sm(int cfg) { return ring2_cfg(cfg) ? 16 / ring2_cfg_warps(cfg) : cfg == 1 ? 1 : cfg == 3 ? 3 : 2; }
 
 }  // namespace dwtb200

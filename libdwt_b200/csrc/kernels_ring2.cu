@@ -30,9 +30,12 @@
 
 namespace dwtb200 {
 
-template <class T> struct R2 {
+// CW = warps (windows) per CTA: 8 for rows of at least 8 windows, 4 / 2 / 1 for the narrower levels of a batch of frames (a level of
+// 1024 / 512 / 256 columns is 4 / 2 / 1 windows wide: an 8-warp CTA would run with half, a quarter, an eighth of its warps and the
+// SM with as little of its occupancy); 16 / CW CTAs per SM keep 16 warps and ~200 KB of ring per SM in every shape.
+template <class T, int CW_ = 8> struct R2 {
     static constexpr int ES = (int)sizeof(T), VPL = 32 / ES, HV = VPL / 2, OUTW = 32 * VPL;
-    static constexpr int CW = 8, NCTA = 2, THREADS = CW * 32;   // 8 warps, all consumers; they take turns as the producer
+    static constexpr int CW = CW_, NCTA = 16 / CW_, THREADS = CW * 32;   // all warps are consumers; they take turns as the producer
     static constexpr int HPAD = 4;                   // raw samples staged beyond either end of the band (the lifting reach)
     static constexpr int ROWB = CW * 1024 + 64;      // bytes of a staged band row (>= (CW * OUTW + 2 * HPAD) * ES)
     static constexpr int SLOTB = 2 * ROWB;           // a row pair; inverse: four subband segments of SEGB bytes
@@ -192,10 +195,10 @@ template <class WV, int VPL> __device__ __forceinline__ void hinv_edge(typename 
 // forward level
 // =====================================================================================================
 // CTA (band, strip): band = p.bw adjacent column groups of 32 * VPL columns (one warp each), strip = p.pps row pairs.
-template <class WV> __global__ void __launch_bounds__(R2<typename WV::T>::THREADS, R2<typename WV::T>::NCTA) k_fwd_ring2(const LevelParams p)
+template <class WV, int CW> __global__ void __launch_bounds__(R2<typename WV::T, CW>::THREADS, R2<typename WV::T, CW>::NCTA) k_fwd_ring2(const LevelParams p)
 {
     using T = typename WV::T;
-    using C = R2<T>;
+    using C = R2<T, CW>;
     constexpr int VPL = C::VPL, HV = C::HV, OUTW = C::OUTW, ES = C::ES, HPAD = C::HPAD;
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,10 +382,10 @@ template <class WV> __global__ void __launch_bounds__(R2<typename WV::T>::THREAD
 // =====================================================================================================
 // A slot holds the four subband row segments one iteration consumes: [LL | HL] of coefficient row 2k and [LH | HH] of row 2k+1.
 // Needs 16-byte aligned HL / HH column origins (p.sub_aligned); the host falls back to k_inv_level otherwise.
-template <class WV> __global__ void __launch_bounds__(R2<typename WV::T>::THREADS, R2<typename WV::T>::NCTA) k_inv_ring2(const LevelParams p)
+template <class WV, int CW> __global__ void __launch_bounds__(R2<typename WV::T, CW>::THREADS, R2<typename WV::T, CW>::NCTA) k_inv_ring2(const LevelParams p)
 {
     using T = typename WV::T;
-    using C = R2<T>;
+    using C = R2<T, CW>;
     static_assert(!WV::INV_COLS_FIRST, "columns-first inverses lift rows on register values: kernels_ring.cu");
     constexpr int VPL = C::VPL, HV = C::HV, OUTW = C::OUTW, ES = C::ES, HPS = C::HPS, SEGB = C::SEGB, SW = OUTW / 2;
     extern __shared__ __align__(128) unsigned char ring_smem[];
@@ -551,16 +554,29 @@ template <class K> static cudaError_t prep2(K kern, int smem)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     return e;
 }
+template <class F> static void dispatch_cw(int cw, F &&f)
+{
+    if (cw <= 1) f(std::integral_constant<int, 1>{});
+    else if (cw == 2) f(std::integral_constant<int, 2>{});
+    else if (cw <= 4) f(std::integral_constant<int, 4>{});
+    else f(std::integral_constant<int, 8>{});
+}
 cudaError_t preload_ring2()
 {
     cudaError_t e = cudaSuccess;
     for (int kind = 0; kind < K_COUNT; kind++)
         dispatch_kind(kind, [&](auto wv) {
             using WV = decltype(wv);
-            using C = R2<typename WV::T>;
-            if (e == cudaSuccess) e = prep2(k_fwd_ring2<WV>, C::SMEM);
-            if constexpr (!WV::INV_COLS_FIRST) {
-                if (e == cudaSuccess) e = prep2(k_inv_ring2<WV>, C::SMEM);
+            if constexpr (sizeof(typename WV::T) == 4) {   // the kinds ring2_width_ok admits
+                for (int cw = 1; cw <= 8; cw *= 2)
+                    dispatch_cw(cw, [&](auto c) {
+                        constexpr int CW = decltype(c)::value;
+                        using C = R2<typename WV::T, CW>;
+                        if (e == cudaSuccess) e = prep2(k_fwd_ring2<WV, CW>, C::SMEM);
+                        if constexpr (!WV::INV_COLS_FIRST) {
+                            if (e == cudaSuccess) e = prep2(k_inv_ring2<WV, CW>, C::SMEM);
+                        }
+                    });
             }
         });
     return e;
@@ -572,22 +588,33 @@ bool ring2_inverse_ok(int kind) { return !(kind == K_CDF53_I32 || kind == K_CDF9
 bool ring2_width_ok(int kind, int W) { return kind_elem_size(kind) == 4 && W % ring2_out_width(kind) == 0; }
 int ring2_out_width(int kind) { return 32 * (32 / kind_elem_size(kind)); }
 
-void launch_fwd_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st)
+void launch_fwd_ring2(int kind, const LevelParams &p, int frames, int cw, cudaStream_t st)
 {
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
-        using C = R2<typename WV::T>;
-        launch_pdl(k_fwd_ring2<WV>, dim3(p.nbands * p.nstrips, frames), dim3(C::THREADS), (size_t)C::SMEM, st, p.chain.pdl, p);
+        if constexpr (sizeof(typename WV::T) == 4)
+            dispatch_cw(cw, [&](auto c) {
+                constexpr int CW = decltype(c)::value;
+                using C = R2<typename WV::T, CW>;
+                launch_pdl(k_fwd_ring2<WV, CW>, dim3(p.nbands * p.nstrips, frames), dim3(C::THREADS), (size_t)C::SMEM, st, p.chain.pdl, p);
+            });
     });
 }
-void launch_inv_ring2(int kind, const LevelParams &p, int frames, cudaStream_t st)
+void launch_inv_ring2(int kind, const LevelParams &p, int frames, int cw, cudaStream_t st)
 {
     dispatch_kind(kind, [&](auto wv) {
         using WV = decltype(wv);
-        using C = R2<typename WV::T>;
-        if constexpr (!WV::INV_COLS_FIRST)
-            launch_pdl(k_inv_ring2<WV>, dim3(p.nbands * p.nstrips, frames), dim3(C::THREADS), (size_t)C::SMEM, st, p.chain.pdl, p);
+        if constexpr (sizeof(typename WV::T) == 4 && !WV::INV_COLS_FIRST)
+            dispatch_cw(cw, [&](auto c) {
+                constexpr int CW = decltype(c)::value;
+                using C = R2<typename WV::T, CW>;
+                launch_pdl(k_inv_ring2<WV, CW>, dim3(p.nbands * p.nstrips, frames), dim3(C::THREADS), (size_t)C::SMEM, st, p.chain.pdl, p);
+            });
     });
 }
+// the CTA shapes of this generation as ring cfg numbers: RING_CFG_V2 (8 warps) and RING_CFG_V2 + 2, + 3, + 4 (4, 2, 1 warps)
+int ring2_cfg_for(int ncg) { return ncg >= 5 ? RING_CFG_V2 : ncg >= 3 ? RING_CFG_V2 + 2 : ncg == 2 ? RING_CFG_V2 + 3 : RING_CFG_V2 + 4; }
+int ring2_cfg_warps(int cfg) { return cfg == RING_CFG_V2 ? 8 : cfg == RING_CFG_V2 + 2 ? 4 : cfg == RING_CFG_V2 + 3 ? 2 : 1; }
+bool ring2_cfg(int cfg) { return cfg == RING_CFG_V2 || (cfg >= RING_CFG_V2 + 2 && cfg <= RING_CFG_V2 + 4); }
 
 }  // namespace dwtb200
