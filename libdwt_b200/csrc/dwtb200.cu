@@ -81,7 +81,7 @@ struct Ctx {
     int ring = 3;       // bit 0 / 1: forward / inverse streaming levels take the bulk-copy ring kernels (kernels_ring.cu)
     int ring_v2 = 1;    // the ring levels take the 256-column kernels (kernels_ring2.cu) where they apply; scoped off for the interleaved layout
     int ring_waves = 3, ring_pps_min = 0, ring_pps_max = 0;   // strip-length search range of the ring kernels (0: defaults)
-    int vol3 = 1;       // forward 3-D: one pass over the volume where the tile kernel applies (kernels_vol.cu, k_vol3_fwd)
+    int vol3 = 1;       // 3-D: one pass over the volume where the tile kernel applies (kernels_vol.cu: 1 = k_vol3t, 2 = k_vol3, 0 = two passes)
     int chain = 1;      // kernels of a pyramid overlap through completion counters (struct Chain): bit 0 ring levels, bit 1 tile / tail
     int epoch = 0;   // bumped by every tuning change: part of the graph cache key
 } g;
@@ -435,7 +435,7 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
     case DWTB200_TUNE_PYR: break;   // the fused tile-pyramid kernels were removed in round 2 (never faster than one tile launch per level)
-    case DWTB200_TUNE_VOL3: g.vol3 = value != 0; break;
+    case DWTB200_TUNE_VOL3: g.vol3 = value < 0 || value > 2 ? 1 : value; break;
 #ifdef DWTB200_DEBUG_KEYS   // measurement-only knobs (profiles/scripts): not part of the release ABI
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;
@@ -2372,7 +2372,7 @@ static int volume_axes(dwtb200_volume *v, int inverse)
         p.src = v->buf[v->cur];
         p.dst = v->buf[v->cur ^ 1];
         if (g.vol3 && vol3_applies(p)) {   // all three axes in one pass: buf[cur] -> buf[cur^1]
-            launch_vol3(p, inverse, g.sm_count, g.st);
+            launch_vol3(p, inverse, g.vol3, g.sm_count, g.st);
             v->cur ^= 1;
             CK(cudaGetLastError());
             return DWTB200_OK;

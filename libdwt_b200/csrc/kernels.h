@@ -189,7 +189,8 @@ void launch_vol_xy(VolParams p, int inverse, int sm_count, cudaStream_t st);
 void launch_vol_z(VolParams p, int inverse, int sm_count, cudaStream_t st);
 // all three axes in ONE pass over the volume (tiles of 64 x 32 positions marching along z); volumes it applies to
 bool vol3_applies(const VolParams &p);
-void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st);
+// variant 1: tile staged by one tensor copy per slice (k_vol3t); 2: by cp.async (k_vol3, also the fallback without a tensor map)
+void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream_t st);
 
 struct Axis3Params {
     const float *src;

@@ -13,6 +13,9 @@
 //   k_vol3     volumes of at least 64 x 32 x 16: all three axes in ONE pass (tiles marching along z, see below)
 // Two passes over the volume (4*S bytes) instead of three; both directions apply x, then y, then z like
 // the reference (the inverse is NOT the mirrored order there either), so results are bit-identical.
+#include <cuda.h>
+
+#include "ring_common.cuh"
 #include "stream_common.cuh"
 
 namespace dwtb200 {
@@ -387,11 +390,217 @@ template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol
     }
 }
 
+
+// =====================================================================================================
+// the same pass with the tile staged by the tensor-copy engine (round 2)
+// =====================================================================================================
+// k_vol3 spends about a fifth of its instructions on staging (720 cp.async of 16 bytes per slice and CTA, their addresses and
+// mirror tests).  Here ONE thread issues ONE cp.async.bulk.tensor per slice: a 76 x 40 x 1 box of a 3-D tensor map over the
+// source volume (coordinates may leave the volume: the engine fills zeros there), completion counted on an mbarrier.  CTAs
+// whose staged window leaves the volume replace the zeros by the mirrored samples (<= 4 shared-memory moves per thread and
+// slice, listed once).  The x pass of slice i and the y pass of slice i - 1 share a phase (the x-lifted buffer is double
+// buffered), so a slice costs one __syncthreads instead of two and every warp has work in every phase.
+constexpr int V3T_BW = V3_SW + 4;                         // box width: 76 columns, so that the staged pitch keeps 16-byte row accesses conflict-free
+constexpr int V3T_STAGE = V3_SH * V3T_BW;                 // floats per staged slice (12160 bytes, a multiple of 128)
+constexpr int V3T_XB = V3_SH * V3_XP;                     // floats per x-lifted buffer
+constexpr int V3T_SMEM = (V3_NBUF * V3T_STAGE + 2 * V3T_XB) * (int)sizeof(float) + 64;
+constexpr int V3T_NFIX = 4;                               // (4 + 4) x 40 + (4 + 4) x 72 = 896 halo positions for 256 threads
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
+template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3t(const VolParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) float v3_smem[];
+    float *stage = v3_smem, *xb = v3_smem + V3_NBUF * V3T_STAGE;
+    const uint32_t bars = smem_u32(xb + 2 * V3T_XB);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * V3_TX, y0 = blockIdx.y * V3_TY;
+    const int nx = p.nx, ny = p.ny, N = p.nz;
+
+    constexpr int WARM = INV ? 4 : 3, DELAY = 1;
+    const int units = INV ? (N >> 1) + 1 : (N + 1) >> 1;
+    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, units);
+    if (k0 >= k1) return;
+    const int m0 = k0 + DELAY - WARM, m1 = k1 - 1 + DELAY;
+    const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + (INV ? 0 : 1);
+
+    if (tid == 0) {
+        for (int b = 0; b < V3_NBUF; b++) mbar_init(bars + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // halo positions of the staged window that lie outside the volume, and the staged position of their mirror image
+    const bool edge = x0 < V3_HALO || x0 + V3_TX + V3_HALO > nx || y0 < V3_HALO || y0 + V3_TY + V3_HALO > ny;
+    int fix[V3T_NFIX];
+#pragma unroll
+    for (int k = 0; k < V3T_NFIX; k++) {
+        fix[k] = -1;
+        if (!edge) continue;
+        int id = tid + k * V3_THREADS, r, c;
+        if (id < 8 * V3_SH) {   // four columns left of the volume, four right of it
+            r = id % V3_SH;
+            const int s = id / V3_SH;
+            c = s < 4 ? s : nx - (x0 - V3_HALO) + (s - 4);
+        } else {
+            id -= 8 * V3_SH;
+            if (id >= 8 * V3_SW) continue;
+            c = id % V3_SW;
+            const int s = id / V3_SW;
+            r = s < 4 ? s : ny - (y0 - V3_HALO) + (s - 4);
+        }
+        if (r < 0 || r >= V3_SH || c < 0 || c >= V3_SW) continue;
+        const int gx = x0 - V3_HALO + c, gy = y0 - V3_HALO + r;
+        if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) continue;
+        const int sc = reflect(gx, nx) - (x0 - V3_HALO), sr = reflect(gy, ny) - (y0 - V3_HALO);
+        if (sc < 0 || sc >= V3_SW || sr < 0 || sr >= V3_SH) continue;
+        fix[k] = (r * V3T_BW + c) << 16 | (sr * V3T_BW + sc);
+    }
+    __syncthreads();
+    auto issue = [&](int i) {
+        if (tid == 0 && i < nsl) {
+            const int b = i % V3_NBUF;
+            mbar_expect_tx(bars + 8 * b, V3T_STAGE * (uint32_t)sizeof(float));
+            tma_load_3d(smem_u32(stage + b * V3T_STAGE), &tmap, x0 - V3_HALO, y0 - V3_HALO, reflect(zfirst + i, N), bars + 8 * b);
+        }
+    };
+
+    const int px = tid % V3_TX, ps = tid / V3_TX;
+    T st[WV::NS][8];
+#pragma unroll
+    for (int s = 0; s < WV::NS; s++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[s][i] = 0.f;
+    const int rows_ok = (x0 + px < nx) ? min(max(ny - (y0 + 8 * ps), 0), 8) : 0;
+    float *out = p.dst + (int64_t)(y0 + 8 * ps) * p.d_pitch + x0 + px;
+    const int dp = (int)p.d_pitch;
+    auto put = [&](int z, const T(&o)[8]) {
+        if (z < 0 || z >= N) return;
+        float *q = out + (int64_t)z * p.d_slice;
+        if (rows_ok == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) q[j * dp] = o[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < rows_ok) q[j * dp] = o[j];
+        }
+    };
+    const int xr = tid % V3_SH, xsg = tid / V3_SH;
+    // phase i: x lifting of slice i (if there is one) into xb[i & 1], y lifting of slice i - 1 from xb[(i - 1) & 1] into v
+    auto phase = [&](int i, T(&v)[8], bool have_y) {
+        issue(i + 2);   // into the buffer slice i - 1 was read from (every thread is past the barrier of phase i - 1)
+        if (i < nsl) {
+            float *buf = stage + (i % V3_NBUF) * V3T_STAGE;
+            mbar_wait(bars + 8 * (i % V3_NBUF), (uint32_t)(i / V3_NBUF) & 1u);
+            if (edge) {
+#pragma unroll
+                for (int k = 0; k < V3T_NFIX; k++)
+                    if (fix[k] >= 0) buf[fix[k] >> 16] = buf[fix[k] & 0xffff];
+                __syncthreads();
+            }
+            if (xsg < V3_TX / 16) {
+                T w[24], L[8], H[8];
+                const float4 *src4 = reinterpret_cast<const float4 *>(buf + xr * V3T_BW + 16 * xsg);
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const float4 q4 = src4[j];
+                    w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
+                }
+                if constexpr (INV) window_inv_p<WV, 8>(w, L, H);
+                else window_fwd_p<WV, 8>(w, L, H);
+                float4 *dst4 = reinterpret_cast<float4 *>(xb + (i & 1) * V3T_XB + xr * V3_XP + 16 * xsg);
+#pragma unroll
+                for (int j = 0; j < 4; j++) dst4[j] = make_float4(L[2 * j], H[2 * j], L[2 * j + 1], H[2 * j + 1]);
+            }
+        }
+        if (have_y) {
+            T w[16], L[4], H[4];
+            const float *col = xb + ((i - 1) & 1) * V3T_XB + (8 * ps) * V3_XP + px;
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j] = col[j * V3_XP];
+            if constexpr (INV) window_inv_p<WV, 4>(w, L, H);
+            else window_fwd_p<WV, 4>(w, L, H);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[2 * j] = L[j];
+                v[2 * j + 1] = H[j];
+            }
+        }
+        if (edge) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the mirror writes, before the engine refills the buffer
+        __syncthreads();
+    };
+
+    issue(0);
+    issue(1);
+    {
+        T none[8];
+        phase(0, none, false);
+    }
+    if constexpr (!INV) {
+        phase(1, st[0], true);   // slice 0 of the sequence seeds the z pipeline, then pairs (2q+1, 2q+2)
+        for (int q = 0; q < npairs; q++) {
+            T a[8], b[8], oL[8], oH[8];
+            phase(2 * q + 2, a, true);
+            phase(2 * q + 3, b, true);
+            vfwd<WV, 8>(a, b, st, oL, oH);
+            const int kk = m0 + q - DELAY;
+            if (kk >= k0) {
+                put(2 * kk, oL);
+                put(2 * kk + 1, oH);
+            }
+        }
+    } else {
+        for (int q = 0; q < npairs; q++) {
+            T a[8], b[8], oO[8], oE[8];
+            phase(2 * q + 1, a, true);
+            phase(2 * q + 2, b, true);
+            vinv<WV, 8>(a, b, st, oO, oE);
+            const int kk = m0 + q - DELAY;
+            if (kk >= k0) {
+                put(2 * kk - 1, oO);
+                put(2 * kk, oE);
+            }
+        }
+    }
+}
+
+// tensor map over the source volume (driver entry point fetched through the runtime: no link against libcuda)
+static bool vol3_tensor_map(const VolParams &p, CUtensorMap *map)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    if ((reinterpret_cast<uintptr_t>(p.src) & 15) || (p.s_pitch & 3) || (p.s_slice & 3)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.nx, (cuuint64_t)p.ny, (cuuint64_t)p.nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.s_pitch * sizeof(float), (cuuint64_t)p.s_slice * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)V3T_BW, (cuuint32_t)V3_SH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p.src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }   // at least one full tile
-void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st)
+void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream_t st)
 {
     static bool prepared = false;
     if (!prepared) {
+        cudaFuncSetAttribute(k_vol3t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
         cudaFuncSetAttribute(k_vol3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         cudaFuncSetAttribute(k_vol3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         prepared = true;
@@ -420,6 +629,12 @@ void launch_vol3(VolParams p, int inverse, int sm_count, cudaStream_t st)
     p.pps = (units + best - 1) / best;
     p.nstrips = (units + p.pps - 1) / p.pps;
     const dim3 grid(tx, ty, p.nstrips);
+    CUtensorMap map;
+    if (variant != 2 && vol3_tensor_map(p, &map)) {   // variant 2 (DWTB200_TUNE_VOL3 = 2): the cp.async staging of round 1
+        if (inverse) k_vol3t<true><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        else k_vol3t<false><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        return;
+    }
     if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
     else k_vol3<false><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
 }

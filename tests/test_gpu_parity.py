@@ -467,15 +467,15 @@ def test_volume_parity(dev, oracle, shape):
 @pytest.mark.parametrize("shape", [(128, 32, 16), (129, 33, 17), (300, 100, 31), (520, 300, 70), (1000, 64, 40), (131, 200, 130)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_volume_single_pass(dev, oracle, shape):
-    """k_vol3 (x, y and z lifting in ONE pass: tiles of 128 x 32 positions marching along z) on seeded noise against the
-    oracle, and the two-pass kernels (DWTB200_TUNE_VOL3 = 0) must give the same bits"""
+    """the one-pass kernels (x, y and z lifting in ONE pass: tiles of 64 x 32 positions marching along z; DWTB200_TUNE_VOL3 = 1 staged by
+    tensor copies, 2 by cp.async) on seeded noise against the oracle, and the two-pass kernels (0) must give the same bits"""
     nx, ny, nz = shape
     rng = np.random.default_rng(nx * 7 + nz)
     a = (rng.standard_normal((nz, ny, nx)) * 10.0 ** rng.integers(-2, 3, size=(nz, ny, nx))).astype(np.float32)
     want = np.zeros_like(a)
     oracle.fwd3(a, want)
     L = dev.lib()
-    for vol3 in (1, 0):
+    for vol3 in (1, 2, 0):
         L.check(L.c.dwtb200_set_tuning(9, vol3))
         try:
             got = np.zeros_like(a)
@@ -488,7 +488,7 @@ def test_volume_single_pass(dev, oracle, shape):
     c = (rng.standard_normal((nz, ny, nx)) * 10.0 ** rng.integers(-2, 3, size=(nz, ny, nx))).astype(np.float32)
     want = c.copy()
     oracle.inv3(want)
-    for vol3 in (1, 0):
+    for vol3 in (1, 2, 0):
         L.check(L.c.dwtb200_set_tuning(9, vol3))
         try:
             got = c.copy()
