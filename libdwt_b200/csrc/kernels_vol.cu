@@ -413,7 +413,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  : "memory");
 }
 
-template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol3t(const VolParams p, const __grid_constant__ CUtensorMap tmap)
+template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA) k_vol3t(const VolParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) float v3_smem[];
     float *stage = v3_smem, *xb = v3_smem + V3_NBUF * V3T_STAGE;
@@ -590,6 +590,7 @@ static bool vol3_tensor_map(const VolParams &p, CUtensorMap *map)
     const cuuint64_t strides[2] = {(cuuint64_t)p.s_pitch * sizeof(float), (cuuint64_t)p.s_slice * sizeof(float)};
     const cuuint32_t box[3] = {(cuuint32_t)V3T_BW, (cuuint32_t)V3_SH, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
+    // L2 promotion none / 64 / 128 / 256 bytes: no measurable difference (1024^3 forward 1.819 - 1.822 ms)
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p.src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -599,14 +600,21 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
 {
     static bool prepared = false;
     if (!prepared) {
-        cudaFuncSetAttribute(k_vol3t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
-        cudaFuncSetAttribute(k_vol3t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
+        cudaFuncSetAttribute(k_vol3t<false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_vol3t<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_vol3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         cudaFuncSetAttribute(k_vol3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         prepared = true;
     }
     const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
     const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
+    // CTAs per SM of the tensor-copy kernels: the inverse fits three (80 registers), the forward spills there (1024^3: inverse 1.91 -> 1.85 ms,
+    // forward 1.82 -> 1.99 ms); variant 3 forces three, 4 two
+    const int ncta = variant == 2 ? V3_NCTA : variant == 3 ? 3 : variant == 4 ? 2 : inverse ? 3 : 2;
     const double warm = inverse ? 4.0 : 3.0;
     // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
     int best = 1;
@@ -615,7 +623,7 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
         const int pps = (units + zs - 1) / zs;
         if (zs > 1 && pps < 24) break;
         const int64_t n = (int64_t)tx * ty * ((units + pps - 1) / pps);
-        const int64_t slots = (int64_t)sm_count * V3_NCTA, waves = (n + slots - 1) / slots;
+        const int64_t slots = (int64_t)sm_count * ncta, waves = (n + slots - 1) / slots;
         // the CTAs of one wave start together and stay in phase, so the two CTAs of an SM sit in the same (x / y / z) phase at the
         // same time; several waves of shorter ranges drift apart and overlap each other's phases (measured: 768^3 in one wave of
         // 288 CTAs 1.50 ms, 1024^3 in seven waves at the same per-voxel cost 2.54 ms;
@@ -631,8 +639,13 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
     const dim3 grid(tx, ty, p.nstrips);
     CUtensorMap map;
     if (variant != 2 && vol3_tensor_map(p, &map)) {   // variant 2 (DWTB200_TUNE_VOL3 = 2): the cp.async staging of round 1
-        if (inverse) k_vol3t<true><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
-        else k_vol3t<false><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        if (ncta == 3) {
+            if (inverse) k_vol3t<true, 3><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+            else k_vol3t<false, 3><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        } else {
+            if (inverse) k_vol3t<true, 2><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+            else k_vol3t<false, 2><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        }
         return;
     }
     if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
