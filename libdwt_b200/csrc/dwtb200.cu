@@ -1873,6 +1873,42 @@ struct Pipe {
     }
 } g_pipe;
 
+// DWTB200_PIPE_TRACE=1: time stamps (ms after the call's start) of every stage of the pipelined host path, on stderr
+struct PipeTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Stamp { const char *what; int chunk; cudaEvent_t e; };
+    std::vector<Stamp> stamps;
+    void begin(cudaStream_t st)
+    {
+        static const bool want = getenv("DWTB200_PIPE_TRACE") && atoi(getenv("DWTB200_PIPE_TRACE")) != 0;
+        on = want;
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, st);
+    }
+    void mark(const char *what, int chunk, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        stamps.push_back({what, chunk, e});
+    }
+    void end()
+    {
+        if (!on) return;
+        for (const Stamp &s : stamps) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t0, s.e);
+            fprintf(stderr, "pipe %-8s %2d %8.3f ms\n", s.what, s.chunk, ms);
+            cudaEventDestroy(s.e);
+        }
+        cudaEventDestroy(t0);
+        stamps.clear();
+    }
+};
+
 bool pipeline_applies(const dwtb200_image *im, int64_t sx, int64_t sy, int ix, int iy, int J, DensePlan &pl)
 {
     if (!g.pipeline || g.force_generic || im->frames != 1 || sy != (int64_t)im->es || ix != im->ox || iy != im->oy || J < 2) return false;
@@ -1916,6 +1952,8 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
     CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(2 * nch), 0));
     CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(2 * nch), 0));
     CK(cudaEventRecord(g_t0, g.st));
+    PipeTrace tr;
+    tr.begin(g.st);
 
     if (!inverse) {
         std::vector<int> up_hi(nch);   // host rows < up_hi[c] have been uploaded once chunk c's upload is done
@@ -1927,6 +1965,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             row = std::max(row, r1);
             up_hi[c] = row;
             CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+            tr.mark("up", c, g_pipe.up);
         }
         for (int c = 0; c < nch; c++) {
             const int k0 = s_lo[c] * pps, k1 = std::min(s_lo[c + 1] * pps, nLy), kh = std::min(k1, nHy);
@@ -1936,8 +1975,10 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             q.nstrips = s_lo[c + 1] - s_lo[c];
             stream_fwd(im->kind, q, 1, g.st);
             CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            tr.mark("kernel", c, g.st);
             CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
             CK(d2h(k0, k1, nLx, W, dst_plane));   // HL rows: these host rows were uploaded before the kernel ran
+            tr.mark("dn-HL", c, g_pipe.dn);
             // LH | HH rows land in host rows [nLy + k0, nLy + kh): wait until those were uploaded -- on a stream of their
             // own, so that the HL rows of the following ranges do not queue up behind that wait.  (Measured and dropped:
             // pipelining level 1 behind level 0, and walking the ranges bottom-up so that LH | HH never wait; the D2H
@@ -1947,6 +1988,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(nch + c), 0));
             if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(cu), 0));
             CK(d2h(nLy + k0, nLy + kh, 0, W, dst_plane, g_pipe.dn2));
+            tr.mark("dn-LHHH", c, g_pipe.dn2);
         }
         {   // levels 1 .. J-1 on the LL band (stream order after the last range)
             const int rr = run_dense_uncaptured(im, false, J, pl, 1);
@@ -1954,8 +1996,10 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(g_t1, g.st));
+        tr.mark("levels", 0, g.st);
         CK(cudaStreamWaitEvent(g_pipe.dn, g_t1, 0));
         CK(d2h(0, nLy, 0, nLx, dst_plane));
+        tr.mark("dn-LL", 0, g_pipe.dn);
     } else {
         // LL quadrant first, inverted down to level 1
         CK(h2d(0, nLy, 0, nLx, src_plane));
@@ -1981,6 +2025,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             hl_hi[c] = a0;
             hh_hi[c] = b0;
             CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+            tr.mark("up", c, g_pipe.up);
         }
         for (int c = 0; c < nch; c++) {
             const int q0 = s_lo[c] * pps, q1 = std::min(s_lo[c + 1] * pps, units);
@@ -1990,6 +2035,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             q.nstrips = s_lo[c + 1] - s_lo[c];
             stream_inv(im->kind, q, 1, g.st);
             CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            tr.mark("kernel", c, g.st);
             CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
             const int r0 = std::max(0, 2 * q0 - 1), r1 = std::min(H, 2 * q1 - 1);   // rows this range reconstructs
             // host row r still holds coefficients: HL row r (r < nLy) or LH|HH row r - nLy; overwrite only once uploaded
@@ -1997,6 +2043,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
             while (cu < nch - 1 && (hl_hi[cu] < std::min(r1, nLy) || hh_hi[cu] < std::min(std::max(0, r1 - nLy), nHy))) cu++;
             if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(cu), 0));
             CK(d2h(r0, r1, 0, W, dst_plane));
+            tr.mark("dn", c, g_pipe.dn);
         }
         CK(cudaEventRecord(g_t1, g.st));
     }
@@ -2005,6 +2052,7 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
     CK(cudaStreamSynchronize(g_pipe.up));
     CK(cudaStreamSynchronize(g.st));
     CK(cudaGetLastError());
+    tr.end();
     CK(cudaEventElapsedTime(&g_last_ms, g_t0, g_t1));
     im->cur ^= 1;
     im->last_path = 0;
