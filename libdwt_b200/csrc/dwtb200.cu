@@ -1854,13 +1854,13 @@ dwtb200_image *host_image(int kind, int ox, int oy)
 // A synchronous in-place call on host memory is PCIe-bound (2 x 256 MiB for an 8192^2 float image against
 // ~0.2 ms of kernels), so the large dense case overlaps the two directions of the link: level 0 is run strip
 // range by strip range while the image is still arriving, and each range's finished rows go back while the
-// next range is uploaded.  Forward: the H subbands of level 0 (3/4 of the output) leave early, then levels
-// 1..J run on the LL band and its quadrant follows.  Inverse: the LL quadrant goes first and is inverted down
+// next range is uploaded.  Forward: the H subbands of level 0 (3/4 of the output) and of level 1 (3/16) leave early, then
+// levels 2..J run on the LL band of level 1 and its quadrant follows.  Inverse: the LL quadrant goes first and is inverted down
 // to level 1, then the level-0 subbands arrive range by range and the reconstructed rows leave.  The call is
 // in place on the caller's buffer, so a download may only overwrite host rows whose old content has already
 // been uploaded; the waits below encode exactly that.
 struct Pipe {
-    cudaStream_t up = nullptr, dn = nullptr, dn2 = nullptr;
+    cudaStream_t up = nullptr, dn = nullptr, dn2 = nullptr, dn3 = nullptr;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t get(size_t i)
     {
@@ -1923,132 +1923,168 @@ int host_pipelined(bool inverse, dwtb200_image *im, char *host, int64_t sx, int 
         CK(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&g_pipe.dn, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&g_pipe.dn2, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_pipe.dn3, cudaStreamNonBlocking));
     }
     const size_t es = im->es;
     const int W = im->ox, H = im->oy;
     const int nLx = (W + 1) >> 1, nLy = (H + 1) >> 1, nHy = H >> 1;
+    const int nLx1 = (nLx + 1) >> 1, nLy1 = (nLy + 1) >> 1, nHy1 = nLy >> 1;   // level 1 works on the nLx x nLy LL band
     char *src_plane = (char *)im->plane[im->cur], *dst_plane = (char *)im->plane[im->cur ^ 1];
     const size_t dpitch = (size_t)im->pitch * es;
-    LevelParams lp;
+    LevelParams lp, lp1;
+    memset(&lp1, 0, sizeof lp1);
     if (inverse) inv_level_params(im, 0, J, src_plane, dst_plane, lp);
     else fwd_level_params(im, 0, J, Band{src_plane, im->pitch, im->frame}, dst_plane, lp);
+    // forward: level 1 is pipelined behind level 0 when it is a streaming level with levels beyond it, so that three quarters of the LL
+    // quadrant leave while the image is still arriving (8192^2 float: 7.70 -> 7.35 ms).  The inverse keeps level 1 with the rest of
+    // the pyramid: with level 1 in front of level 0 range by range the first rows leave after 0.8 instead of 1.6 ms, but every
+    // reconstructed row overwrites coefficients of both levels, the uploads have to run further ahead and the call takes 7.6
+    // instead of 7.35 ms (profiles/pipe_trace_r2.txt)
+    const bool two = !inverse && J >= 3 && pl.jt >= 2 && pl.type[1] == PLAN_STREAM;
+    if (two) fwd_level_params(im, 1, J, ll_band(im, 0), dst_plane, lp1);
     const int nstrips = lp.nstrips, pps = lp.pps;
+    const int nstrips1 = two ? lp1.nstrips : 0, pps1 = two ? lp1.pps : 1;
     const int nch = nstrips < 16 ? nstrips : 16;
-    auto h2d = [&](int r0, int r1, int c0, int c1, char *plane) -> cudaError_t {   // rows [r0,r1) x columns [c0,c1)
-        if (r1 <= r0 || c1 <= c0) return cudaSuccess;
-        return cudaMemcpy2DAsync(plane + (size_t)r0 * dpitch + (size_t)c0 * es, dpitch, host + (size_t)r0 * sx + (size_t)c0 * es, (size_t)sx,
-                                 (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, g_pipe.up);
+    // events: [0, nch) level kernels of chunk c done; nch: previous work on g.st done; nch + 1 + i: upload piece i done
+    const size_t EV_PREV = (size_t)nch, EV_UP = (size_t)nch + 1;
+    struct Piece {
+        int r0, r1, c0, c1;
     };
-    auto d2h = [&](int r0, int r1, int c0, int c1, char *plane, cudaStream_t on = nullptr) -> cudaError_t {
+    std::vector<Piece> pieces;   // host rectangles in upload order (rows, columns in elements)
+    auto upload = [&](int r0, int r1, int c0, int c1, char *plane) -> cudaError_t {   // rows [r0,r1) x columns [c0,c1)
         if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+        const cudaError_t e = cudaMemcpy2DAsync(plane + (size_t)r0 * dpitch + (size_t)c0 * es, dpitch, host + (size_t)r0 * sx + (size_t)c0 * es, (size_t)sx,
+                                                (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, g_pipe.up);
+        if (e != cudaSuccess) return e;
+        pieces.push_back(Piece{r0, r1, c0, c1});
+        return cudaEventRecord(g_pipe.get(EV_UP + pieces.size() - 1), g_pipe.up);
+    };
+    // the call is in place: a download may only overwrite host memory whose old content has been uploaded.  Index of the last upload
+    // piece that overlaps the rectangle (-1: none); uploads are one stream, so waiting for that piece's event covers the earlier ones
+    auto landing = [&](int r0, int r1, int c0, int c1) -> int {
+        for (int i = (int)pieces.size() - 1; i >= 0; i--)
+            if (pieces[i].r0 < r1 && r0 < pieces[i].r1 && pieces[i].c0 < c1 && c0 < pieces[i].c1) return i;
+        return -1;
+    };
+    // download of rows [r0,r1) x columns [c0,c1) on stream `on`, after the kernels of chunk c and the uploads it would overwrite
+    auto download = [&](int c, int r0, int r1, int c0, int c1, char *plane, cudaStream_t on, int have_piece) -> cudaError_t {
+        if (r1 <= r0 || c1 <= c0) return cudaSuccess;
+        cudaError_t e = cudaStreamWaitEvent(on, g_pipe.get((size_t)c), 0);
+        if (e != cudaSuccess) return e;
+        const int k = landing(r0, r1, c0, c1);
+        if (k > have_piece && (e = cudaStreamWaitEvent(on, g_pipe.get(EV_UP + (size_t)k), 0)) != cudaSuccess) return e;
         return cudaMemcpy2DAsync(host + (size_t)r0 * sx + (size_t)c0 * es, (size_t)sx, plane + (size_t)r0 * dpitch + (size_t)c0 * es, dpitch,
-                                 (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, on ? on : g_pipe.dn);
+                                 (size_t)(c1 - c0) * es, r1 - r0, cudaMemcpyDefault, on);
     };
-    std::vector<int> s_lo(nch + 1);
+    std::vector<int> s_lo(nch + 1), up_last(nch, -1);
     for (int c = 0; c <= nch; c++) s_lo[c] = (int)((int64_t)nstrips * c / nch);
-    // events: [0, nch) upload of chunk c done; [nch, 2 nch) kernel of chunk c done; 2 nch: previous work on g.st done
-    CK(cudaEventRecord(g_pipe.get(2 * nch), g.st));
-    CK(cudaStreamWaitEvent(g_pipe.up, g_pipe.get(2 * nch), 0));
-    CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(2 * nch), 0));
-    CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(2 * nch), 0));
+    CK(cudaEventRecord(g_pipe.get(EV_PREV), g.st));
+    CK(cudaStreamWaitEvent(g_pipe.up, g_pipe.get(EV_PREV), 0));
+    CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(EV_PREV), 0));
+    CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(EV_PREV), 0));
+    CK(cudaStreamWaitEvent(g_pipe.dn3, g_pipe.get(EV_PREV), 0));
     CK(cudaEventRecord(g_t0, g.st));
     PipeTrace tr;
     tr.begin(g.st);
+    auto range = [&](const LevelParams &of, int s0, int s1) {
+        LevelParams q = of;
+        q.strip0 = s0;
+        q.nstrips = s1 - s0;
+        if (inverse) stream_inv(im->kind, q, 1, g.st);
+        else stream_fwd(im->kind, q, 1, g.st);
+    };
 
     if (!inverse) {
-        std::vector<int> up_hi(nch);   // host rows < up_hi[c] have been uploaded once chunk c's upload is done
         int row = 0;
         for (int c = 0; c < nch; c++) {
             const int k1 = std::min(s_lo[c + 1] * pps, nLy);
             const int r1 = (c == nch - 1) ? H : std::min(H, 2 * k1 + 4);   // the range's kernel reads rows up to 2 k1 + 2
-            CK(h2d(row, r1, 0, W, src_plane));
+            CK(upload(row, r1, 0, W, src_plane));
             row = std::max(row, r1);
-            up_hi[c] = row;
-            CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+            up_last[c] = (int)pieces.size() - 1;
             tr.mark("up", c, g_pipe.up);
         }
+        int s1_done = 0;   // level-1 strips launched so far
         for (int c = 0; c < nch; c++) {
             const int k0 = s_lo[c] * pps, k1 = std::min(s_lo[c + 1] * pps, nLy), kh = std::min(k1, nHy);
-            CK(cudaStreamWaitEvent(g.st, g_pipe.get(c), 0));
-            LevelParams q = lp;
-            q.strip0 = s_lo[c];
-            q.nstrips = s_lo[c + 1] - s_lo[c];
-            stream_fwd(im->kind, q, 1, g.st);
-            CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            CK(cudaStreamWaitEvent(g.st, g_pipe.get(EV_UP + (size_t)up_last[c]), 0));
+            range(lp, s_lo[c], s_lo[c + 1]);
+            // level 1 on the LL rows that are complete now: a strip range [.., e) reads LL rows up to 2 e pps1 + 2
+            int s1_hi = s1_done;
+            if (two) {
+                if (c == nch - 1) s1_hi = nstrips1;
+                else
+                    while (s1_hi < nstrips1 && std::min(2 * (s1_hi + 1) * pps1 + 4, nLy) <= k1) s1_hi++;
+                if (s1_hi > s1_done) range(lp1, s1_done, s1_hi);
+            }
+            CK(cudaEventRecord(g_pipe.get((size_t)c), g.st));
             tr.mark("kernel", c, g.st);
-            CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
-            CK(d2h(k0, k1, nLx, W, dst_plane));   // HL rows: these host rows were uploaded before the kernel ran
+            CK(download(c, k0, k1, nLx, W, dst_plane, g_pipe.dn, up_last[c]));   // HL rows: these host rows were uploaded before the kernel ran
             tr.mark("dn-HL", c, g_pipe.dn);
-            // LH | HH rows land in host rows [nLy + k0, nLy + kh): wait until those were uploaded -- on a stream of their
-            // own, so that the HL rows of the following ranges do not queue up behind that wait.  (Measured and dropped:
-            // pipelining level 1 behind level 0, and walking the ranges bottom-up so that LH | HH never wait; the D2H
-            // engine, not the order, bounds this path: 7.6 ms for 2 x 256 MiB against 5.4 ms for the copies alone.)
-            int cu = c;
-            while (cu < nch - 1 && up_hi[cu] < nLy + kh) cu++;
-            CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(nch + c), 0));
-            if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn2, g_pipe.get(cu), 0));
-            CK(d2h(nLy + k0, nLy + kh, 0, W, dst_plane, g_pipe.dn2));
+            // LH | HH rows land in host rows [nLy + k0, nLy + kh): not before those were uploaded -- on a stream of their own, so that the
+            // rows of the following ranges that may land at once do not queue up behind that wait
+            CK(download(c, nLy + k0, nLy + kh, 0, W, dst_plane, g_pipe.dn2, up_last[c]));
             tr.mark("dn-LHHH", c, g_pipe.dn2);
+            if (s1_hi > s1_done) {   // the same for the level-1 subbands inside the LL quadrant
+                const int j0 = s1_done * pps1, j1 = std::min(s1_hi * pps1, nLy1), jh = std::min(j1, nHy1);
+                CK(download(c, j0, j1, nLx1, nLx, dst_plane, g_pipe.dn, up_last[c]));
+                CK(download(c, nLy1 + j0, nLy1 + jh, 0, nLx, dst_plane, g_pipe.dn3, up_last[c]));
+                tr.mark("dn-lvl1", c, g_pipe.dn3);
+                s1_done = s1_hi;
+            }
         }
-        {   // levels 1 .. J-1 on the LL band (stream order after the last range)
-            const int rr = run_dense_uncaptured(im, false, J, pl, 1);
+        {   // the levels behind the pipelined ones on their LL band (stream order after the last range)
+            const int rr = run_dense_uncaptured(im, false, J, pl, two ? 2 : 1);
             if (rr) return rr;
         }
         CK(cudaGetLastError());
         CK(cudaEventRecord(g_t1, g.st));
         tr.mark("levels", 0, g.st);
         CK(cudaStreamWaitEvent(g_pipe.dn, g_t1, 0));
-        CK(d2h(0, nLy, 0, nLx, dst_plane));
+        if (two) CK(cudaMemcpy2DAsync(host, (size_t)sx, dst_plane, dpitch, (size_t)nLx1 * es, nLy1, cudaMemcpyDefault, g_pipe.dn));
+        else CK(cudaMemcpy2DAsync(host, (size_t)sx, dst_plane, dpitch, (size_t)nLx * es, nLy, cudaMemcpyDefault, g_pipe.dn));
         tr.mark("dn-LL", 0, g_pipe.dn);
     } else {
-        // LL quadrant first, inverted down to level 1
-        CK(h2d(0, nLy, 0, nLx, src_plane));
-        CK(cudaEventRecord(g_pipe.get(2 * nch + 1), g_pipe.up));
-        CK(cudaStreamWaitEvent(g.st, g_pipe.get(2 * nch + 1), 0));
+        // the LL quadrant first, inverted down to level 1
+        CK(upload(0, nLy, 0, nLx, src_plane));
+        CK(cudaStreamWaitEvent(g.st, g_pipe.get(EV_UP), 0));
         {
             const int rr = run_dense_uncaptured(im, true, J, pl, 1);
             if (rr) return rr;
         }
         CK(cudaGetLastError());
         const int units = (H >> 1) + 1;
-        std::vector<int> hl_hi(nch), hh_hi(nch);   // HL rows < hl_hi[c] / LH|HH rows < hh_hi[c] uploaded after chunk c
-        int a0 = 0, b0 = 0;
+        // uploads of chunk c: the subband rows its kernel reads (< q1 + 2), and the coefficients its reconstructed rows [.., r1) will
+        // overwrite (host row r holds HL row r, or LH|HH row r - nLy) -- the HL rows therefore run ahead at twice the pace -- so that
+        // no download has to wait for a later chunk (8.35 -> 7.25 ms)
+        int hl0 = 0, hh0 = 0;
+        auto upto = [](int cur, int limit, int a, int b) { return std::max(cur, std::min(limit, std::max(a, b))); };
         for (int c = 0; c < nch; c++) {
-            const int q1 = std::min(s_lo[c + 1] * pps, units);
-            // HL rows run ahead at twice the pace: the rows a range reconstructs in the top half of the image overwrite HL
-            // rows up to 2 q1, and a download may only overwrite coefficients that have been uploaded (8.35 -> 7.25 ms)
-            const int a1 = (c == nch - 1) ? nLy : std::min(nLy, 2 * q1 + 2), b1 = (c == nch - 1) ? nHy : std::min(nHy, q1 + 2);
-            CK(h2d(a0, a1, nLx, W, src_plane));
-            CK(h2d(nLy + b0, nLy + b1, 0, W, src_plane));
-            a0 = std::max(a0, a1);
-            b0 = std::max(b0, b1);
-            hl_hi[c] = a0;
-            hh_hi[c] = b0;
-            CK(cudaEventRecord(g_pipe.get(c), g_pipe.up));
+            const bool last = c == nch - 1;
+            const int q1 = std::min(s_lo[c + 1] * pps, units), r1 = last ? H : std::min(H, 2 * q1 - 1);
+            const int a = last ? nLy : upto(hl0, nLy, q1 + 2, r1), b = last ? nHy : upto(hh0, nHy, q1 + 2, r1 - nLy);
+            CK(upload(hl0, a, nLx, W, src_plane));
+            CK(upload(nLy + hh0, nLy + b, 0, W, src_plane));
+            hl0 = a;
+            hh0 = b;
+            up_last[c] = (int)pieces.size() - 1;
             tr.mark("up", c, g_pipe.up);
         }
         for (int c = 0; c < nch; c++) {
             const int q0 = s_lo[c] * pps, q1 = std::min(s_lo[c + 1] * pps, units);
-            CK(cudaStreamWaitEvent(g.st, g_pipe.get(c), 0));
-            LevelParams q = lp;
-            q.strip0 = s_lo[c];
-            q.nstrips = s_lo[c + 1] - s_lo[c];
-            stream_inv(im->kind, q, 1, g.st);
-            CK(cudaEventRecord(g_pipe.get(nch + c), g.st));
+            CK(cudaStreamWaitEvent(g.st, g_pipe.get(EV_UP + (size_t)up_last[c]), 0));
+            range(lp, s_lo[c], s_lo[c + 1]);
+            CK(cudaEventRecord(g_pipe.get((size_t)c), g.st));
             tr.mark("kernel", c, g.st);
-            CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(nch + c), 0));
             const int r0 = std::max(0, 2 * q0 - 1), r1 = std::min(H, 2 * q1 - 1);   // rows this range reconstructs
-            // host row r still holds coefficients: HL row r (r < nLy) or LH|HH row r - nLy; overwrite only once uploaded
-            int cu = c;
-            while (cu < nch - 1 && (hl_hi[cu] < std::min(r1, nLy) || hh_hi[cu] < std::min(std::max(0, r1 - nLy), nHy))) cu++;
-            if (cu > c) CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(cu), 0));
-            CK(d2h(r0, r1, 0, W, dst_plane));
+            CK(download(c, r0, r1, 0, W, dst_plane, g_pipe.dn, up_last[c]));
             tr.mark("dn", c, g_pipe.dn);
         }
         CK(cudaEventRecord(g_t1, g.st));
     }
     CK(cudaStreamSynchronize(g_pipe.dn));
     CK(cudaStreamSynchronize(g_pipe.dn2));
+    CK(cudaStreamSynchronize(g_pipe.dn3));
     CK(cudaStreamSynchronize(g_pipe.up));
     CK(cudaStreamSynchronize(g.st));
     CK(cudaGetLastError());
@@ -2099,7 +2135,7 @@ void dwtb200_release_host_cache(void)
     // the pipelined host path's streams and events, and the transform timing events, go with the cache
     for (cudaEvent_t e : g_pipe.ev) cudaEventDestroy(e);
     g_pipe.ev.clear();
-    for (cudaStream_t *s : {&g_pipe.up, &g_pipe.dn, &g_pipe.dn2}) {
+    for (cudaStream_t *s : {&g_pipe.up, &g_pipe.dn, &g_pipe.dn2, &g_pipe.dn3}) {
         if (*s) cudaStreamDestroy(*s);
         *s = nullptr;
     }

@@ -536,7 +536,7 @@ def test_pipelined_host_path(dev, oracle, kind):
     shapes = [(4096, 4096), (3001, 2999), (7919, 6007), (4100, 2050)] if t != "d" else [(3001, 2999), (2200, 2100)]
     fails = []
     for (ox, oy) in shapes:
-        for j in (-1, 2):
+        for j in (-1, 2, 3):   # J >= 3: level 1 is pipelined with level 0
             fails += both(dev, oracle, w, t, ox, oy, j, 0)
             assert L.c.dwtb200_last_transform_ms() > 0
     fails += both(dev, oracle, w, t, 3001, 2999, -1, 0, row_bytes=3001 * es + 13)   # unaligned row stride
