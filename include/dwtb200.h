@@ -194,7 +194,7 @@ void dwtb200_set_strip_rows(int rows);
  *                          bits 4-6 force a CTA shape (0 = chosen per level: 7 consumer warps x 2 CTAs per SM, or 5 x 3 for
  *                          large batches of 2048-wide frames; 1 = 15 x 1, 2 = 8 x 2, 3 = 5 x 3, 5 = 7 x 2)
  *   DWTB200_TUNE_VOL3      1 (default): the 3-D transforms of volumes of at least 64 x 32 x 16 run in ONE pass over the volume, tiles staged by
- *                          tensor copies (k_vol3t; 3 / 4 force three / two CTAs per SM); 2: the same pass staged by cp.async (k_vol3);
+ *                          tensor copies (k_vol3t); 2: the same pass staged by cp.async (k_vol3, round 1);
  *                          0: always x + y per slice, then z (two passes)
  *   DWTB200_TUNE_PYR       accepted and ignored (the fused tile-pyramid kernels of round 1 were never faster and are gone)
  *   DWTB200_TUNE_CHAIN     1: the kernels of a pyramid are launched with programmatic stream serialization and wait for

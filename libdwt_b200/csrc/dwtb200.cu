@@ -435,7 +435,7 @@ int dwtb200_set_tuning(int key, long long value)
     case DWTB200_TUNE_RING: g.ring = (int)value; break;
     case DWTB200_TUNE_CHAIN: g.chain = (int)value; break;
     case DWTB200_TUNE_PYR: break;   // the fused tile-pyramid kernels were removed in round 2 (never faster than one tile launch per level)
-    case DWTB200_TUNE_VOL3: g.vol3 = value < 0 || value > 4 ? 1 : value; break;
+    case DWTB200_TUNE_VOL3: g.vol3 = value < 0 || value > 2 ? 1 : value; break;
 #ifdef DWTB200_DEBUG_KEYS   // measurement-only knobs (profiles/scripts): not part of the release ABI
     case 97: g.ring_waves = (int)(value & 0xff); g.ring_pps_min = (int)((value >> 8) & 0xff); g.ring_pps_max = (int)((value >> 16) & 0xfff); break;
     case 98: g.pfd = (int)value; break;

@@ -10,7 +10,8 @@
 //              -> blockIdx.y = z; subbands stay interleaved, so rows are stored where they were read
 //   k_vol_z    z lifting: a warp owns 32*VPL columns of one row y and streams through a strip of slice
 //              pairs with the same register pipeline (no horizontal dependency -> no halo lanes)
-//   k_vol3     volumes of at least 64 x 32 x 16: all three axes in ONE pass (tiles marching along z, see below)
+//   k_vol3t    volumes of at least 64 x 32 x 16: all three axes in ONE pass (tiles marching along z, staged by tensor copies;
+//              k_vol3 is the same pass staged by cp.async, kept as DWTB200_TUNE_VOL3 = 2 and as the fallback without a tensor map)
 // Two passes over the volume (4*S bytes) instead of three; both directions apply x, then y, then z like
 // the reference (the inverse is NOT the mirrored order there either), so results are bit-identical.
 #include <cuda.h>
@@ -399,11 +400,13 @@ template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol
 // source volume (coordinates may leave the volume: the engine fills zeros there), completion counted on an mbarrier.  CTAs
 // whose staged window leaves the volume replace the zeros by the mirrored samples (<= 4 shared-memory moves per thread and
 // slice, listed once).  The x pass of slice i and the y pass of slice i - 1 share a phase (the x-lifted buffer is double
-// buffered), so a slice costs one __syncthreads instead of two and every warp has work in every phase.
+// buffered), so a slice costs one __syncthreads instead of two and every warp has work in every phase.  NBUF staging
+// buffers: NBUF - 1 slices in flight.  1024^3: 2.53 -> 1.77 ms forward, 2.62 -> 1.83 ms inverse (60 -> 42 instructions per
+// voxel; profiles/ncu_vol3t_r2.txt).
 constexpr int V3T_BW = V3_SW + 4;                         // box width: 76 columns, so that the staged pitch keeps 16-byte row accesses conflict-free
 constexpr int V3T_STAGE = V3_SH * V3T_BW;                 // floats per staged slice (12160 bytes, a multiple of 128)
 constexpr int V3T_XB = V3_SH * V3_XP;                     // floats per x-lifted buffer
-constexpr int V3T_SMEM = (V3_NBUF * V3T_STAGE + 2 * V3T_XB) * (int)sizeof(float) + 64;
+constexpr int v3t_smem(int nbuf) { return (nbuf * V3T_STAGE + 2 * V3T_XB) * (int)sizeof(float) + 64; }
 constexpr int V3T_NFIX = 4;                               // (4 + 4) x 40 + (4 + 4) x 72 = 896 halo positions for 256 threads
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
@@ -413,10 +416,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  : "memory");
 }
 
-template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA) k_vol3t(const VolParams p, const __grid_constant__ CUtensorMap tmap)
+template <bool INV, int NCTA, int NBUF> __global__ void __launch_bounds__(V3_THREADS, NCTA) k_vol3t(const VolParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) float v3_smem[];
-    float *stage = v3_smem, *xb = v3_smem + V3_NBUF * V3T_STAGE;
+    float *stage = v3_smem, *xb = v3_smem + NBUF * V3T_STAGE;
     const uint32_t bars = smem_u32(xb + 2 * V3T_XB);
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * V3_TX, y0 = blockIdx.y * V3_TY;
@@ -430,7 +433,7 @@ template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA
     const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + (INV ? 0 : 1);
 
     if (tid == 0) {
-        for (int b = 0; b < V3_NBUF; b++) mbar_init(bars + 8 * b, 1);
+        for (int b = 0; b < NBUF; b++) mbar_init(bars + 8 * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // halo positions of the staged window that lie outside the volume, and the staged position of their mirror image
@@ -462,7 +465,7 @@ template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA
     __syncthreads();
     auto issue = [&](int i) {
         if (tid == 0 && i < nsl) {
-            const int b = i % V3_NBUF;
+            const int b = i % NBUF;
             mbar_expect_tx(bars + 8 * b, V3T_STAGE * (uint32_t)sizeof(float));
             tma_load_3d(smem_u32(stage + b * V3T_STAGE), &tmap, x0 - V3_HALO, y0 - V3_HALO, reflect(zfirst + i, N), bars + 8 * b);
         }
@@ -494,8 +497,8 @@ template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA
     auto phase = [&](int i, T(&v)[8], bool have_y) {
         issue(i + 2);   // into the buffer slice i - 1 was read from (every thread is past the barrier of phase i - 1)
         if (i < nsl) {
-            float *buf = stage + (i % V3_NBUF) * V3T_STAGE;
-            mbar_wait(bars + 8 * (i % V3_NBUF), (uint32_t)(i / V3_NBUF) & 1u);
+            float *buf = stage + (i % NBUF) * V3T_STAGE;
+            mbar_wait(bars + 8 * (i % NBUF), (uint32_t)(i / NBUF) & 1u);
             if (edge) {
 #pragma unroll
                 for (int k = 0; k < V3T_NFIX; k++)
@@ -542,6 +545,7 @@ template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA
     }
     if constexpr (!INV) {
         phase(1, st[0], true);   // slice 0 of the sequence seeds the z pipeline, then pairs (2q+1, 2q+2)
+#pragma unroll 2
         for (int q = 0; q < npairs; q++) {
             T a[8], b[8], oL[8], oH[8];
             phase(2 * q + 2, a, true);
@@ -554,6 +558,7 @@ template <bool INV, int NCTA> __global__ void __launch_bounds__(V3_THREADS, NCTA
             }
         }
     } else {
+#pragma unroll 2
         for (int q = 0; q < npairs; q++) {
             T a[8], b[8], oO[8], oE[8];
             phase(2 * q + 1, a, true);
@@ -600,21 +605,13 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
 {
     static bool prepared = false;
     if (!prepared) {
-        cudaFuncSetAttribute(k_vol3t<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
-        cudaFuncSetAttribute(k_vol3t<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
-        cudaFuncSetAttribute(k_vol3t<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
-        cudaFuncSetAttribute(k_vol3t<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3T_SMEM);
-        cudaFuncSetAttribute(k_vol3t<false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_vol3t<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_vol3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         cudaFuncSetAttribute(k_vol3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         prepared = true;
     }
     const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
     const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
-    // CTAs per SM of the tensor-copy kernels: the inverse fits three (80 registers), the forward spills there (1024^3: inverse 1.91 -> 1.85 ms,
-    // forward 1.82 -> 1.99 ms); variant 3 forces three, 4 two
-    const int ncta = variant == 2 ? V3_NCTA : variant == 3 ? 3 : variant == 4 ? 2 : inverse ? 3 : 2;
+    const int ncta = variant != 2 && inverse ? 3 : V3_NCTA;   // CTAs per SM (see below)
     const double warm = inverse ? 4.0 : 3.0;
     // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
     int best = 1;
@@ -639,13 +636,18 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
     const dim3 grid(tx, ty, p.nstrips);
     CUtensorMap map;
     if (variant != 2 && vol3_tensor_map(p, &map)) {   // variant 2 (DWTB200_TUNE_VOL3 = 2): the cp.async staging of round 1
-        if (ncta == 3) {
-            if (inverse) k_vol3t<true, 3><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
-            else k_vol3t<false, 3><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
-        } else {
-            if (inverse) k_vol3t<true, 2><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
-            else k_vol3t<false, 2><<<grid, V3_THREADS, V3T_SMEM, st>>>(p, map);
+        // forward: 2 CTAs per SM (108 registers; at 80 it spills and 1024^3 takes 1.99 instead of 1.82 ms), 4 staging buffers;
+        // inverse: 3 CTAs per SM (80 registers, no spills: 1.91 -> 1.83 ms), 3 buffers.  The slice-pair loop is unrolled twice so that
+        // the z state is not moved back into place every iteration (forward 1.82 -> 1.77 ms; profiles/ncu_vol3t_r2.txt)
+        static bool prepared_t = false;
+        if (!prepared_t) {
+            cudaFuncSetAttribute(k_vol3t<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(4));
+            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(3));
+            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            prepared_t = true;
         }
+        if (inverse) k_vol3t<true, 3, 3><<<grid, V3_THREADS, v3t_smem(3), st>>>(p, map);
+        else k_vol3t<false, 2, 4><<<grid, V3_THREADS, v3t_smem(4), st>>>(p, map);
         return;
     }
     if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);

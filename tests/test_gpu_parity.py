@@ -464,7 +464,8 @@ def test_volume_parity(dev, oracle, shape):
     v.close()
 
 
-@pytest.mark.parametrize("shape", [(128, 32, 16), (129, 33, 17), (300, 100, 31), (520, 300, 70), (1000, 64, 40), (131, 200, 130)],
+@pytest.mark.parametrize("shape", [(128, 32, 16), (129, 33, 17), (300, 100, 31), (520, 300, 70), (1000, 64, 40), (131, 200, 130), (64, 32, 16), (67, 36, 19),
+                                   (193, 97, 50)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_volume_single_pass(dev, oracle, shape):
     """the one-pass kernels (x, y and z lifting in ONE pass: tiles of 64 x 32 positions marching along z; DWTB200_TUNE_VOL3 = 1 staged by
