@@ -300,7 +300,7 @@ def run_ours(args):
     assert im.last_launches == 1
     bytes0 = 2 * 4 * PIX * M
     im.fill(0, 0, 6)
-    roof = {"bound": "hbm", "kernel": f"k_fwd_ring2<W97F> (level 0 of dwt_cdf97_2f_s, {M} frames of 8192x8192 per launch)",
+    roof = {"bound": "hbm", "kernel": f"k_fwd_ring2<W97F, 8> (level 0 of dwt_cdf97_2f_s, {M} frames of 8192x8192 per launch)",
             "achieved": bytes0 / t_fwd0 / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
             "frac": bytes0 / t_fwd0 / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": bytes0,
             "us_per_launch": t_fwd0 * 1e6,
@@ -310,7 +310,7 @@ def run_ours(args):
         try:
             tj = json.load(open(tr))
             roof["traffic"] = tj["k_fwd_ring2_w97f_level0_dram_bytes_per_launch_4_frames"] * M / 4
-            roof["traffic_source"] = tj["source"]
+            roof["traffic_source"] = tj["source_ring2"]
         except Exception:
             pass
 
@@ -434,6 +434,15 @@ def run_ours(args):
             volume = {"workload": f"{n}^3 float volume, one level, forward / inverse, device-resident", "fwd_ms": tf * 1e3, "inv_ms": ti * 1e3,
                       "fwd_gvoxel_s": n ** 3 / tf / 1e9, "inv_gvoxel_s": n ** 3 / ti / 1e9,
                       "fwd_roofline_frac": b / tf / 1e9 / peak, "inv_roofline_frac": b / ti / 1e9 / peak}
+            try:   # DRAM traffic of the two launches from the committed ncu capture (profiles/ncu_vol3t_r2.txt)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                if n == 1024:
+                    volume["kernel"] = "k_vol3t (one pass over the volume, tile staged by cp.async.bulk.tensor)"
+                    volume["algorithmic_bytes"] = b
+                    volume["fwd_traffic"] = tj["k_vol3t_fwd_1024cubed_dram_bytes_per_launch"]
+                    volume["inv_traffic"] = tj["k_vol3t_inv_1024cubed_dram_bytes_per_launch"]
+            except Exception:
+                pass
             # end to end through the reference-facing host entry points (cdf97_3f_op_sep_horizontal_s / cdf97_3i_ip_sep_horizontal_s ->
             # dwtb200_fwd3_host / dwtb200_inv3_host) on page-locked volumes (volume_alloc_realiably_locked of the compat layer)
             try:
