@@ -464,7 +464,7 @@ def run_ours(args):
                 volume["e2e"] = {"fwd_ms": (t1 - t0) * 1e3, "inv_ms": (t2 - t1) * 1e3, "fwd_gvoxel_s": n ** 3 / (t1 - t0) / 1e9,
                                  "inv_gvoxel_s": n ** 3 / (t2 - t1) / 1e9, "h2d_bytes": nb, "d2h_bytes": nb,
                                  "roundtrip_max_abs_err": float(np.abs(dst[::97, ::89] - src[::97, ::89]).max()),
-                                 "what": "pinned host volumes, upload + transform + download per call (wall clock)"}
+                                 "what": "pinned host volumes through dwtb200_fwd3_host / dwtb200_inv3_host: z ranges uploaded, transformed and downloaded in a pipeline (wall clock per call)"}
                 L.c.dwtb200_host_free(hs); L.c.dwtb200_host_free(hd)
             except Exception as e:
                 volume["e2e"] = {"skipped": str(e)}

@@ -188,7 +188,7 @@ void dwtb200_set_strip_rows(int rows);
  *   DWTB200_TUNE_MID_MAX   accepted and ignored (the persistent mid-level kernels of round 1 were never faster and are gone)
  *   DWTB200_TUNE_PDL       1: kernels of a pyramid are chained by programmatic dependent launch (0: measured no gain)
  *   DWTB200_TUNE_NARROW    1: streaming kernels hold 16 instead of 32 bytes per lane: twice the warps per SM (0)
- *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips and download for large dense images (1)
+ *   DWTB200_TUNE_PIPELINE  1: the *_host calls overlap upload, level-0 strips / z ranges and download for large dense images and volumes (1)
  *   DWTB200_TUNE_RING      bit 0 / bit 1: forward / inverse streaming levels stage their input through a shared-memory
  *                          ring filled by the bulk-copy engine (cp.async.bulk + mbarrier) instead of a register double buffer;
  *                          bits 4-6 force a CTA shape (0 = chosen per level: 7 consumer warps x 2 CTAs per SM, or 5 x 3 for
@@ -204,7 +204,10 @@ enum { DWTB200_TUNE_TILE_MAX = 0, DWTB200_TUNE_TAIL_MAX = 1, DWTB200_TUNE_MID_MA
 int dwtb200_set_tuning(int key, long long value);
 
 /* ---- 3-D, one level, interleaved subbands (src/volume-dwt.c:727, 677, 1115; struct volume_t
- * src/volume.h:14-24: stride_x = pixel, stride_y = row, stride_z = slice, all in bytes) -------- */
+ * src/volume.h:14-24: stride_x = pixel, stride_y = row, stride_z = slice, all in bytes) --------
+ * The host calls are synchronous (results in the caller's memory at return); src and dst may be the same volume.  Volumes of
+ * 64 MiB and more go through a pipeline: z ranges are uploaded, transformed and downloaded concurrently (pin the volumes --
+ * volume_alloc_realiably_locked of the compat layer, dwtb200_host_alloc -- for the copies to overlap). */
 int dwtb200_fwd3_host(const void *src, size_t s_stride_x, size_t s_stride_y, size_t s_stride_z, void *dst,
                       size_t d_stride_x, size_t d_stride_y, size_t d_stride_z, int size_x, int size_y, int size_z);
 int dwtb200_inv3_host(void *vol, size_t stride_x, size_t stride_y, size_t stride_z, int size_x, int size_y,

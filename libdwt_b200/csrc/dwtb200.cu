@@ -2518,13 +2518,100 @@ static dwtb200_volume *host_volume(int nx, int ny, int nz)
     g_host_vol = dwtb200_volume_create(nx, ny, nz);
     return g_host_vol;
 }
+// Large volumes through the *_host calls: the z ranges of the one-pass kernel are launched one by one while the volume is still
+// arriving, and every range's finished slices leave while the next range is uploaded (the 3-D transforms leave every coefficient
+// where its sample was -- interleaved subbands -- so a download never lands on slices that have not been uploaded).  1024^3:
+// upload, transform, download one after the other 154 ms; pipelined, both directions of the link at once.
+static bool host3_pipeline_applies(const dwtb200_volume *v, size_t sx_src, size_t sx_dst)
+{
+    if (!g.pipeline || g.vol3 == 0 || g.force_generic || sx_src != sizeof(float) || sx_dst != sizeof(float)) return false;
+    VolParams p;
+    memset(&p, 0, sizeof p);
+    p.nx = v->nx;
+    p.ny = v->ny;
+    p.nz = v->nz;
+    return vol3_applies(p) && v->nz >= 64 && (size_t)v->nx * v->ny * v->nz * sizeof(float) >= ((size_t)64 << 20);
+}
+static int host3_pipelined(bool inverse, dwtb200_volume *v, const char *src, size_t ssy, size_t ssz, char *dst, size_t dsy, size_t dsz)
+{
+    if (!g_pipe.up) {
+        CK(cudaStreamCreateWithFlags(&g_pipe.up, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_pipe.dn, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_pipe.dn2, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_pipe.dn3, cudaStreamNonBlocking));
+    }
+    const int nz = v->nz, units = inverse ? (nz >> 1) + 1 : (nz + 1) >> 1;
+    const int want = std::min(16, std::max(1, units / 8)), pps = (units + want - 1) / want, nr = (units + pps - 1) / pps;
+    VolParams p;
+    memset(&p, 0, sizeof p);
+    p.nx = v->nx;
+    p.ny = v->ny;
+    p.nz = nz;
+    p.s_pitch = p.d_pitch = v->pitch;
+    p.s_slice = p.d_slice = v->slice;
+    p.src = v->buf[v->cur];
+    p.dst = v->buf[v->cur ^ 1];
+    // slices [z0, z1) between the host volume (rows hy, slices hz bytes apart) and a device plane
+    auto slab = [&](char *host, size_t hy, size_t hz, float *dev, int z0, int z1, bool up, cudaStream_t on) -> cudaError_t {
+        if (z1 <= z0) return cudaSuccess;
+        char *hp = host + (size_t)z0 * hz;
+        float *dp = dev + (size_t)z0 * v->slice;
+        if (hz % hy == 0) {
+            cudaMemcpy3DParms c;
+            memset(&c, 0, sizeof c);
+            const cudaPitchedPtr h = make_cudaPitchedPtr(hp, hy, v->nx, hz / hy), d = make_cudaPitchedPtr(dp, v->pitch * sizeof(float), v->nx, v->ny);
+            c.srcPtr = up ? h : d;
+            c.dstPtr = up ? d : h;
+            c.extent = make_cudaExtent((size_t)v->nx * sizeof(float), v->ny, z1 - z0);
+            c.kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+            return cudaMemcpy3DAsync(&c, on);
+        }
+        for (int z = z0; z < z1; z++, hp += hz, dp += v->slice) {
+            const cudaError_t e = up ? cudaMemcpy2DAsync(dp, v->pitch * sizeof(float), hp, hy, (size_t)v->nx * sizeof(float), v->ny, cudaMemcpyHostToDevice, on)
+                                     : cudaMemcpy2DAsync(hp, hy, dp, v->pitch * sizeof(float), (size_t)v->nx * sizeof(float), v->ny, cudaMemcpyDeviceToHost, on);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    // events: [0, nr) upload for range c done; [nr, 2 nr) kernel of range c done; 2 nr: previous work on g.st
+    CK(cudaEventRecord(g_pipe.get(2 * (size_t)nr), g.st));
+    CK(cudaStreamWaitEvent(g_pipe.up, g_pipe.get(2 * (size_t)nr), 0));
+    CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get(2 * (size_t)nr), 0));
+    int zup = 0;
+    for (int c = 0; c < nr; c++) {   // range c reads the slices up to 2 k1 + 2 (mirrored into the volume at its end)
+        const int k1 = std::min((c + 1) * pps, units), need = (c == nr - 1) ? nz : std::min(nz, 2 * k1 + 4);
+        CK(slab(const_cast<char *>(src), ssy, ssz, v->buf[v->cur], zup, need, true, g_pipe.up));
+        zup = std::max(zup, need);
+        CK(cudaEventRecord(g_pipe.get((size_t)c), g_pipe.up));
+    }
+    for (int c = 0; c < nr; c++) {
+        const int k0 = c * pps, k1 = std::min((c + 1) * pps, units);
+        CK(cudaStreamWaitEvent(g.st, g_pipe.get((size_t)c), 0));
+        launch_vol3_ranges(p, inverse ? 1 : 0, g.vol3, pps, c, 1, g.st);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(g_pipe.get((size_t)(nr + c)), g.st));
+        CK(cudaStreamWaitEvent(g_pipe.dn, g_pipe.get((size_t)(nr + c)), 0));
+        // slices this range writes: forward pairs (2k, 2k+1), inverse pairs (2k-1, 2k); all of them below the slices uploaded so far
+        const int z0 = inverse ? std::max(0, 2 * k0 - 1) : 2 * k0, z1 = std::min(nz, inverse ? 2 * k1 - 1 : 2 * k1);
+        CK(slab(dst, dsy, dsz, v->buf[v->cur ^ 1], z0, (c == nr - 1) ? nz : z1, false, g_pipe.dn));
+    }
+    CK(cudaStreamSynchronize(g_pipe.dn));
+    CK(cudaStreamSynchronize(g_pipe.up));
+    CK(cudaStreamSynchronize(g.st));
+    CK(cudaGetLastError());
+    v->cur ^= 1;
+    return DWTB200_OK;
+}
 int dwtb200_fwd3_host(const void *src, size_t ssx, size_t ssy, size_t ssz, void *dst, size_t dsx, size_t dsy, size_t dsz,
                       int nx, int ny, int nz)
 {
     API_LOCK();
     NEED_DEV();
+    if (!src || !dst) return fail(DWTB200_EINVAL, "fwd3_host: null argument");
+    if (nx < 5 || ny < 5 || nz < 5) return fail(DWTB200_EINVAL, "fwd3_host: every size must be >= 5 (src/dwt-simple.c:2172)");
     dwtb200_volume *v = host_volume(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
+    if (host3_pipeline_applies(v, ssx, dsx)) return host3_pipelined(false, v, (const char *)src, ssy, ssz, (char *)dst, dsy, dsz);
     int r = dwtb200_volume_upload(v, src, ssx, ssy, ssz);
     if (!r) r = dwtb200_volume_fwd3(v);
     if (!r) r = dwtb200_volume_download(v, dst, dsx, dsy, dsz);
@@ -2534,8 +2621,10 @@ int dwtb200_inv3_host(void *vol, size_t sx, size_t sy, size_t sz, int nx, int ny
 {
     API_LOCK();
     NEED_DEV();
+    if (!vol) return fail(DWTB200_EINVAL, "inv3_host: null argument");
     dwtb200_volume *v = host_volume(nx, ny, nz);
     if (!v) return DWTB200_ENOMEM;
+    if (host3_pipeline_applies(v, sx, sx)) return host3_pipelined(true, v, (const char *)vol, sy, sz, (char *)vol, sy, sz);
     int r = dwtb200_volume_upload(v, vol, sx, sy, sz);
     if (!r) r = dwtb200_volume_inv3(v);
     if (!r) r = dwtb200_volume_download(v, vol, sx, sy, sz);

@@ -184,6 +184,7 @@ struct VolParams {
     int64_t s_pitch, s_slice, d_pitch, d_slice;
     int nx, ny, nz;
     int ncg, nstrips, pps;   // filled by the launchers
+    int strip0;              // k_vol3 / k_vol3t: first z range of this launch (pipelined host path; 0 otherwise)
 };
 void launch_vol_xy(VolParams p, int inverse, int sm_count, cudaStream_t st);
 void launch_vol_z(VolParams p, int inverse, int sm_count, cudaStream_t st);
@@ -191,6 +192,8 @@ void launch_vol_z(VolParams p, int inverse, int sm_count, cudaStream_t st);
 bool vol3_applies(const VolParams &p);
 // variant 1: tile staged by one tensor copy per slice (k_vol3t); 2: by cp.async (k_vol3, also the fallback without a tensor map)
 void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream_t st);
+// the z ranges [strip0, strip0 + count) of the same pass cut into ranges of pps slice pairs (the pipelined host path launches it range by range)
+void launch_vol3_ranges(VolParams p, int inverse, int variant, int pps, int strip0, int count, cudaStream_t st);
 
 struct Axis3Params {
     const float *src;

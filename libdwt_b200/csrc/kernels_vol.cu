@@ -265,7 +265,7 @@ template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol
     // the slice schedule of k_vol_z: forward pairs (2m+1, 2m+2) after a seed slice 2 m0, inverse pairs (2k, 2k+1)
     constexpr int WARM = INV ? 4 : 3, DELAY = 1;
     const int units = INV ? (N >> 1) + 1 : (N + 1) >> 1;
-    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, units);
+    const int k0 = (blockIdx.z + p.strip0) * p.pps, k1 = min(k0 + p.pps, units);
     if (k0 >= k1) return;
     const int m0 = k0 + DELAY - WARM, m1 = k1 - 1 + DELAY;
     const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + (INV ? 0 : 1);   // slices zfirst .. zfirst + nsl - 1 (mirrored into the volume)
@@ -427,7 +427,7 @@ template <bool INV, int NCTA, int NBUF> __global__ void __launch_bounds__(V3_THR
 
     constexpr int WARM = INV ? 4 : 3, DELAY = 1;
     const int units = INV ? (N >> 1) + 1 : (N + 1) >> 1;
-    const int k0 = blockIdx.z * p.pps, k1 = min(k0 + p.pps, units);
+    const int k0 = (blockIdx.z + p.strip0) * p.pps, k1 = min(k0 + p.pps, units);
     if (k0 >= k1) return;
     const int m0 = k0 + DELAY - WARM, m1 = k1 - 1 + DELAY;
     const int zfirst = 2 * m0, npairs = m1 - m0 + 1, nsl = 2 * npairs + (INV ? 0 : 1);
@@ -601,7 +601,7 @@ static bool vol3_tensor_map(const VolParams &p, CUtensorMap *map)
 }
 
 bool vol3_applies(const VolParams &p) { return p.nx >= V3_TX && p.ny >= V3_TY && p.nz >= 16; }   // at least one full tile
-void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream_t st)
+static void vol3_prepare()
 {
     static bool prepared = false;
     if (!prepared) {
@@ -609,6 +609,34 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
         cudaFuncSetAttribute(k_vol3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM);
         prepared = true;
     }
+}
+static void vol3_launch(const VolParams &p, int inverse, int variant, int count, cudaStream_t st)
+{
+    const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
+    const dim3 grid(tx, ty, count);
+    CUtensorMap map;
+    if (variant != 2 && vol3_tensor_map(p, &map)) {   // variant 2 (DWTB200_TUNE_VOL3 = 2): the cp.async staging of round 1
+        // forward: 2 CTAs per SM (108 registers; at 80 it spills and 1024^3 takes 1.99 instead of 1.82 ms), 4 staging buffers;
+        // inverse: 3 CTAs per SM (80 registers, no spills: 1.91 -> 1.83 ms), 3 buffers.  The slice-pair loop is unrolled twice so that
+        // the z state is not moved back into place every iteration (forward 1.82 -> 1.77 ms; profiles/ncu_vol3t_r2.txt)
+        static bool prepared_t = false;
+        if (!prepared_t) {
+            cudaFuncSetAttribute(k_vol3t<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(4));
+            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(3));
+            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            prepared_t = true;
+        }
+        if (inverse) k_vol3t<true, 3, 3><<<grid, V3_THREADS, v3t_smem(3), st>>>(p, map);
+        else k_vol3t<false, 2, 4><<<grid, V3_THREADS, v3t_smem(4), st>>>(p, map);
+        return;
+    }
+    if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+    else k_vol3<false><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+}
+
+void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream_t st)
+{
+    vol3_prepare();
     const int tx = (p.nx + V3_TX - 1) / V3_TX, ty = (p.ny + V3_TY - 1) / V3_TY;
     const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
     const int ncta = variant != 2 && inverse ? 3 : V3_NCTA;   // CTAs per SM (see below)
@@ -633,25 +661,18 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
     }
     p.pps = (units + best - 1) / best;
     p.nstrips = (units + p.pps - 1) / p.pps;
-    const dim3 grid(tx, ty, p.nstrips);
-    CUtensorMap map;
-    if (variant != 2 && vol3_tensor_map(p, &map)) {   // variant 2 (DWTB200_TUNE_VOL3 = 2): the cp.async staging of round 1
-        // forward: 2 CTAs per SM (108 registers; at 80 it spills and 1024^3 takes 1.99 instead of 1.82 ms), 4 staging buffers;
-        // inverse: 3 CTAs per SM (80 registers, no spills: 1.91 -> 1.83 ms), 3 buffers.  The slice-pair loop is unrolled twice so that
-        // the z state is not moved back into place every iteration (forward 1.82 -> 1.77 ms; profiles/ncu_vol3t_r2.txt)
-        static bool prepared_t = false;
-        if (!prepared_t) {
-            cudaFuncSetAttribute(k_vol3t<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(4));
-            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3t_smem(3));
-            cudaFuncSetAttribute(k_vol3t<true, 3, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            prepared_t = true;
-        }
-        if (inverse) k_vol3t<true, 3, 3><<<grid, V3_THREADS, v3t_smem(3), st>>>(p, map);
-        else k_vol3t<false, 2, 4><<<grid, V3_THREADS, v3t_smem(4), st>>>(p, map);
-        return;
-    }
-    if (inverse) k_vol3<true><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
-    else k_vol3<false><<<grid, V3_THREADS, V3_SMEM, st>>>(p);
+    p.strip0 = 0;
+    vol3_launch(p, inverse, variant, p.nstrips, st);
+}
+void launch_vol3_ranges(VolParams p, int inverse, int variant, int pps, int strip0, int count, cudaStream_t st)
+{
+    vol3_prepare();
+    const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
+    p.pps = pps;
+    p.nstrips = (units + pps - 1) / pps;
+    p.strip0 = strip0;
+    if (strip0 + count > p.nstrips) count = p.nstrips - strip0;
+    if (count > 0) vol3_launch(p, inverse, variant, count, st);
 }
 
 static int pick_pps(int units, int64_t other_warps, int sm_count)

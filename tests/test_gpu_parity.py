@@ -528,6 +528,32 @@ def test_wide_pattern_and_row_offset(dev, oracle):
         img.close()
 
 
+@pytest.mark.parametrize("shape", [(520, 300, 130), (256, 257, 301), (1000, 70, 257)], ids=lambda s: "x".join(map(str, s)))
+def test_volume_pipelined_host_path(dev, oracle, shape):
+    """volumes of 64 MiB and more through the host calls: z ranges uploaded, transformed and downloaded in a pipeline
+    (host3_pipelined, dwtb200.cu); same bits as the oracle and as the plain upload -> transform -> download path"""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + 3 * nz)
+    a = (rng.standard_normal((nz, ny, nx)) * 10.0 ** rng.integers(-2, 3, size=(nz, ny, nx))).astype(np.float32)
+    want = np.zeros_like(a)
+    oracle.fwd3(a, want)
+    back = want.copy()
+    oracle.inv3(back)
+    L = dev.lib()
+    for pipeline in (1, 0):
+        L.check(L.c.dwtb200_set_tuning(5, pipeline))
+        try:
+            got = np.zeros_like(a)
+            dev.fwd3(a, got)
+            bad = got.view(np.uint32) != want.view(np.uint32)
+            assert not bad.any(), f"pipeline={pipeline}: {bad.sum()} voxels differ (forward), first at {np.argwhere(bad)[0]}"
+            dev.inv3(got)
+            bad = got.view(np.uint32) != back.view(np.uint32)
+            assert not bad.any(), f"pipeline={pipeline}: {bad.sum()} voxels differ (inverse), first at {np.argwhere(bad)[0]}"
+        finally:
+            L.check(L.c.dwtb200_set_tuning(5, 1))
+
+
 # ---- the pipelined host path (large dense images): upload / level-0 strips / download overlapped, in place ----
 @pytest.mark.parametrize("kind", KINDS, ids=KIDS)
 def test_pipelined_host_path(dev, oracle, kind):
