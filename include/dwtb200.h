@@ -167,6 +167,11 @@ int dwtb200_image_conv_show(dwtb200_image *src, dwtb200_image *dst, int size_i_b
 /* dwt_util_save_to_pgm_s / _d (src/libdwt.c:19794, 19877) for a device-resident frame: grey values computed on the device (one byte
  * per sample crosses PCIe instead of the plane), the same "P2" text file written by the host */
 int dwtb200_image_save_pgm(dwtb200_image *img, int frame, const char *filename, double max_value, int size_i_big_x, int size_i_big_y);
+/* dwt_util_save_sym_to_pgm_s (src/libdwt.c:26184): samples in [-max_value, +max_value], shifted by +max_value and written against
+ * twice the maximum (both in the image's own precision, as dwt_util_shift_s and the reference's call do) */
+int dwtb200_image_save_sym_pgm(dwtb200_image *img, int frame, const char *filename, double max_value, int size_i_big_x, int size_i_big_y);
+/* dwt_util_save_to_mat_s (src/libdwt.c:24430) for a device-resident frame: "%f" values separated by commas, one row per line */
+int dwtb200_image_save_mat(dwtb200_image *img, int frame, const char *filename, int size_i_big_x, int size_i_big_y);
 /* bit-exact comparison of the current planes of two images on the device: number of differing samples */
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b);
 /* max |a-b| over the current planes (float/double kinds), cf. dwt_util_compare_s (src/libdwt.c:1593) */

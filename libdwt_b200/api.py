@@ -52,6 +52,7 @@ SYMBOLS = [
     ("dwtb200_image_diff", _i64, [_vp, _vp]), ("dwtb200_image_maxabs", _dbl, [_vp, _vp]),
     ("dwtb200_image_copy", _i, [_vp, _vp]),
     ("dwtb200_image_conv_show", _i, [_vp, _vp, _i, _i]), ("dwtb200_image_save_pgm", _i, [_vp, _i, C.c_char_p, _dbl, _i, _i]),
+    ("dwtb200_image_save_sym_pgm", _i, [_vp, _i, C.c_char_p, _dbl, _i, _i]), ("dwtb200_image_save_mat", _i, [_vp, _i, C.c_char_p, _i, _i]),
     ("dwtb200_image_last_launches", _i, [_vp]), ("dwtb200_image_last_path", _i, [_vp]),
     ("dwtb200_force_generic", None, [_i]), ("dwtb200_set_strip_rows", None, [_i]),
     ("dwtb200_set_tuning", _i, [_i, C.c_longlong]),
@@ -409,6 +410,14 @@ class DeviceImage:
     def save_pgm(self, filename, max_value, frame=0, inner=None):
         iy, ix = inner if inner is not None else (self.size_y, self.size_x)
         self.L.check(self.L.c.dwtb200_image_save_pgm(self.h, frame, filename.encode(), max_value, ix, iy))
+
+    def save_sym_pgm(self, filename, max_value, frame=0, inner=None):
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        self.L.check(self.L.c.dwtb200_image_save_sym_pgm(self.h, frame, filename.encode(), max_value, ix, iy))
+
+    def save_mat(self, filename, frame=0, inner=None):
+        iy, ix = inner if inner is not None else (self.size_y, self.size_x)
+        self.L.check(self.L.c.dwtb200_image_save_mat(self.h, frame, filename.encode(), ix, iy))
 
     def copy_from(self, other):
         self.L.check(self.L.c.dwtb200_image_copy(self.h, other.h))

@@ -1743,10 +1743,8 @@ int dwtb200_image_conv_show(dwtb200_image *src, dwtb200_image *dst, int ix, int 
 
 // dwt_util_save_to_pgm_s / _d (src/libdwt.c:19794, 19877): the grey values are computed on the device, one byte per sample is copied
 // to the host, the text file ("P2", one value per line) is written there
-int dwtb200_image_save_pgm(dwtb200_image *im, int frame, const char *filename, double max_value, int ix, int iy)
+static int save_pgm(dwtb200_image *im, int frame, const char *filename, double max_value, double shift, int shifted, int ix, int iy)
 {
-    API_LOCK();
-    NEED_DEV();
     if (!im || !filename || frame < 0 || frame >= im->frames || ix < 0 || iy < 0 || ix > im->ox || iy > im->oy || max_value == 0.0 ||
         kind_elem_class(im->kind) == 0)
         return fail(DWTB200_EINVAL, "image_save_pgm: float or double image, a frame, a file name and a nonzero maximum");
@@ -1756,7 +1754,7 @@ int dwtb200_image_save_pgm(dwtb200_image *im, int frame, const char *filename, d
     std::vector<unsigned char> h(n ? n : 1);
     if (n) {
         CK(cudaMalloc((void **)&d, n));
-        launch_pgm_quant(kind_elem_class(im->kind), frame_ptr(im, im->cur, frame), im->pitch, d, ix, iy, max_value, g.st);
+        launch_pgm_quant(kind_elem_class(im->kind), frame_ptr(im, im->cur, frame), im->pitch, d, ix, iy, max_value, shift, shifted, g.st);
         cudaMemcpyAsync(h.data(), d, n, cudaMemcpyDeviceToHost, g.st);
         const cudaError_t e = cudaStreamSynchronize(g.st);
         cudaFree(d);
@@ -1775,6 +1773,64 @@ int dwtb200_image_save_pgm(dwtb200_image *im, int frame, const char *filename, d
     const bool ok = fwrite(out.data(), 1, out.size(), file) == out.size();
     fclose(file);
     return ok ? DWTB200_OK : fail(DWTB200_EINVAL, "image_save_pgm: error writing %s", filename);
+}
+int dwtb200_image_save_pgm(dwtb200_image *im, int frame, const char *filename, double max_value, int ix, int iy)
+{
+    API_LOCK();
+    NEED_DEV();
+    return save_pgm(im, frame, filename, max_value, 0.0, 0, ix, iy);
+}
+// dwt_util_save_sym_to_pgm_s (src/libdwt.c:26184): coefficients in [-max, +max] shifted by +max (in the image's own precision, as
+// dwt_util_shift_s does) and written against 2 max
+int dwtb200_image_save_sym_pgm(dwtb200_image *im, int frame, const char *filename, double max_value, int ix, int iy)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!(max_value > 0.0)) return fail(DWTB200_EINVAL, "image_save_sym_pgm: the maximum must be positive");
+    const bool f32 = im && kind_elem_class(im->kind) == 1;
+    const double twice = f32 ? (double)(2.f * (float)max_value) : 2.0 * max_value;
+    return save_pgm(im, frame, filename, twice, max_value, 1, ix, iy);
+}
+// dwt_util_save_to_mat_s (src/libdwt.c:24430): the top-left ix x iy samples of a frame as text, "%f" separated by commas, one row per
+// line.  Text output is host work; the samples are brought over once, packed.
+int dwtb200_image_save_mat(dwtb200_image *im, int frame, const char *filename, int ix, int iy)
+{
+    API_LOCK();
+    NEED_DEV();
+    if (!im || !filename || frame < 0 || frame >= im->frames || ix < 0 || iy < 0 || ix > im->ox || iy > im->oy || kind_elem_class(im->kind) == 0)
+        return fail(DWTB200_EINVAL, "image_save_mat: float or double image, a frame and a file name");
+    ImageScope scope(im);
+    const size_t n = (size_t)ix * (size_t)iy;
+    std::vector<char> h(n ? n * im->es : 1);
+    if (n) {
+        CK(cudaMemcpy2DAsync(h.data(), (size_t)ix * im->es, frame_ptr(im, im->cur, frame), im->pitch * im->es, (size_t)ix * im->es, iy, cudaMemcpyDeviceToHost,
+                             g.st));
+        CK(cudaStreamSynchronize(g.st));
+    }
+    FILE *file = fopen(filename, "w");
+    if (!file) return fail(DWTB200_EINVAL, "image_save_mat: cannot open %s", filename);
+    std::string out;
+    char buf[400];   // "%f" of a double can be 300+ characters
+    for (int y = 0; y < iy; y++) {
+        for (int x = 0; x < ix; x++) {
+            const size_t i = (size_t)y * ix + x;
+            const double v = im->es == 8 ? ((const double *)h.data())[i] : (double)((const float *)h.data())[i];
+            const int len = snprintf(buf, sizeof buf, "%f", v);
+            out.append(buf, (size_t)len);
+            if (x + 1 != ix) out.push_back(',');
+        }
+        out.push_back('\n');
+        if (out.size() > (1u << 20)) {
+            if (fwrite(out.data(), 1, out.size(), file) != out.size()) {
+                fclose(file);
+                return fail(DWTB200_EINVAL, "image_save_mat: error writing %s", filename);
+            }
+            out.clear();
+        }
+    }
+    const bool ok = fwrite(out.data(), 1, out.size(), file) == out.size();
+    fclose(file);
+    return ok ? DWTB200_OK : fail(DWTB200_EINVAL, "image_save_mat: error writing %s", filename);
 }
 
 int64_t dwtb200_image_diff(dwtb200_image *a, dwtb200_image *b)

@@ -172,7 +172,8 @@ void launch_copy2d(int elem_size, void *dst, int64_t dpitch, const void *src, in
 void launch_compare(int elem_size, const void *a, const void *b, int64_t pitch, int64_t frame, int nx, int ny, int frames,
                     int mode, unsigned long long *out, cudaStream_t st);
 void launch_conv_show(int elem_class, const void *src, int64_t sp, void *dst, int64_t dp, int nx, int ny, cudaStream_t st);
-void launch_pgm_quant(int elem_class, const void *src, int64_t sp, unsigned char *dst, int nx, int ny, double maxv, cudaStream_t st);
+void launch_pgm_quant(int elem_class, const void *src, int64_t sp, unsigned char *dst, int nx, int ny, double maxv, double shift, int shifted,
+                      cudaStream_t st);
 void launch_moments(int elem_class, const void *a, int64_t pitch_elems, int nx, int ny, double *out3, cudaStream_t st);
 void launch_volume_fill(float *buf, int64_t pitch, int64_t slice, int nx, int ny, int nz, cudaStream_t st);
 

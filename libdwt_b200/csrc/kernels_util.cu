@@ -206,11 +206,17 @@ void launch_conv_show(int elem_class, const void *src, int64_t sp, void *dst, in
 }
 // the grey value dwt_util_save_to_pgm_s writes for a sample (src/libdwt.c:19794-19866): (int)(255 * px / max_value) in float,
 // 255 above max_value, 0 below zero and for NaN; one byte per sample is all that crosses PCIe
-template <class T> __global__ void __launch_bounds__(256) k_pgm_quant(const T *src, int64_t sp, unsigned char *dst, int nx, int ny, T maxv)
+// `shift` is added first (dwt_util_shift_s, src/libdwt.c:25530: the symmetric writer dwt_util_save_sym_to_pgm_s, :26184, shifts by
+// +max and saves with 2 max)
+template <class T> __global__ void __launch_bounds__(256) k_pgm_quant(const T *src, int64_t sp, unsigned char *dst, int nx, int ny, T maxv, T shift, int shifted)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= nx || y >= ny) return;
-    const T px = src[(int64_t)y * sp + x];
+    T px = src[(int64_t)y * sp + x];
+    if (shifted) {
+        if constexpr (sizeof(T) == 8) px = __dadd_rn(px, shift);
+        else px = __fadd_rn(px, shift);
+    }
     int val;
     if constexpr (sizeof(T) == 8) val = (int)__ddiv_rn(__dmul_rn(255.0, px), maxv);
     else val = (int)__fdiv_rn(__fmul_rn(255.f, px), maxv);
@@ -219,12 +225,13 @@ template <class T> __global__ void __launch_bounds__(256) k_pgm_quant(const T *s
     if (px < T(0)) val = 0;
     dst[(int64_t)y * nx + x] = (unsigned char)min(max(val, 0), 255);
 }
-void launch_pgm_quant(int elem_class, const void *src, int64_t sp, unsigned char *dst, int nx, int ny, double maxv, cudaStream_t st)
+void launch_pgm_quant(int elem_class, const void *src, int64_t sp, unsigned char *dst, int nx, int ny, double maxv, double shift, int shifted,
+                      cudaStream_t st)
 {
     if (nx <= 0 || ny <= 0) return;
     const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
-    if (elem_class == 2) k_pgm_quant<double><<<g, b, 0, st>>>((const double *)src, sp, dst, nx, ny, maxv);
-    else k_pgm_quant<float><<<g, b, 0, st>>>((const float *)src, sp, dst, nx, ny, (float)maxv);
+    if (elem_class == 2) k_pgm_quant<double><<<g, b, 0, st>>>((const double *)src, sp, dst, nx, ny, maxv, shift, shifted);
+    else k_pgm_quant<float><<<g, b, 0, st>>>((const float *)src, sp, dst, nx, ny, (float)maxv, (float)shift, shifted);
 }
 
 // ---- moments of a rectangle (a subband of the Mallat plane): sum, sum of squares, max |x|, in double ----

@@ -65,6 +65,31 @@ def test_pgm_of_a_device_resident_plane(dev, ref, tmp_path):
     img.close()
 
 
+def test_symmetric_pgm_and_mat_of_a_device_resident_plane(dev, ref, tmp_path):
+    """dwt_util_save_sym_to_pgm_s (src/libdwt.c:26184) and dwt_util_save_to_mat_s (:24430): the same files."""
+    ox, oy = 200, 120
+    img = dev.DeviceImage(dev.CDF97_F32, ox, oy)
+    img.fill(0, 0)
+    img.fwd2(3)
+    a = img.download()
+    f_dev, f_ref = str(tmp_path / "dev.out"), str(tmp_path / "ref.out")
+    sym = ref.lib.dwt_util_save_sym_to_pgm_s
+    sym.argtypes = [C.c_char_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    for mx in (4.0, 0.7):   # 0.7: coefficients beyond the range on both sides
+        img.save_sym_pgm(f_dev, mx)
+        assert sym(f_ref.encode(), mx, a.ctypes.data, a.strides[0], a.strides[1], ox, oy) == 0
+        assert open(f_dev, "rb").read() == open(f_ref, "rb").read()
+    mat = ref.lib.dwt_util_save_to_mat_s
+    mat.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    img.save_mat(f_dev)
+    assert mat(f_ref.encode(), a.ctypes.data, ox, oy, a.strides[0], a.strides[1]) == 0
+    assert open(f_dev, "rb").read() == open(f_ref, "rb").read()
+    img.save_mat(f_dev, inner=(50, 70))
+    assert mat(f_ref.encode(), a.ctypes.data, 70, 50, a.strides[0], a.strides[1]) == 0
+    assert open(f_dev, "rb").read() == open(f_ref, "rb").read()
+    img.close()
+
+
 class Volume(C.Structure):
     _fields_ = [("size_x", C.c_int), ("size_y", C.c_int), ("size_z", C.c_int), ("stride_x", C.c_size_t), ("stride_y", C.c_size_t),
                 ("stride_z", C.c_size_t), ("data", C.c_void_p)]
