@@ -15,6 +15,7 @@
 // Two passes over the volume (4*S bytes) instead of three; both directions apply x, then y, then z like
 // the reference (the inverse is NOT the mirrored order there either), so results are bit-identical.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "ring_common.cuh"
 #include "stream_common.cuh"
@@ -641,24 +642,27 @@ void launch_vol3(VolParams p, int inverse, int variant, int sm_count, cudaStream
     const int units = inverse ? (p.nz >> 1) + 1 : (p.nz + 1) >> 1;
     const int ncta = variant != 2 && inverse ? 3 : V3_NCTA;   // CTAs per SM (see below)
     const double warm = inverse ? 4.0 : 3.0;
-    // z ranges: enough CTAs for full waves of one CTA per SM, ranges of at least 32 slice pairs (3 warm-up pairs are recomputed per range)
+    // z ranges.  Every range recomputes `warm` slice pairs, yet many short ranges beat few long ones: the CTAs of a wave start together
+    // and stay in phase (x / y / z lifting, staging waits), later waves drift apart and fill each other's gaps.  Fitted on 512^3, 768^3
+    // and 1024^3 (profiles/ncu_vol3t_r2.txt, "z ranges"): time ~ (1 + warm / pps) (1 + B / waves), B = 1.44 with three CTAs per SM
+    // (inverse), 0.7 with two, and half of the idle share of the last wave; 1024^3 inverse: 7 ranges of 74 pairs 1.81 ms, 13 of 40 1.70 ms
     int best = 1;
     double best_cost = 1e30;
     for (int zs = 1; zs <= 32; zs++) {
         const int pps = (units + zs - 1) / zs;
-        if (zs > 1 && pps < 24) break;
+        if (zs > 1 && pps < 26) break;   // shorter ranges cost more than the model says (512^3: 16 ranges of 16 pairs 0.273 ms, 9 of 29 0.254 ms)
         const int64_t n = (int64_t)tx * ty * ((units + pps - 1) / pps);
-        const int64_t slots = (int64_t)sm_count * ncta, waves = (n + slots - 1) / slots;
-        // the CTAs of one wave start together and stay in phase, so the two CTAs of an SM sit in the same (x / y / z) phase at the
-        // same time; several waves of shorter ranges drift apart and overlap each other's phases (measured: 768^3 in one wave of
-        // 288 CTAs 1.50 ms, 1024^3 in seven waves at the same per-voxel cost 2.54 ms;
-        // delaying the second CTA of every SM by a microsecond at its start changes nothing once there are several waves)
-        const double cost = (1.0 + warm / pps) * (double)(waves * slots) / (double)n * (waves < 3 ? 1.2 : 1.0);
+        const double slots = (double)sm_count * ncta, waves = (double)n / slots, whole = (double)((n + (int64_t)slots - 1) / (int64_t)slots);
+        const double cost = (1.0 + warm / pps) * (1.0 + (ncta == 3 ? 1.44 : 0.7) / waves) * (1.0 + 0.5 * (whole / waves - 1.0));
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best = zs;
         }
     }
+#ifdef DWTB200_DEBUG_KEYS   // measurement only: number of z ranges forced from the environment
+    if (const char *e = getenv("DWTB200_VOL3_ZS"))
+        if (atoi(e) > 0) best = atoi(e);
+#endif
     p.pps = (units + best - 1) / best;
     p.nstrips = (units + p.pps - 1) / p.pps;
     p.strip0 = 0;
