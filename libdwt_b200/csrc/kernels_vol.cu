@@ -402,7 +402,7 @@ template <bool INV> __global__ void __launch_bounds__(V3_THREADS, V3_NCTA) k_vol
 // whose staged window leaves the volume replace the zeros by the mirrored samples (<= 4 shared-memory moves per thread and
 // slice, listed once).  The x pass of slice i and the y pass of slice i - 1 share a phase (the x-lifted buffer is double
 // buffered), so a slice costs one __syncthreads instead of two and every warp has work in every phase.  NBUF staging
-// buffers: NBUF - 1 slices in flight.  1024^3: 2.53 -> 1.77 ms forward, 2.62 -> 1.83 ms inverse (60 -> 42 instructions per
+// buffers: NBUF - 1 slices in flight.  1024^3: 2.53 -> 1.70 ms forward, 2.62 -> 1.72 ms inverse (60 -> 41 instructions per
 // voxel; profiles/ncu_vol3t_r2.txt).
 constexpr int V3T_BW = V3_SW + 4;                         // box width: 76 columns, so that the staged pitch keeps 16-byte row accesses conflict-free
 constexpr int V3T_STAGE = V3_SH * V3T_BW;                 // floats per staged slice (12160 bytes, a multiple of 128)
@@ -496,7 +496,7 @@ template <bool INV, int NCTA, int NBUF> __global__ void __launch_bounds__(V3_THR
     const int xr = tid % V3_SH, xsg = tid / V3_SH;
     // phase i: x lifting of slice i (if there is one) into xb[i & 1], y lifting of slice i - 1 from xb[(i - 1) & 1] into v
     auto phase = [&](int i, T(&v)[8], bool have_y) {
-        issue(i + 2);   // into the buffer slice i - 1 was read from (every thread is past the barrier of phase i - 1)
+        issue(i + NBUF - 1);   // into the buffer slice i - 1 was read from (every thread is past the barrier of phase i - 1)
         if (i < nsl) {
             float *buf = stage + (i % NBUF) * V3T_STAGE;
             mbar_wait(bars + 8 * (i % NBUF), (uint32_t)(i / NBUF) & 1u);
@@ -538,8 +538,8 @@ template <bool INV, int NCTA, int NBUF> __global__ void __launch_bounds__(V3_THR
         __syncthreads();
     };
 
-    issue(0);
-    issue(1);
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; i++) issue(i);
     {
         T none[8];
         phase(0, none, false);
