@@ -20,6 +20,8 @@ libdwt_b200/libdwt_compat.so: $(CSRC)/libdwt_compat.c include/libdwt_compat.h in
 # The reference's UNMODIFIED example programs, compiled from where they lie and linked against the
 # B200 library first and the compiled reference (for everything outside the hot path) second.
 # Build container only (needs $(REF)); the binaries travel to the GPU box in build/ (git-ignored).
+# examples/test (the reference's own round-trip test program) calls the transforms only through the reference's
+# dwt_util_test2_* helpers, so the compat library is forced in front (--no-as-needed) for its entry points to be the ones they reach.
 REF ?= /root/reference
 EXAMPLES = simple simple-int simple-double simple-perf simple-perf-int simple-single-loop simple-perf-single
 examples: libdwt_b200/libdwt_compat.so oracle
@@ -28,6 +30,9 @@ examples: libdwt_b200/libdwt_compat.so oracle
 	  gcc -std=c99 -O2 -D_POSIX_C_SOURCE=199309L -D_GNU_SOURCE -I$(REF)/src $$src -o build/examples/$$e \
 	    -Llibdwt_b200 -ldwt_compat -ldwtb200 -Loracle/_ref -l:libdwt_ref.so -lm -lrt -fopenmp \
 	    -Wl,-rpath,'$$ORIGIN/../../libdwt_b200:$$ORIGIN/../../oracle/_ref' || exit 1; done; \
+	  gcc -std=c99 -O2 -D_POSIX_C_SOURCE=199309L -D_GNU_SOURCE -I$(REF)/src $(REF)/examples/test/test.c -o build/examples/test \
+	    -Llibdwt_b200 -Wl,--no-as-needed -ldwt_compat -ldwtb200 -Wl,--as-needed -Loracle/_ref -l:libdwt_ref.so -lm -lrt -fopenmp \
+	    -Wl,-rpath,'$$ORIGIN/../../libdwt_b200:$$ORIGIN/../../oracle/_ref' || exit 1; \
 	 else echo "examples: $(REF) absent, keeping prebuilt build/examples (if any)"; fi
 
 oracle:

@@ -27,6 +27,18 @@ def test_unmodified_example_runs_on_the_gpu(name, tmp_path):
         assert m and 0 < float(m.group(1)) < 0.01, out[-2000:]   # 1920x1080, one level: well under 10 ms on a B200
 
 
+def test_reference_test_program_runs_on_the_gpu(tmp_path):
+    """examples/test/test.c (the reference's own round-trip test of the path -- float in place and out of place under 16
+    acceleration settings, double, integer 9/7; 256 x 256, prime stride, decompose_one = 1), unmodified, with libdwt_compat.so in
+    front of the compiled reference so that the transforms its dwt_util_test2_* helpers call are the device ones"""
+    exe = os.path.join(ROOT, "build", "examples", "test")
+    assert os.path.exists(exe), f"{exe} missing: run `make examples` in the build container (it travels via gpurun)"
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=180)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-2000:]
+    assert out.count("success") == 34 and "fail" not in out, out[-3000:]
+
+
 def test_measure_perf_harness_writes_plot_data(tmp_path):
     """dwt_util_measure_perf_cdf97_2_s / _inplace_s of libdwt_compat.so (src/libdwt.c:22559, 22646): sizes min_x .. max_x growing
     by 1.13, one 'pixels <TAB> seconds' line per size in each plot file, timed on the device"""
