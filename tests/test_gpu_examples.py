@@ -39,6 +39,22 @@ def test_reference_test_program_runs_on_the_gpu(tmp_path):
     assert out.count("success") == 34 and "fail" not in out, out[-3000:]
 
 
+@pytest.mark.parametrize("name", ["subbands", "subbands-int"])
+def test_subbands_examples_write_the_reference_files(name, tmp_path):
+    """examples/subbands, subbands-int (unmodified): forward transform, the LH subbands erased through dwt_util_subband_*, inverse, both
+    images saved as PGM -- the files must be the ones the same program writes with the compiled reference alone
+    (tests/golden/examples_md5.json, made by tests/golden/make_examples_md5.py)"""
+    import hashlib
+    import json
+    exe = os.path.join(ROOT, "build", "examples", name)
+    assert os.path.exists(exe), f"{exe} missing: run `make examples` in the build container (it travels via gpurun)"
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "examples_md5.json")))[name]
+    got = {f: hashlib.md5(open(tmp_path / f, "rb").read()).hexdigest() for f in want}
+    assert got == want
+
+
 def test_measure_perf_harness_writes_plot_data(tmp_path):
     """dwt_util_measure_perf_cdf97_2_s / _inplace_s of libdwt_compat.so (src/libdwt.c:22559, 22646): sizes min_x .. max_x growing
     by 1.13, one 'pixels <TAB> seconds' line per size in each plot file, timed on the device"""
