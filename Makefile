@@ -30,7 +30,7 @@ examples: libdwt_b200/libdwt_compat.so oracle
 	  gcc -std=c99 -O2 -D_POSIX_C_SOURCE=199309L -D_GNU_SOURCE -I$(REF)/src $$src -o build/examples/$$e \
 	    -Llibdwt_b200 -ldwt_compat -ldwtb200 -Loracle/_ref -l:libdwt_ref.so -lm -lrt -fopenmp \
 	    -Wl,-rpath,'$$ORIGIN/../../libdwt_b200:$$ORIGIN/../../oracle/_ref' || exit 1; done; \
-	  for e in test/test subbands/subbands subbands-int/subbands; do \
+	  for e in test/test subbands/subbands subbands-int/subbands load/simple load-int/simple simple-newapi/simple; do \
 	  gcc -std=c99 -O2 -D_POSIX_C_SOURCE=199309L -D_GNU_SOURCE -I$(REF)/src $(REF)/examples/$$e.c -o build/examples/$${e%%/*} \
 	    -Llibdwt_b200 -Wl,--no-as-needed -ldwt_compat -ldwtb200 -Wl,--as-needed -Loracle/_ref -l:libdwt_ref.so -lm -lrt -fopenmp \
 	    -Wl,-rpath,'$$ORIGIN/../../libdwt_b200:$$ORIGIN/../../oracle/_ref' || exit 1; done; \

@@ -39,10 +39,11 @@ def test_reference_test_program_runs_on_the_gpu(tmp_path):
     assert out.count("success") == 34 and "fail" not in out, out[-3000:]
 
 
-@pytest.mark.parametrize("name", ["subbands", "subbands-int"])
+@pytest.mark.parametrize("name", ["subbands", "subbands-int", "load", "load-int"])
 def test_subbands_examples_write_the_reference_files(name, tmp_path):
     """examples/subbands, subbands-int (unmodified): forward transform, the LH subbands erased through dwt_util_subband_*, inverse, both
-    images saved as PGM -- the files must be the ones the same program writes with the compiled reference alone
+    images saved as PGM; examples/load, load-int (9/7 float / 9/7 integer lifting on the default image, coefficients shown through
+    dwt_util_conv_show) -- the files must be the ones the same program writes with the compiled reference alone
     (tests/golden/examples_md5.json, made by tests/golden/make_examples_md5.py)"""
     import hashlib
     import json
@@ -53,6 +54,16 @@ def test_subbands_examples_write_the_reference_files(name, tmp_path):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "examples_md5.json")))[name]
     got = {f: hashlib.md5(open(tmp_path / f, "rb").read()).hexdigest() for f in want}
     assert got == want
+
+
+def test_newapi_example_runs_on_the_gpu(tmp_path):
+    """examples/simple-newapi (unmodified): the in-place family's forward / inverse pairs, two round trips compared by the reference"""
+    exe = os.path.join(ROOT, "build", "examples", "simple-newapi")
+    assert os.path.exists(exe), f"{exe} missing: run `make examples` in the build container (it travels via gpurun)"
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-2000:]
+    assert out.count("success") == 2 and "images differs" not in out, out[-2000:]
 
 
 def test_measure_perf_harness_writes_plot_data(tmp_path):
