@@ -221,3 +221,17 @@ def test_inplace_oracle_vs_reference_random_inputs(oracle, ref, wavelet):
         ref.inv2_inplace(a, wavelet, Ja, 1, inner=(iy, ix))
         oracle.inv2_inplace(b, wavelet, Jb, 1, inner=(iy, ix))
         assert (bits(a, "s") == bits(b, "s")).all()
+
+
+def test_example_file_digests_are_those_of_the_compiled_reference():
+    """tests/golden/examples_md5.json (what the GPU tests of the reference's subbands / load examples compare with) is what those
+    programs write when linked against the compiled reference alone; re-made here when the reference tree is present"""
+    import importlib.util
+    import shutil
+    ROOT = os.path.dirname(HERE)
+    if not os.path.isdir("/root/reference/examples") or not shutil.which("gcc") or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdwt_ref.so")):
+        pytest.skip("needs /root/reference, gcc and oracle/_ref/libdwt_ref.so")
+    spec = importlib.util.spec_from_file_location("make_examples_md5", os.path.join(ROOT, "tests", "golden", "make_examples_md5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.digests() == json.load(open(os.path.join(ROOT, "tests", "golden", "examples_md5.json")))
